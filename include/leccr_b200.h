@@ -1,0 +1,185 @@
+/*
+ * leccr_b200 -- C ABI of the B200-native dense cross-modal similarity stage of LECCR.
+ *
+ * The reference (LiJiaBei-7/leccr) has no FFI layer: its boundary for this path is four Python
+ * callables.  The Python shims in leccr_b200/ keep those signatures and call
+ * the entry points below through ctypes; any other host can bind the same symbols.  Citations are
+ * relative to /root/reference/LECCR/.
+ *
+ * Conventions
+ *  - plain C, no C++ types, no exceptions; every function returns LECCR_OK (0) or a negative code;
+ *    leccr_strerror() names it, leccr_last_cuda_error() returns the captured CUDA error string.
+ *  - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all memory
+ *    (including workspaces); nothing is retained after the call returns; no device allocation and no
+ *    host synchronisation happen inside (calls are stream-ordered on `stream`, a cudaStream_t).
+ *  - matrices are row-major; `ld` counts elements; 16-bit operands must be 16-byte aligned with
+ *    ld % 8 == 0 (TMA requirement).
+ *  - the library targets sm_100a only and refuses other devices (LECCR_ERR_ARCH). There is no CPU
+ *    path.
+ */
+#ifndef LECCR_B200_H_
+#define LECCR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LECCR_OK 0
+#define LECCR_ERR_ARG (-1)        /* bad shape / null pointer / unsupported option            */
+#define LECCR_ERR_ALIGN (-2)      /* pointer or leading dimension violates the TMA alignment   */
+#define LECCR_ERR_ARCH (-3)       /* current device is not compute capability 10.x             */
+#define LECCR_ERR_CUDA (-4)       /* a CUDA runtime call failed (see leccr_last_cuda_error)    */
+#define LECCR_ERR_WORKSPACE (-5)  /* workspace too small                                       */
+#define LECCR_ERR_DRIVER (-6)     /* cuTensorMapEncodeTiled unavailable or failed              */
+
+/* element types of caller tensors */
+#define LECCR_F32 0
+#define LECCR_F16 1
+#define LECCR_BF16 2
+/* tensor-core operand formats (tcgen05 kind::f16) */
+#define LECCR_FMT_F16 0
+#define LECCR_FMT_BF16 1
+/* operand layouts produced by leccr_prep */
+#define LECCR_LAYOUT_HI 0    /* [hi]            K = D                                   */
+#define LECCR_LAYOUT_X3_ROWS 1 /* [hi | lo | hi]  K = 3D  (rows role of the split product) */
+#define LECCR_LAYOUT_X3_COLS 2 /* [hi | hi | lo]  K = 3D  (cols role)                      */
+/* double_sim fusion modes */
+#define LECCR_FUSE_NORM 1 /* video_Retrieval_caption_double_sim.py:178 */
+#define LECCR_FUSE_RAW 2  /* image_Retrieval_caption.py:244-246        */
+
+#define LECCR_STAT_WORDS 4 /* floats per tensor written by leccr_prep: max|hi row|, max|residual row|, max|x|, bad flag */
+#define LECCR_TOPK_KP 16   /* candidates kept per (row, column chunk) by the streaming top-k */
+#define LECCR_RANK_CAP 10  /* ranks >= this are reported as lower bounds (Recall@1/5/10 only needs < 10) */
+
+typedef void* leccr_stream_t; /* cudaStream_t */
+
+const char* leccr_strerror(int code);
+const char* leccr_last_cuda_error(void);
+int leccr_abi_version(void);
+/* LECCR_OK when the current CUDA device can run the kernels (cc 10.x). */
+int leccr_check_device(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Operand preparation.  Replaces nothing in the reference by itself; it is the prologue of every
+ * similarity GEMM (the reference multiplies fp32 tensors directly, models/xvlm.py:273,
+ * image_Retrieval_caption.py:151).  `normalize` fuses F.normalize(x, dim=-1)
+ * (models/xvlm.py:245-256).  src_dtype F32 casts; F16/BF16 sources are used in place by the GEMMs
+ * and only need leccr_stats16.
+ *   dst16     : [n][ld_dst] 16-bit, ld_dst >= D (layout HI) or 3D (X3), ld_dst % 8 == 0
+ *   rn_hi/lo  : [n] row norms of the 16-bit operand / of its rounding residual (may be NULL)
+ *   stats     : LECCR_STAT_WORDS floats, zero-initialised by the caller, max-combined
+ * ------------------------------------------------------------------------------------------ */
+int leccr_prep(const float* src, int64_t n, int D, int64_t ld_src, int normalize, int fmt, int layout,
+               void* dst16, int64_t ld_dst, float* rn_hi, float* rn_lo, float* stats,
+               leccr_stream_t stream);
+int leccr_stats16(const void* src16, int fmt, int64_t n, int D, int64_t ld_src, float* rn_hi,
+                  float* rn_lo, float* stats, leccr_stream_t stream);
+/* [n][D] -> [D][ld_dst] (ld_dst >= n, columns n..ld_dst zero-filled). */
+int leccr_transpose16(const void* src16, int64_t n, int D, int64_t ld_src, void* dst16, int64_t ld_dst,
+                      leccr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * leccr_sim_f32: S = scale * rows16 . cols16^T   (fp32 out, materialised)
+ * Replaces: score_matrix_i2t = image_embeds @ text_embeds.t()   image_Retrieval_caption.py:151
+ *           c_sim = caption_embeds.reshape(-1,d) @ text_embeds.T video_Retrieval_caption_double_sim.py:174
+ * With X3 operands (K = 3D) the product is fp32-accurate; with HI operands it carries the 16-bit
+ * rounding of the inputs.  k_splits > 1 accumulates split-K partials with red.add into S, which the
+ * caller must have zeroed; scale_dev (optional device scalar) is multiplied into scale.
+ * ------------------------------------------------------------------------------------------ */
+int leccr_sim_f32(const void* rows16, int64_t ld_rows, const void* cols16, int64_t ld_cols, int64_t n_rows,
+                  int64_t n_cols, int K, int fmt, float* S, int64_t ld_S, float scale,
+                  const float* scale_dev, int k_splits, leccr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * leccr_sim_topk: fused similarity + streaming per-row top-k (+ exact Recall ranks) for one or two
+ * orientations in ONE tensor-core launch; the n_rows x n_cols matrix never reaches HBM.
+ * Replaces: image_Retrieval_caption.py:151-163 (matmul + D2H) and :261-295 (np.argsort ranking).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct leccr_topk_problem {
+  /* 16-bit tensor-core operands (from leccr_prep, or the caller's own fp16/bf16 tensors) */
+  const void* rows16;
+  const void* cols16;
+  int64_t ld_rows16, ld_cols16;
+  int64_t n_rows, n_cols;
+  /* outputs */
+  float* topk_val; /* [n_rows][k] approximate scores, descending (ties: lower column first) */
+  int32_t* topk_idx;
+  /* exact Recall support (optional: gt_off == NULL disables everything below) */
+  const int32_t* gt_off; /* CSR offsets [n_rows + 1] of each row's ground-truth columns */
+  const int32_t* gt_ids;
+  const void* rows_x; /* original (un-rounded) operands used for exact re-scoring */
+  const void* cols_x;
+  int64_t ld_rows_x, ld_cols_x;
+  int x_dtype;              /* LECCR_F32 / F16 / BF16 */
+  const float* rn_hi;       /* [n_rows] from leccr_prep / leccr_stats16 of the rows operand */
+  const float* rn_lo;
+  const float* col_stats;   /* LECCR_STAT_WORDS of the cols operand */
+  int32_t* rank;            /* [n_rows]: min over GT of #{j : s_j > s_gt}; exact when < LECCR_RANK_CAP */
+  int32_t* recall_counts;   /* [3] += #{rank < 1, 5, 10}  (zeroed by the caller) */
+  float* gt_score;          /* [nnz] exact fp32 score of each ground-truth pair (may be NULL) */
+} leccr_topk_problem;
+
+size_t leccr_sim_topk_workspace(const leccr_topk_problem* probs, int n_prob, int tiles_per_chunk);
+int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, int k,
+                   int tiles_per_chunk /* 0 = auto */, void* workspace, size_t workspace_bytes,
+                   leccr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * leccr_infonce_fwd / leccr_infonce_bwd: symmetric InfoNCE over all-gathered embeddings.
+ * Replaces: XVLMBase.get_contrastive_loss  models/xvlm.py:260-292 (forward: :273-292; backward:
+ * autograd of the same lines followed by AllGather.backward :62-67, which keeps the local rows).
+ *   a16, b16     : [n][D] 16-bit all-gathered image / text operands (leccr_prep, layout HI)
+ *   idx          : [n] int64 labels (idx_all, :285) or NULL for the arange labels of :277
+ *   temp         : device scalar self.temp
+ *   out          : [4] loss, dloss/dtemp, loss_i2t, loss_t2i
+ *   lse2 / rcnt  : [2][n] per-row log2-domain log-sum-exp and 1/|positives| (saved for backward)
+ * Backward (local rows [row_begin, row_begin + row_count) only):
+ *   aT16, bT16   : [D][ldT] transposed operands (leccr_transpose16)
+ *   grad_out     : device scalar dL/dloss
+ *   dA, dB       : [row_count][D] fp32 (overwritten)
+ * ------------------------------------------------------------------------------------------ */
+size_t leccr_infonce_fwd_workspace(int64_t n, int tiles_per_chunk);
+int leccr_infonce_fwd(const void* a16, const void* b16, int64_t ld16, const int64_t* idx, int64_t n, int D,
+                      int fmt, const float* temp, float* out, float* lse2, float* rcnt,
+                      int tiles_per_chunk, void* workspace, size_t workspace_bytes,
+                      leccr_stream_t stream);
+size_t leccr_infonce_bwd_workspace(int64_t n, int64_t row_count);
+int leccr_infonce_bwd(const void* a16, const void* b16, int64_t ld16, const void* aT16, const void* bT16,
+                      int64_t ldT, const int64_t* idx, int64_t n, int D, int fmt, const float* temp,
+                      const float* lse2, const float* rcnt, int64_t row_begin, int64_t row_count,
+                      const float* grad_out, float* dA, float* dB, void* workspace,
+                      size_t workspace_bytes, leccr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Ranking of a materialised fp32 score matrix S [R][C] (the drop-in itm_eval).
+ * Replaces: itm_eval  image_Retrieval_caption.py:261-295 == video_..._double_sim.py:194-230.
+ *   rank_rows: rank[r] = min_{g in gt(r)} #{c : S[r][c] > S[r][g]}          (i2t, :265-278)
+ *   rank_cols: rank[c] = min_{g in gt(c)} #{r : S[r][c] > S[g][c]}          (t2i, :288-290, read
+ *              from the same matrix: the reference's t2i matrix is the transpose view, :152)
+ *   recall_counts: counts[0..2] += #{rank < 1, 5, 10}                        (:281-283, :293-295)
+ * scratch for rank_cols: int32[nnz], zeroed by the caller.
+ * ------------------------------------------------------------------------------------------ */
+int leccr_rank_rows(const float* S, int64_t ld, int64_t R, int64_t C, const int32_t* gt_off,
+                    const int32_t* gt_ids, int32_t* rank, leccr_stream_t stream);
+int leccr_rank_cols(const float* S, int64_t ld, int64_t R, int64_t C, const int32_t* gt_off,
+                    const int32_t* gt_ids, int32_t* scratch_nnz, int32_t* rank, leccr_stream_t stream);
+int leccr_recall_counts(const int32_t* rank, int64_t n, int32_t* counts, leccr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * leccr_double_sim_fuse: in place S <- w1 * f(S) + w2 * f(max_n Cn)
+ * Replaces: norm_score + fusion  video_Retrieval_caption_double_sim.py:87-91,175-178 (mode NORM,
+ * f = (x - max x) / (max x - min x) over the whole matrix) and image_Retrieval_caption.py:239-246
+ * (mode RAW, f = identity).
+ *   S  : [numel] fp32 text-video similarity;  Cn : [n_cap][numel] caption similarities
+ *   Cmax : [numel] scratch receiving max_n Cn;  mm : 4 x uint32 scratch
+ * ------------------------------------------------------------------------------------------ */
+int leccr_double_sim_fuse(float* S, const float* Cn, int n_cap, int64_t numel, float* Cmax, uint32_t* mm,
+                          float w1, float w2, int mode, leccr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LECCR_B200_H_ */

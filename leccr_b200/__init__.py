@@ -1,0 +1,13 @@
+"""leccr_b200 -- B200-native dense cross-modal similarity stage of LECCR.
+
+Drop-in replacements for the reference's hot path:
+  AllGather / allgather, get_contrastive_loss      models/xvlm.py:50-70, 260-292
+  evaluation_coarse (image / video double_sim)     image_Retrieval_caption.py:83-163,
+                                                   video_Retrieval_caption_double_sim.py:94-190
+  itm_eval                                         image_Retrieval_caption.py:261-317
+plus the additive fused_eval (similarity + top-k + Recall without materialising N x M).
+
+The arithmetic lives in libleccr_b200.so (hand-written sm_100a CUDA behind a C ABI, see
+include/leccr_b200.h).  There is no CPU path: calls raise if the library or a B200 is missing.
+"""
+__version__ = "0.1.0"

@@ -1,0 +1,111 @@
+"""ctypes binding of include/leccr_b200.h.
+
+There is no CPU path: if the library is missing or a call fails, this module raises.
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+i64 = ctypes.c_int64
+c_int = ctypes.c_int
+c_float = ctypes.c_float
+vp = ctypes.c_void_p
+sz = ctypes.c_size_t
+
+OK = 0
+F32, F16, BF16 = 0, 1, 2
+FMT_F16, FMT_BF16 = 0, 1
+LAYOUT_HI, LAYOUT_X3_ROWS, LAYOUT_X3_COLS = 0, 1, 2
+FUSE_NORM, FUSE_RAW = 1, 2
+STAT_WORDS = 4
+TOPK_KP = 16
+RANK_CAP = 10
+
+
+class TopkProblem(ctypes.Structure):
+    """Mirror of struct leccr_topk_problem."""
+
+    _fields_ = [
+        ("rows16", vp), ("cols16", vp),
+        ("ld_rows16", i64), ("ld_cols16", i64),
+        ("n_rows", i64), ("n_cols", i64),
+        ("topk_val", vp), ("topk_idx", vp),
+        ("gt_off", vp), ("gt_ids", vp),
+        ("rows_x", vp), ("cols_x", vp),
+        ("ld_rows_x", i64), ("ld_cols_x", i64),
+        ("x_dtype", c_int),
+        ("rn_hi", vp), ("rn_lo", vp), ("col_stats", vp),
+        ("rank", vp), ("recall_counts", vp), ("gt_score", vp),
+    ]
+
+
+_SIGNATURES = {
+    "leccr_strerror": (ctypes.c_char_p, [c_int]),
+    "leccr_last_cuda_error": (ctypes.c_char_p, []),
+    "leccr_abi_version": (c_int, []),
+    "leccr_check_device": (c_int, []),
+    "leccr_prep": (c_int, [vp, i64, c_int, i64, c_int, c_int, c_int, vp, i64, vp, vp, vp, vp]),
+    "leccr_stats16": (c_int, [vp, c_int, i64, c_int, i64, vp, vp, vp, vp]),
+    "leccr_transpose16": (c_int, [vp, i64, c_int, i64, vp, i64, vp]),
+    "leccr_sim_f32": (c_int, [vp, i64, vp, i64, i64, i64, c_int, c_int, vp, i64, c_float, vp, c_int, vp]),
+    "leccr_sim_topk_workspace": (sz, [ctypes.POINTER(TopkProblem), c_int, c_int]),
+    "leccr_sim_topk": (c_int, [ctypes.POINTER(TopkProblem), c_int, c_int, c_int, c_int, c_int, vp, sz, vp]),
+    "leccr_infonce_fwd_workspace": (sz, [i64, c_int]),
+    "leccr_infonce_fwd": (c_int, [vp, vp, i64, vp, i64, c_int, c_int, vp, vp, vp, vp, c_int, vp, sz, vp]),
+    "leccr_infonce_bwd_workspace": (sz, [i64, i64]),
+    "leccr_infonce_bwd": (c_int, [vp, vp, i64, vp, vp, i64, vp, i64, c_int, c_int, vp, vp, vp, i64, i64,
+                                  vp, vp, vp, vp, sz, vp]),
+    "leccr_rank_rows": (c_int, [vp, i64, i64, i64, vp, vp, vp, vp]),
+    "leccr_rank_cols": (c_int, [vp, i64, i64, i64, vp, vp, vp, vp, vp]),
+    "leccr_recall_counts": (c_int, [vp, i64, vp, vp]),
+    "leccr_double_sim_fuse": (c_int, [vp, vp, c_int, i64, vp, vp, c_float, c_float, c_int, vp]),
+}
+
+EXPORTS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+class LeccrError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """Load (building first if the .so is absent) and type the C ABI. Raises if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        _build.build()
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the export is missing: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != OK:
+        lib = load()
+        msg = lib.leccr_strerror(rc).decode()
+        detail = lib.leccr_last_cuda_error().decode()
+        raise LeccrError(f"{what} failed: {msg}" + (f" [{detail}]" if detail else ""))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream

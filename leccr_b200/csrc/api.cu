@@ -1,0 +1,628 @@
+// Host side of the C ABI declared in include/leccr_b200.h: argument checking, TMA descriptor
+// construction, work decomposition and kernel launches.  No device allocation, no synchronisation.
+#include "../../include/leccr_b200.h"
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+#include "epilogues.cuh"
+#include "gemm_sm100.cuh"
+#include "kernels.cuh"
+
+using namespace leccr;
+
+namespace {
+
+thread_local char g_cuda_err[256] = "";
+
+int cuda_fail(cudaError_t e, const char* where) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, cudaGetErrorString(e));
+  return LECCR_ERR_CUDA;
+}
+#define CUDA_TRY(expr)                                   \
+  do {                                                   \
+    cudaError_t _e = (expr);                             \
+    if (_e != cudaSuccess) return cuda_fail(_e, #expr);  \
+  } while (0)
+#define LAUNCH_CHECK(name)                                   \
+  do {                                                       \
+    cudaError_t _e = cudaGetLastError();                     \
+    if (_e != cudaSuccess) return cuda_fail(_e, name);       \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+      sms = v;
+    else
+      return 148;
+  }
+  return sms;
+}
+
+// 2-D K-major 16-bit operand [n][K] (ld elements) with a {BK, box_rows} box and 128-byte swizzle.
+int make_tmap(CUtensorMap* tm, const void* base, int64_t n, int64_t K, int64_t ld, int fmt, int box_rows) {
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld & 7) != 0) return LECCR_ERR_ALIGN;
+  if (n <= 0 || K <= 0 || ld < K) return LECCR_ERR_ARG;
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return LECCR_ERR_DRIVER;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(n)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, fmt == LECCR_FMT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                   2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return LECCR_ERR_DRIVER;
+  }
+  return LECCR_OK;
+}
+
+struct Plan {
+  int row_block_begin, row_blocks, col_tiles, n_chunks, tiles_per_chunk;
+};
+
+Plan plan_problem(int64_t n_cols, int64_t row_begin, int64_t row_count, int tiles_per_chunk) {
+  Plan p;
+  p.row_block_begin = static_cast<int>(row_begin / BM);
+  p.row_blocks = static_cast<int>((row_begin + row_count + BM - 1) / BM) - p.row_block_begin;
+  p.col_tiles = static_cast<int>((n_cols + BN - 1) / BN);
+  int tpc = std::max(1, std::min(tiles_per_chunk, p.col_tiles));
+  p.n_chunks = (p.col_tiles + tpc - 1) / tpc;
+  p.tiles_per_chunk = tpc;
+  return p;
+}
+
+// Column-chunk length shared by the problems of one launch: aim at ~4 work items per SM so the
+// static round-robin schedule balances, but keep chunks long enough to amortise per-item state.
+int auto_tiles_per_chunk(int64_t total_tiles, int min_tpc) {
+  int64_t t = total_tiles / (4LL * num_sms());
+  return static_cast<int>(std::max<int64_t>(min_tpc, std::min<int64_t>(t, 64)));
+}
+
+int fill_problem(SimProblem& P, const void* rows16, int64_t ld_rows, const void* cols16, int64_t ld_cols,
+                 int64_t n_rows, int64_t n_cols, int K, int fmt, const Plan& pl, int item_base) {
+  int rc = make_tmap(&P.tm_rows, rows16, n_rows, K, ld_rows, fmt, BM);
+  if (rc != LECCR_OK) return rc;
+  rc = make_tmap(&P.tm_cols, cols16, n_cols, K, ld_cols, fmt, BN);
+  if (rc != LECCR_OK) return rc;
+  P.n_rows = static_cast<int>(n_rows);
+  P.n_cols = static_cast<int>(n_cols);
+  P.row_block_begin = pl.row_block_begin;
+  P.row_blocks = pl.row_blocks;
+  P.col_tiles = pl.col_tiles;
+  P.n_chunks = pl.n_chunks;
+  P.tiles_per_chunk = pl.tiles_per_chunk;
+  P.item_base = item_base;
+  return LECCR_OK;
+}
+
+constexpr int kStages = 4;
+
+template <class Epi>
+int launch_gemm(const SimLaunch& L, const typename Epi::Params& EP, cudaStream_t stream) {
+  auto kern = sim_gemm_kernel<Epi, kStages>;
+  constexpr size_t smem = sim_gemm_smem_bytes<Epi, kStages>();
+  static_assert(smem <= 232448, "exceeds the 227 KB shared memory limit of sm_100");
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(sim_gemm_kernel)");
+  if (L.n_items <= 0) return LECCR_OK;
+  const int grid = std::min(L.n_items, num_sms());
+  kern<<<grid, kGemmThreads, smem, stream>>>(L, EP);
+  LAUNCH_CHECK("sim_gemm_kernel");
+  return LECCR_OK;
+}
+
+bool bad_fmt(int fmt) { return fmt != LECCR_FMT_F16 && fmt != LECCR_FMT_BF16; }
+
+}  // namespace
+
+extern "C" {
+
+const char* leccr_strerror(int code) {
+  switch (code) {
+    case LECCR_OK: return "ok";
+    case LECCR_ERR_ARG: return "invalid argument (shape, null pointer or unsupported option)";
+    case LECCR_ERR_ALIGN: return "operand violates TMA alignment (16-byte base, ld % 8 == 0)";
+    case LECCR_ERR_ARCH: return "device is not sm_100 (B200); leccr_b200 has no other backend";
+    case LECCR_ERR_CUDA: return "CUDA runtime error (see leccr_last_cuda_error)";
+    case LECCR_ERR_WORKSPACE: return "workspace too small";
+    case LECCR_ERR_DRIVER: return "cuTensorMapEncodeTiled unavailable or failed";
+    default: return "unknown leccr error code";
+  }
+}
+const char* leccr_last_cuda_error(void) { return g_cuda_err; }
+int leccr_abi_version(void) { return 1; }
+
+int leccr_check_device(void) {
+  int dev = 0, major = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  return major == 10 ? LECCR_OK : LECCR_ERR_ARCH;
+}
+
+// ------------------------------------------------------------------------------------ prep
+int leccr_prep(const float* src, int64_t n, int D, int64_t ld_src, int normalize, int fmt, int layout,
+               void* dst16, int64_t ld_dst, float* rn_hi, float* rn_lo, float* stats,
+               leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (src == nullptr || dst16 == nullptr || n <= 0 || D <= 0 || bad_fmt(fmt) || layout < 0 || layout > 2)
+    return LECCR_ERR_ARG;
+  const int64_t K = layout == 0 ? D : 3LL * D;
+  if (ld_src < D || ld_dst < K) return LECCR_ERR_ARG;
+  const int wpb = 8;
+  const unsigned grid = static_cast<unsigned>((n + wpb - 1) / wpb);
+  uint16_t* dst = static_cast<uint16_t*>(dst16);
+  if (fmt == LECCR_FMT_F16)
+    prep_rows_kernel<0><<<grid, wpb * 32, 0, stream>>>(src, ld_src, (int)n, D, normalize, layout, dst, ld_dst,
+                                                      rn_hi, rn_lo, stats);
+  else
+    prep_rows_kernel<1><<<grid, wpb * 32, 0, stream>>>(src, ld_src, (int)n, D, normalize, layout, dst, ld_dst,
+                                                      rn_hi, rn_lo, stats);
+  LAUNCH_CHECK("prep_rows_kernel");
+  return LECCR_OK;
+}
+
+int leccr_stats16(const void* src16, int fmt, int64_t n, int D, int64_t ld_src, float* rn_hi, float* rn_lo,
+                  float* stats, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (src16 == nullptr || n <= 0 || D <= 0 || bad_fmt(fmt) || ld_src < D) return LECCR_ERR_ARG;
+  const int wpb = 8;
+  const unsigned grid = static_cast<unsigned>((n + wpb - 1) / wpb);
+  const uint16_t* s = static_cast<const uint16_t*>(src16);
+  if (fmt == LECCR_FMT_F16)
+    stats_rows16_kernel<0><<<grid, wpb * 32, 0, stream>>>(s, ld_src, (int)n, D, rn_hi, rn_lo, stats);
+  else
+    stats_rows16_kernel<1><<<grid, wpb * 32, 0, stream>>>(s, ld_src, (int)n, D, rn_hi, rn_lo, stats);
+  LAUNCH_CHECK("stats_rows16_kernel");
+  return LECCR_OK;
+}
+
+int leccr_transpose16(const void* src16, int64_t n, int D, int64_t ld_src, void* dst16, int64_t ld_dst,
+                      leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (src16 == nullptr || dst16 == nullptr || n <= 0 || D <= 0 || ld_src < D || ld_dst < n) return LECCR_ERR_ARG;
+  dim3 grid(static_cast<unsigned>((ld_dst + 31) / 32), static_cast<unsigned>((D + 31) / 32));
+  dim3 block(32, 8);
+  transpose16_kernel<<<grid, block, 0, stream>>>(static_cast<const uint16_t*>(src16), ld_src, (int)n, D,
+                                                 static_cast<uint16_t*>(dst16), ld_dst);
+  LAUNCH_CHECK("transpose16_kernel");
+  return LECCR_OK;
+}
+
+// ------------------------------------------------------------------------------------ sim_f32
+int leccr_sim_f32(const void* rows16, int64_t ld_rows, const void* cols16, int64_t ld_cols, int64_t n_rows,
+                  int64_t n_cols, int K, int fmt, float* S, int64_t ld_S, float scale, const float* scale_dev,
+                  int k_splits, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (rows16 == nullptr || cols16 == nullptr || S == nullptr || n_rows <= 0 || n_cols <= 0 || K <= 0 ||
+      bad_fmt(fmt) || ld_S < n_cols)
+    return LECCR_ERR_ARG;
+  int rc = leccr_check_device();
+  if (rc != LECCR_OK) return rc;
+  SimLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.n_prob = 1;
+  L.fmt = fmt;
+  L.k_chunks = (K + BK - 1) / BK;
+  Plan pl;
+  if (k_splits > 1) {
+    L.kc_per_split = (L.k_chunks + k_splits - 1) / k_splits;
+    L.k_splits = (L.k_chunks + L.kc_per_split - 1) / L.kc_per_split;
+    pl = plan_problem(n_cols, 0, n_rows, 1 << 30);
+    pl.n_chunks = L.k_splits;
+    if (L.k_splits == 1) L.k_splits = 0;
+  } else {
+    const int64_t tiles = ((n_rows + BM - 1) / BM) * ((n_cols + BN - 1) / BN);
+    pl = plan_problem(n_cols, 0, n_rows, auto_tiles_per_chunk(tiles, 1));
+  }
+  rc = fill_problem(L.prob[0], rows16, ld_rows, cols16, ld_cols, n_rows, n_cols, K, fmt, pl, 0);
+  if (rc != LECCR_OK) return rc;
+  L.n_items = pl.row_blocks * pl.n_chunks;
+  EpiStore::Params EP;
+  memset(&EP, 0, sizeof(EP));
+  EP.out[0] = S;
+  EP.ld[0] = ld_S;
+  EP.scale[0] = scale;
+  EP.scale_ptr[0] = scale_dev;
+  EP.accumulate = L.k_splits > 1 ? 1 : 0;
+  return launch_gemm<EpiStore>(L, EP, stream);
+}
+
+// ------------------------------------------------------------------------------------ sim_topk
+// Work decomposition of a top-k launch.  The per-row candidate merge holds n_chunks * KP <= 256
+// candidates, so a row's columns are split into at most kMaxTopkChunks chunks.  Each problem gets a
+// share of ~4 work items per SM proportional to its tile count.
+constexpr int kMaxTopkChunks = 256 / LECCR_TOPK_KP;
+
+static int topk_plan(const leccr_topk_problem* probs, int n_prob, int tiles_per_chunk, Plan* plans) {
+  int64_t total_tiles = 0;
+  for (int p = 0; p < n_prob; ++p)
+    total_tiles += ((probs[p].n_rows + BM - 1) / BM) * ((probs[p].n_cols + BN - 1) / BN);
+  for (int p = 0; p < n_prob; ++p) {
+    const int64_t row_blocks = (probs[p].n_rows + BM - 1) / BM;
+    const int64_t col_tiles = (probs[p].n_cols + BN - 1) / BN;
+    int tpc = tiles_per_chunk;
+    if (tpc <= 0) {
+      const double share = 4.0 * num_sms() * static_cast<double>(row_blocks * col_tiles) / static_cast<double>(total_tiles);
+      int64_t chunks = static_cast<int64_t>(share / static_cast<double>(row_blocks) + 0.5);
+      chunks = std::max<int64_t>(1, std::min<int64_t>(chunks, std::min<int64_t>(kMaxTopkChunks, col_tiles)));
+      tpc = static_cast<int>((col_tiles + chunks - 1) / chunks);
+    }
+    plans[p] = plan_problem(probs[p].n_cols, 0, probs[p].n_rows, tpc);
+    if (plans[p].n_chunks > kMaxTopkChunks) return LECCR_ERR_ARG;
+  }
+  return LECCR_OK;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+size_t leccr_sim_topk_workspace(const leccr_topk_problem* probs, int n_prob, int tiles_per_chunk) {
+  if (probs == nullptr || n_prob < 1 || n_prob > 2) return 0;
+  Plan plans[2];
+  if (topk_plan(probs, n_prob, tiles_per_chunk, plans) != LECCR_OK) return 0;
+  size_t bytes = 0;
+  for (int p = 0; p < n_prob; ++p) {
+    const size_t cand = static_cast<size_t>(probs[p].n_rows) * plans[p].n_chunks * LECCR_TOPK_KP;
+    bytes += align256(cand * 4) * 2 + align256(static_cast<size_t>(probs[p].n_rows) * 4);
+  }
+  return bytes;
+}
+
+int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, int k, int tiles_per_chunk,
+                   void* workspace, size_t workspace_bytes, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (probs == nullptr || n_prob < 1 || n_prob > 2 || D <= 0 || bad_fmt(fmt) || k < 1 || k > LECCR_TOPK_KP)
+    return LECCR_ERR_ARG;
+  for (int p = 0; p < n_prob; ++p) {
+    const leccr_topk_problem& q = probs[p];
+    if (q.rows16 == nullptr || q.cols16 == nullptr || q.n_rows <= 0 || q.n_cols <= 0 || q.topk_val == nullptr ||
+        q.topk_idx == nullptr)
+      return LECCR_ERR_ARG;
+    if (q.gt_off != nullptr &&
+        (q.gt_ids == nullptr || q.rows_x == nullptr || q.cols_x == nullptr || q.rn_hi == nullptr ||
+         q.rn_lo == nullptr || q.col_stats == nullptr || q.rank == nullptr || q.x_dtype < 0 || q.x_dtype > 2))
+      return LECCR_ERR_ARG;
+  }
+  int rc = leccr_check_device();
+  if (rc != LECCR_OK) return rc;
+  Plan plans[2];
+  rc = topk_plan(probs, n_prob, tiles_per_chunk, plans);
+  if (rc != LECCR_OK) return rc;  // tiles_per_chunk too small: more than 16 column chunks per row
+  if (workspace == nullptr || workspace_bytes < leccr_sim_topk_workspace(probs, n_prob, tiles_per_chunk))
+    return LECCR_ERR_WORKSPACE;
+  SimLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.n_prob = n_prob;
+  L.fmt = fmt;
+  L.k_chunks = (D + BK - 1) / BK;
+  EpiTopK<LECCR_TOPK_KP>::Params EP;
+  memset(&EP, 0, sizeof(EP));
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  float* cand_val[2];
+  int* cand_idx[2];
+  int* flag[2];
+  int item_base = 0;
+  for (int p = 0; p < n_prob; ++p) {
+    const leccr_topk_problem& q = probs[p];
+    rc = fill_problem(L.prob[p], q.rows16, q.ld_rows16, q.cols16, q.ld_cols16, q.n_rows, q.n_cols, D, fmt,
+                      plans[p], item_base);
+    if (rc != LECCR_OK) return rc;
+    item_base += plans[p].row_blocks * plans[p].n_chunks;
+    const size_t cand = static_cast<size_t>(q.n_rows) * plans[p].n_chunks * LECCR_TOPK_KP;
+    cand_val[p] = reinterpret_cast<float*>(ws);
+    ws += align256(cand * 4);
+    cand_idx[p] = reinterpret_cast<int*>(ws);
+    ws += align256(cand * 4);
+    flag[p] = reinterpret_cast<int*>(ws);
+    ws += align256(static_cast<size_t>(q.n_rows) * 4);
+    EP.out_val[p] = cand_val[p];
+    EP.out_idx[p] = cand_idx[p];
+    EP.n_chunks[p] = plans[p].n_chunks;
+  }
+  L.n_items = item_base;
+  rc = launch_gemm<EpiTopK<LECCR_TOPK_KP>>(L, EP, stream);
+  if (rc != LECCR_OK) return rc;
+
+  for (int p = 0; p < n_prob; ++p) {
+    const leccr_topk_problem& q = probs[p];
+    TopkFinalizeParams F;
+    memset(&F, 0, sizeof(F));
+    F.cand_val = cand_val[p];
+    F.cand_idx = cand_idx[p];
+    F.n_rows = static_cast<int>(q.n_rows);
+    F.n_cols = static_cast<int>(q.n_cols);
+    F.n_chunks = plans[p].n_chunks;
+    F.KP = LECCR_TOPK_KP;
+    F.k = k;
+    F.topk_val = q.topk_val;
+    F.topk_idx = q.topk_idx;
+    F.gt_off = q.gt_off;
+    F.gt_ids = q.gt_ids;
+    F.rows_x = q.rows_x;
+    F.cols_x = q.cols_x;
+    F.ld_rows = q.ld_rows_x;
+    F.ld_cols = q.ld_cols_x;
+    F.D = D;
+    F.x_dtype = q.x_dtype;
+    F.rn_hi = q.rn_hi;
+    F.rn_lo = q.rn_lo;
+    F.col_stats = q.col_stats;
+    // fp32 accumulation of K products in the tensor core: 2 ulp per product, conservatively
+    F.acc_slack = 2.0f * 1.1920929e-7f * static_cast<float>(D);
+    F.rank = q.rank;
+    F.flag = flag[p];
+    F.gt_score = q.gt_score;
+    const int wpb = 8;
+    const unsigned grid = static_cast<unsigned>((q.n_rows + wpb - 1) / wpb);
+    topk_finalize_kernel<<<grid, wpb * 32, 0, stream>>>(F);
+    LAUNCH_CHECK("topk_finalize_kernel");
+    if (q.gt_off != nullptr) {
+      const unsigned g2 = static_cast<unsigned>(std::min<int64_t>(q.n_rows, 4LL * num_sms()));
+      exact_rank_rows_kernel<<<g2, 256, 0, stream>>>(F);
+      LAUNCH_CHECK("exact_rank_rows_kernel");
+      if (q.recall_counts != nullptr) {
+        const unsigned g3 = static_cast<unsigned>(std::min<int64_t>((q.n_rows + 255) / 256, 2LL * num_sms()));
+        recall_count_kernel<<<g3, 256, 0, stream>>>(q.rank, static_cast<int>(q.n_rows), q.recall_counts);
+        LAUNCH_CHECK("recall_count_kernel");
+      }
+    }
+  }
+  return LECCR_OK;
+}
+
+// ------------------------------------------------------------------------------------ InfoNCE
+static Plan infonce_plan(int64_t n, int tiles_per_chunk) {
+  const int64_t tiles = 2 * ((n + BM - 1) / BM) * ((n + BN - 1) / BN);
+  const int tpc = tiles_per_chunk > 0 ? tiles_per_chunk : auto_tiles_per_chunk(tiles, 4);
+  return plan_problem(n, 0, n, tpc);
+}
+
+size_t leccr_infonce_fwd_workspace(int64_t n, int tiles_per_chunk) {
+  if (n <= 0) return 0;
+  const Plan pl = infonce_plan(n, tiles_per_chunk);
+  return 2 * align256(static_cast<size_t>(n) * pl.n_chunks * 5 * 4);
+}
+
+int leccr_infonce_fwd(const void* a16, const void* b16, int64_t ld16, const int64_t* idx, int64_t n, int D,
+                      int fmt, const float* temp, float* out, float* lse2, float* rcnt, int tiles_per_chunk,
+                      void* workspace, size_t workspace_bytes, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (a16 == nullptr || b16 == nullptr || temp == nullptr || out == nullptr || lse2 == nullptr || rcnt == nullptr ||
+      n <= 0 || D <= 0 || bad_fmt(fmt))
+    return LECCR_ERR_ARG;
+  int rc = leccr_check_device();
+  if (rc != LECCR_OK) return rc;
+  if (workspace == nullptr || workspace_bytes < leccr_infonce_fwd_workspace(n, tiles_per_chunk))
+    return LECCR_ERR_WORKSPACE;
+  const Plan pl = infonce_plan(n, tiles_per_chunk);
+  SimLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.n_prob = 2;
+  L.fmt = fmt;
+  L.k_chunks = (D + BK - 1) / BK;
+  const int items = pl.row_blocks * pl.n_chunks;
+  rc = fill_problem(L.prob[0], a16, ld16, b16, ld16, n, n, D, fmt, pl, 0);
+  if (rc != LECCR_OK) return rc;
+  rc = fill_problem(L.prob[1], b16, ld16, a16, ld16, n, n, D, fmt, pl, items);
+  if (rc != LECCR_OK) return rc;
+  L.n_items = 2 * items;
+  const size_t part_bytes = align256(static_cast<size_t>(n) * pl.n_chunks * 5 * 4);
+  float* part0 = static_cast<float*>(workspace);
+  float* part1 = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + part_bytes);
+  EpiLse::Params EP;
+  memset(&EP, 0, sizeof(EP));
+  EP.temp = temp;
+  for (int p = 0; p < 2; ++p) {
+    EP.idx_rows[p] = reinterpret_cast<const long long*>(idx);
+    EP.idx_cols[p] = reinterpret_cast<const long long*>(idx);
+    EP.n_chunks[p] = pl.n_chunks;
+  }
+  EP.part[0] = part0;
+  EP.part[1] = part1;
+  rc = launch_gemm<EpiLse>(L, EP, stream);
+  if (rc != LECCR_OK) return rc;
+  FinalizeLseParams F;
+  memset(&F, 0, sizeof(F));
+  F.part[0] = part0;
+  F.part[1] = part1;
+  F.n[0] = F.n[1] = static_cast<int>(n);
+  F.nch[0] = F.nch[1] = pl.n_chunks;
+  F.lse2[0] = lse2;
+  F.lse2[1] = lse2 + n;
+  F.rcnt[0] = rcnt;
+  F.rcnt[1] = rcnt + n;
+  F.temp = temp;
+  F.out = out;
+  infonce_finalize_kernel<<<1, 1024, 0, stream>>>(F);
+  LAUNCH_CHECK("infonce_finalize_kernel");
+  return LECCR_OK;
+}
+
+static int64_t round_up8(int64_t x) { return (x + 7) & ~static_cast<int64_t>(7); }
+
+size_t leccr_infonce_bwd_workspace(int64_t n, int64_t row_count) {
+  if (n <= 0 || row_count <= 0) return 0;
+  return 2 * align256(static_cast<size_t>(row_count) * round_up8(n) * 2);
+}
+
+int leccr_infonce_bwd(const void* a16, const void* b16, int64_t ld16, const void* aT16, const void* bT16,
+                      int64_t ldT, const int64_t* idx, int64_t n, int D, int fmt, const float* temp,
+                      const float* lse2, const float* rcnt, int64_t row_begin, int64_t row_count,
+                      const float* grad_out, float* dA, float* dB, void* workspace, size_t workspace_bytes,
+                      leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (a16 == nullptr || b16 == nullptr || aT16 == nullptr || bT16 == nullptr || temp == nullptr ||
+      lse2 == nullptr || rcnt == nullptr || dA == nullptr || dB == nullptr || n <= 0 || D <= 0 || bad_fmt(fmt) ||
+      row_begin < 0 || row_count <= 0 || row_begin + row_count > n)
+    return LECCR_ERR_ARG;
+  int rc = leccr_check_device();
+  if (rc != LECCR_OK) return rc;
+  if (workspace == nullptr || workspace_bytes < leccr_infonce_bwd_workspace(n, row_count))
+    return LECCR_ERR_WORKSPACE;
+  const int64_t ldS = round_up8(n);
+  const size_t strip_bytes = align256(static_cast<size_t>(row_count) * ldS * 2);
+  void* strip0 = workspace;
+  void* strip1 = static_cast<uint8_t*>(workspace) + strip_bytes;
+
+  // 1. recompute the logits of the local row strips on the tensor cores, emit G' (16-bit)
+  {
+    const int64_t tiles = 2 * ((row_count + BM - 1) / BM + 1) * ((n + BN - 1) / BN);
+    const Plan pl = plan_problem(n, row_begin, row_count, auto_tiles_per_chunk(tiles, 2));
+    SimLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.n_prob = 2;
+    L.fmt = fmt;
+    L.k_chunks = (D + BK - 1) / BK;
+    const int items = pl.row_blocks * pl.n_chunks;
+    rc = fill_problem(L.prob[0], a16, ld16, b16, ld16, n, n, D, fmt, pl, 0);
+    if (rc != LECCR_OK) return rc;
+    rc = fill_problem(L.prob[1], b16, ld16, a16, ld16, n, n, D, fmt, pl, items);
+    if (rc != LECCR_OK) return rc;
+    L.n_items = 2 * items;
+    EpiGrad::Params EP;
+    memset(&EP, 0, sizeof(EP));
+    EP.temp = temp;
+    EP.fmt = fmt;
+    for (int p = 0; p < 2; ++p) {
+      EP.idx_rows[p] = reinterpret_cast<const long long*>(idx);
+      EP.idx_cols[p] = reinterpret_cast<const long long*>(idx);
+      EP.lse_rows[p] = lse2 + p * n;
+      EP.lse_cols[p] = lse2 + (1 - p) * n;
+      EP.rcnt_rows[p] = rcnt + p * n;
+      EP.rcnt_cols[p] = rcnt + (1 - p) * n;
+      EP.ld[p] = ldS;
+      EP.row0[p] = static_cast<int>(row_begin);
+      EP.nrow[p] = static_cast<int>(row_count);
+    }
+    EP.strip[0] = strip0;
+    EP.strip[1] = strip1;
+    rc = launch_gemm<EpiGrad>(L, EP, stream);
+    if (rc != LECCR_OK) return rc;
+  }
+  // 2. dA_loc = G'[loc,:] B / (2 n temp),  dB_loc = G'[:,loc]^T A / (2 n temp): split-K products
+  CUDA_TRY(cudaMemsetAsync(dA, 0, static_cast<size_t>(row_count) * D * 4, stream));
+  CUDA_TRY(cudaMemsetAsync(dB, 0, static_cast<size_t>(row_count) * D * 4, stream));
+  {
+    SimLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.n_prob = 2;
+    L.fmt = fmt;
+    L.k_chunks = static_cast<int>((n + BK - 1) / BK);
+    Plan pl = plan_problem(D, 0, row_count, 1 << 30);
+    int splits = std::max(1, std::min(L.k_chunks, (2 * num_sms()) / std::max(1, 2 * pl.row_blocks)));
+    L.kc_per_split = (L.k_chunks + splits - 1) / splits;
+    L.k_splits = (L.k_chunks + L.kc_per_split - 1) / L.kc_per_split;
+    pl.n_chunks = L.k_splits;
+    const int items = pl.row_blocks * pl.n_chunks;
+    if (L.k_splits == 1) {
+      L.k_splits = 2;  // keep the split-K decode (all column tiles per item) with a single split
+      L.kc_per_split = L.k_chunks;
+    }
+    rc = fill_problem(L.prob[0], strip0, ldS, bT16, ldT, row_count, D, static_cast<int>(n), fmt, pl, 0);
+    if (rc != LECCR_OK) return rc;
+    rc = fill_problem(L.prob[1], strip1, ldS, aT16, ldT, row_count, D, static_cast<int>(n), fmt, pl, items);
+    if (rc != LECCR_OK) return rc;
+    L.n_items = 2 * items;
+    EpiStore::Params EP;
+    memset(&EP, 0, sizeof(EP));
+    EP.out[0] = dA;
+    EP.out[1] = dB;
+    EP.ld[0] = EP.ld[1] = D;
+    EP.scale[0] = EP.scale[1] = 1.0f / (2.0f * static_cast<float>(n));
+    EP.scale_ptr[0] = EP.scale_ptr[1] = grad_out;
+    EP.div_ptr[0] = EP.div_ptr[1] = temp;
+    EP.accumulate = 1;
+    rc = launch_gemm<EpiStore>(L, EP, stream);
+    if (rc != LECCR_OK) return rc;
+  }
+  return LECCR_OK;
+}
+
+// ------------------------------------------------------------------------------------ ranking
+int leccr_rank_rows(const float* S, int64_t ld, int64_t R, int64_t C, const int32_t* gt_off,
+                    const int32_t* gt_ids, int32_t* rank, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (S == nullptr || gt_off == nullptr || gt_ids == nullptr || rank == nullptr || R <= 0 || C <= 0 || ld < C)
+    return LECCR_ERR_ARG;
+  rank_rows_kernel<<<static_cast<unsigned>(R), 256, 0, stream>>>(S, ld, (int)R, (int)C, gt_off, gt_ids, rank);
+  LAUNCH_CHECK("rank_rows_kernel");
+  return LECCR_OK;
+}
+
+int leccr_rank_cols(const float* S, int64_t ld, int64_t R, int64_t C, const int32_t* gt_off,
+                    const int32_t* gt_ids, int32_t* scratch_nnz, int32_t* rank, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (S == nullptr || gt_off == nullptr || gt_ids == nullptr || rank == nullptr || scratch_nnz == nullptr ||
+      R <= 0 || C <= 0 || ld < C)
+    return LECCR_ERR_ARG;
+  const unsigned gx = static_cast<unsigned>((C + 127) / 128);
+  // enough row slabs to fill the machine
+  int slabs = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((R + 63) / 64, (4LL * num_sms() + gx - 1) / gx)));
+  const int rows_per_block = static_cast<int>((R + slabs - 1) / slabs);
+  slabs = static_cast<int>((R + rows_per_block - 1) / rows_per_block);
+  rank_cols_count_kernel<<<dim3(gx, slabs), 128, 0, stream>>>(S, ld, (int)R, (int)C, gt_off, gt_ids,
+                                                             rows_per_block, scratch_nnz);
+  LAUNCH_CHECK("rank_cols_count_kernel");
+  rank_cols_min_kernel<<<static_cast<unsigned>((C + 255) / 256), 256, 0, stream>>>((int)C, (int)R, gt_off,
+                                                                                    scratch_nnz, rank);
+  LAUNCH_CHECK("rank_cols_min_kernel");
+  return LECCR_OK;
+}
+
+int leccr_recall_counts(const int32_t* rank, int64_t n, int32_t* counts, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (rank == nullptr || counts == nullptr || n <= 0) return LECCR_ERR_ARG;
+  const unsigned g = static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 2LL * num_sms()));
+  recall_count_kernel<<<g, 256, 0, stream>>>(rank, (int)n, counts);
+  LAUNCH_CHECK("recall_count_kernel");
+  return LECCR_OK;
+}
+
+// ------------------------------------------------------------------------------------ double_sim
+int leccr_double_sim_fuse(float* S, const float* Cn, int n_cap, int64_t numel, float* Cmax, uint32_t* mm,
+                          float w1, float w2, int mode, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (S == nullptr || Cn == nullptr || Cmax == nullptr || mm == nullptr || n_cap < 1 || numel <= 0 ||
+      (mode != LECCR_FUSE_NORM && mode != LECCR_FUSE_RAW))
+    return LECCR_ERR_ARG;
+  const unsigned g = static_cast<unsigned>(std::min<int64_t>((numel + 255) / 256, 8LL * num_sms()));
+  mm_init_kernel<<<1, 32, 0, stream>>>(mm);
+  LAUNCH_CHECK("mm_init_kernel");
+  capmax_minmax_kernel<<<g, 256, 0, stream>>>(S, Cn, Cmax, n_cap, numel, mm);
+  LAUNCH_CHECK("capmax_minmax_kernel");
+  fuse_scores_kernel<<<g, 256, 0, stream>>>(S, Cmax, numel, mm, w1, w2, mode);
+  LAUNCH_CHECK("fuse_scores_kernel");
+  return LECCR_OK;
+}
+
+}  // extern "C"

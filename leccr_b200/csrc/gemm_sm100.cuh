@@ -1,0 +1,233 @@
+// Similarity mainloop for sm_100a: S = R * C^T over 16-bit (fp16 / bf16) K-major operands.
+//
+//   R ("rows")  : the entities being ranked / whose softmax rows are formed  [n_rows, K]
+//   C ("cols")  : the gallery / the other modality                           [n_cols, K]
+//
+// One persistent CTA per SM.  Warp 0 feeds shared memory with TMA (128-byte swizzle), warp 1
+// issues tcgen05.mma (128 x 256 x 16, fp32 accumulators in TMEM, two 256-column buffers so the
+// epilogue of tile t overlaps the MMAs of tile t+1), warps 2..5 are the epilogue: thread <-> one
+// row of the tile (TMEM lane), so every per-row reduction the reference performs
+// (top-k, log-sum-exp, min/max, label sums) is thread-local and the N x M matrix never has to
+// exist in HBM.  The epilogue is a policy class (see epilogues.cuh).
+//
+// A work item is (problem, row block of 128, column chunk); a launch can carry two problems
+// (the two orientations i2t / t2i of the same pair of embedding sets).
+#pragma once
+#include "ptx.cuh"
+
+namespace leccr {
+
+constexpr int BM = 128;       // rows per tile   (TMEM lanes)
+constexpr int BN = 256;       // columns per tile (TMEM columns per accumulator buffer)
+constexpr int BK = 64;        // K elements per pipeline stage = one 128-byte swizzle atom
+constexpr int UMMA_K = 16;    // K per tcgen05.mma for 16-bit operands
+constexpr int kGemmThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kAStageBytes = BM * BK * 2;
+constexpr int kBStageBytes = BN * BK * 2;
+constexpr int kStageBytes = kAStageBytes + kBStageBytes;
+constexpr int kTmemCols = 512;
+
+struct SimProblem {
+  CUtensorMap tm_rows;  // box {BK, BM}
+  CUtensorMap tm_cols;  // box {BK, BN}
+  int n_rows, n_cols;
+  int row_block_begin;  // first row block this launch covers (local strips in the backward)
+  int row_blocks;       // number of row blocks this launch covers
+  int col_tiles;        // ceil(n_cols / BN)
+  int n_chunks;         // column chunks per row block
+  int tiles_per_chunk;
+  int item_base;        // first work-item id of this problem
+};
+
+struct SimLaunch {
+  SimProblem prob[2];
+  int n_prob;
+  int n_items;
+  int k_chunks;      // ceil(K / BK)
+  int fmt;           // 0 fp16, 1 bf16
+  int k_splits;      // > 1: a work item's "chunk" is a K range (split-K), all column tiles
+  int kc_per_split;  // K chunks per split
+};
+
+// What an epilogue thread knows about the work item it is in.
+struct ItemCtx {
+  int p;        // problem index
+  int rb;       // row block (absolute)
+  int cc;       // column chunk
+  int row;      // absolute row owned by this thread
+  int n_rows, n_cols;
+  int et;       // epilogue thread id 0..127 (== row within tile)
+  int warp_q;   // TMEM lane quadrant of this warp
+  int lane;
+  uint8_t* smem;  // epilogue-private shared memory (Epi::kSmemBytes)
+};
+
+__device__ __forceinline__ void decode_item(const SimLaunch& L, int item, int& p, int& rb, int& ct0,
+                                            int& ct1, int& cc, int& kc0, int& kc1) {
+  p = (L.n_prob > 1 && item >= L.prob[1].item_base) ? 1 : 0;
+  const SimProblem& P = L.prob[p];
+  int local = item - P.item_base;
+  int r = local / P.n_chunks;
+  cc = local - r * P.n_chunks;
+  rb = P.row_block_begin + r;
+  if (L.k_splits > 1) {
+    ct0 = 0;
+    ct1 = P.col_tiles;
+    kc0 = cc * L.kc_per_split;
+    kc1 = min(L.k_chunks, kc0 + L.kc_per_split);
+  } else {
+    ct0 = cc * P.tiles_per_chunk;
+    ct1 = min(P.col_tiles, ct0 + P.tiles_per_chunk);
+    kc0 = 0;
+    kc1 = L.k_chunks;
+  }
+}
+
+template <class Epi, int kStages>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typename Epi::Params EP) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128-byte swizzle atoms need 1024-byte alignment.
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* stage_base = smem;
+  uint8_t* epi_smem = smem + kStages * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Epi::kSmemBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tfull_bar = bars + 2 * kStages;
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int p = 0; p < L.n_prob; ++p) {
+      tma_prefetch_desc(&L.prob[p].tm_rows);
+      tma_prefetch_desc(&L.prob[p].tm_cols);
+    }
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], kEpiThreads);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < L.n_items; item += gridDim.x) {
+        int p, rb, ct0, ct1, cc, kc0, kc1;
+        decode_item(L, item, p, rb, ct0, ct1, cc, kc0, kc1);
+        const CUtensorMap* tmr = &L.prob[p].tm_rows;
+        const CUtensorMap* tmc = &L.prob[p].tm_cols;
+        for (int ct = ct0; ct < ct1; ++ct) {
+          for (int kc = kc0; kc < kc1; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + stage);
+            uint8_t* sa = stage_base + stage * kStageBytes;
+            uint8_t* sb = sa + kAStageBytes;
+            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+            tma_load_2d(sa, tmr, &full_bar[stage], kc * BK, rb * BM);
+            tma_load_2d(sb, tmc, &full_bar[stage], kc * BK, ct * BN);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(L.fmt, BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t tile_n = 0;
+      for (int item = blockIdx.x; item < L.n_items; item += gridDim.x) {
+        int p, rb, ct0, ct1, cc, kc0, kc1;
+        decode_item(L, item, p, rb, ct0, ct1, cc, kc0, kc1);
+        for (int ct = ct0; ct < ct1; ++ct, ++tile_n) {
+          const uint32_t buf = tile_n & 1u;
+          const uint32_t use = tile_n >> 1;
+          mbar_wait(&tempty_bar[buf], (use & 1u) ^ 1u, 200 + buf);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * BN;
+          for (int kc = kc0; kc < kc1; ++kc) {
+            mbar_wait(&full_bar[stage], phase, 300 + stage);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
+            const uint64_t adesc = make_sw128_kmajor_desc(sa);
+            const uint64_t bdesc = make_sw128_kmajor_desc(sa + kAStageBytes);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // +32 bytes per K step inside the swizzle atom == +2 in the (addr >> 4) field
+              umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kc > kc0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // stage reusable once these MMAs have read it
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          umma_commit(&tfull_bar[buf]);  // accumulator complete
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps)
+    ItemCtx c;
+    c.warp_q = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    c.lane = lane;
+    c.et = c.warp_q * 32 + lane;
+    c.smem = epi_smem;
+    uint32_t tile_n = 0;
+    typename Epi::State st;
+    for (int item = blockIdx.x; item < L.n_items; item += gridDim.x) {
+      int ct0, ct1, kc0, kc1;
+      decode_item(L, item, c.p, c.rb, ct0, ct1, c.cc, kc0, kc1);
+      c.n_rows = L.prob[c.p].n_rows;
+      c.n_cols = L.prob[c.p].n_cols;
+      c.row = c.rb * BM + c.et;
+      Epi::begin(st, EP, c);
+      for (int ct = ct0; ct < ct1; ++ct, ++tile_n) {
+        const uint32_t buf = tile_n & 1u;
+        const uint32_t use = tile_n >> 1;
+        mbar_wait(&tfull_bar[buf], use & 1u, 400 + buf);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + buf * BN + (static_cast<uint32_t>(c.warp_q * 32) << 16);
+        Epi::tile(st, EP, c, taddr, ct * BN);
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[buf]);
+      }
+      Epi::end(st, EP, c);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+template <class Epi, int kStages>
+constexpr size_t sim_gemm_smem_bytes() {
+  return 1024 + static_cast<size_t>(kStages) * kStageBytes + Epi::kSmemBytes + (2 * kStages + 4) * 8 + 16;
+}
+
+}  // namespace leccr

@@ -1,0 +1,599 @@
+// CUDA-core kernels around the tensor-core similarity pass: operand preparation
+// (cast / L2-normalise / split), finalisation of the streamed reductions, and the
+// HBM-bound ranking of an already materialised score matrix.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math_constants.h>
+#include "ptx.cuh"
+
+namespace leccr {
+
+// -------------------------------------------------------------------------------- 16-bit helpers
+template <int FMT>
+__device__ __forceinline__ uint16_t f32_to_16(float x) {
+  if (FMT == 0) {
+    __half h = __float2half_rn(x);
+    return *reinterpret_cast<uint16_t*>(&h);
+  } else {
+    __nv_bfloat16 h = __float2bfloat16_rn(x);
+    return *reinterpret_cast<uint16_t*>(&h);
+  }
+}
+template <int FMT>
+__device__ __forceinline__ float f16_to_32(uint16_t u) {
+  if (FMT == 0) {
+    return __half2float(*reinterpret_cast<__half*>(&u));
+  } else {
+    return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&u));
+  }
+}
+
+// Order-preserving float <-> uint mapping so atomicMax/atomicMin work for any sign.
+__device__ __forceinline__ unsigned f32_ordered(float f) {
+  unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_f32(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// Per-tensor statistics written by the prep kernels (all atomically max-combined; zero-init).
+//   [0] max_i ||hi_i||   [1] max_i ||x_i - hi_i||   [2] max |x|   [3] non-finite / fp16-overflow flag
+constexpr int kStatWords = 4;
+
+// --------------------------------------------------------------------------------
+// prep_rows: fp32 rows -> 16-bit tensor-core operand.  One warp per row.
+//   normalize : F.normalize(x, dim=-1) (eps 1e-12) fused in front of the cast
+//               (models/xvlm.py:245-256 is the step right before the path).
+//   layout 0  : [hi]                 K = D
+//   layout 1  : [hi | lo | hi]       K = 3D, "rows" role of the split product
+//   layout 2  : [hi | hi | lo]       K = 3D, "cols" role:  rows.cols^T = hi.hi + lo.hi + hi.lo
+// lo = cast(x - hi): the product then carries ~fp32 accuracy through 16-bit tensor cores.
+// --------------------------------------------------------------------------------
+template <int FMT>
+__global__ void prep_rows_kernel(const float* __restrict__ src, long long ld_src, int n, int D,
+                                 int normalize, int layout, uint16_t* __restrict__ dst,
+                                 long long ld_dst, float* __restrict__ rn_hi,
+                                 float* __restrict__ rn_lo, float* __restrict__ stats) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float* x = src + static_cast<long long>(row) * ld_src;
+  float inv = 1.f;
+  if (normalize) {
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float t = x[d];
+      ss = fmaf(t, t, ss);
+    }
+    ss = warp_sum(ss);
+    inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  }
+  uint16_t* o = dst + static_cast<long long>(row) * ld_dst;
+  float nh = 0.f, nl = 0.f, amax = 0.f;
+  bool bad = false;
+  for (int d = lane; d < D; d += 32) {
+    const float t = normalize ? x[d] * inv : x[d];
+    const uint16_t h = f32_to_16<FMT>(t);
+    const float hf = f16_to_32<FMT>(h);
+    const float r = t - hf;
+    bad |= !isfinite(hf);
+    amax = fmaxf(amax, fabsf(t));
+    nh = fmaf(hf, hf, nh);
+    if (layout == 0) {
+      o[d] = h;
+      nl = fmaf(r, r, nl);
+    } else {
+      const uint16_t l = f32_to_16<FMT>(r);
+      const float rr = r - f16_to_32<FMT>(l);
+      nl = fmaf(rr, rr, nl);
+      o[d] = h;
+      if (layout == 1) {
+        o[D + d] = l;
+        o[2 * D + d] = h;
+      } else {
+        o[D + d] = h;
+        o[2 * D + d] = l;
+      }
+    }
+  }
+  nh = warp_sum(nh);
+  nl = warp_sum(nl);
+  amax = warp_max(amax);
+  const unsigned anybad = __ballot_sync(0xffffffffu, bad);
+  if (lane == 0) {
+    const float a = sqrtf(nh), b = sqrtf(nl);
+    if (rn_hi) rn_hi[row] = a;
+    if (rn_lo) rn_lo[row] = b;
+    if (stats) {
+      atomicMax(reinterpret_cast<unsigned*>(stats) + 0, __float_as_uint(a));
+      atomicMax(reinterpret_cast<unsigned*>(stats) + 1, __float_as_uint(b));
+      atomicMax(reinterpret_cast<unsigned*>(stats) + 2, __float_as_uint(amax));
+      if (anybad) atomicMax(reinterpret_cast<unsigned*>(stats) + 3, __float_as_uint(1.f));
+    }
+  }
+}
+
+// Row norms / maxima of an operand that is already 16-bit (e.g. a bf16-stored gallery).
+template <int FMT>
+__global__ void stats_rows16_kernel(const uint16_t* __restrict__ src, long long ld_src, int n, int D,
+                                    float* __restrict__ rn_hi, float* __restrict__ rn_lo,
+                                    float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const uint16_t* x = src + static_cast<long long>(row) * ld_src;
+  float nh = 0.f, amax = 0.f;
+  bool bad = false;
+  for (int d = lane; d < D; d += 32) {
+    const float t = f16_to_32<FMT>(x[d]);
+    bad |= !isfinite(t);
+    amax = fmaxf(amax, fabsf(t));
+    nh = fmaf(t, t, nh);
+  }
+  nh = warp_sum(nh);
+  amax = warp_max(amax);
+  const unsigned anybad = __ballot_sync(0xffffffffu, bad);
+  if (lane == 0) {
+    const float a = sqrtf(nh);
+    if (rn_hi) rn_hi[row] = a;
+    if (rn_lo) rn_lo[row] = 0.f;
+    if (stats) {
+      atomicMax(reinterpret_cast<unsigned*>(stats) + 0, __float_as_uint(a));
+      atomicMax(reinterpret_cast<unsigned*>(stats) + 2, __float_as_uint(amax));
+      if (anybad) atomicMax(reinterpret_cast<unsigned*>(stats) + 3, __float_as_uint(1.f));
+    }
+  }
+}
+
+// 16-bit transpose [n][D] -> [D][ldT] (operand of the gradient products: K runs over rows).
+__global__ void transpose16_kernel(const uint16_t* __restrict__ src, long long ld_src, int n, int D,
+                                   uint16_t* __restrict__ dst, long long ld_dst) {
+  __shared__ uint16_t t[32][34];
+  const int r0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, d = d0 + threadIdx.x;
+    t[i][threadIdx.x] = (r < n && d < D) ? src[static_cast<long long>(r) * ld_src + d] : 0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int d = d0 + i, r = r0 + threadIdx.x;
+    if (d < D && r < ld_dst) dst[static_cast<long long>(d) * ld_dst + r] = (r < n) ? t[threadIdx.x][i] : 0;
+  }
+}
+
+// --------------------------------------------------------------------------------
+// infonce_finalize: merge the per-chunk partials of EpiLse, emit per-row lse (log2 units) and
+// 1/cnt for the backward, and the scalars
+//   loss  = (loss_i2t + loss_t2i) / 2                         models/xvlm.py:292
+//   dtemp = d loss / d temp = -(1/temp) * 1/2 * sum_p mean_r (E_r[z] - pz_r / cnt_r)
+// One block.  Orientation p has n[p] rows and nch[p] chunks.
+// --------------------------------------------------------------------------------
+struct FinalizeLseParams {
+  const float* part[2];
+  int n[2];
+  int nch[2];
+  float* lse2[2];
+  float* rcnt[2];
+  const float* temp;
+  float* out;  // [0] loss, [1] dtemp, [2] loss_p0, [3] loss_p1
+};
+
+__global__ void infonce_finalize_kernel(const FinalizeLseParams P) {
+  __shared__ double red[4][32];
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};  // loss_p0, loss_p1, dt_p0, dt_p1
+  for (int p = 0; p < 2; ++p) {
+    for (int r = threadIdx.x; r < P.n[p]; r += blockDim.x) {
+      const float* q = P.part[p] + static_cast<long long>(r) * P.nch[p] * 5;
+      float m = -CUDART_INF_F;
+      for (int c = 0; c < P.nch[p]; ++c) m = fmaxf(m, q[5 * c]);
+      float l = 0.f, w = 0.f, pz = 0.f, cnt = 0.f;
+      for (int c = 0; c < P.nch[p]; ++c) {
+        const float s = exp2f(q[5 * c] - m);
+        l = fmaf(q[5 * c + 1], s, l);
+        w = fmaf(q[5 * c + 2], s, w);
+        pz += q[5 * c + 3];
+        cnt += q[5 * c + 4];
+      }
+      const float lse2 = m + log2f(l);
+      const float rc = cnt > 0.f ? 1.f / cnt : 0.f;
+      P.lse2[p][r] = lse2;
+      P.rcnt[p][r] = rc;
+      // natural-log units: multiply log2-domain quantities by ln 2
+      acc[p] += 0.6931471805599453 * (static_cast<double>(lse2) - static_cast<double>(pz) * rc);
+      acc[2 + p] += 0.6931471805599453 * (static_cast<double>(w) / l - static_cast<double>(pz) * rc);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = 0; k < 4; ++k) {
+    double v = acc[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[k][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot[4] = {0, 0, 0, 0};
+    const int nw = blockDim.x >> 5;
+    for (int k = 0; k < 4; ++k)
+      for (int w = 0; w < nw; ++w) tot[k] += red[k][w];
+    const double l0 = P.n[0] > 0 ? tot[0] / P.n[0] : 0.0;
+    const double l1 = P.n[1] > 0 ? tot[1] / P.n[1] : 0.0;
+    const double d0 = P.n[0] > 0 ? tot[2] / P.n[0] : 0.0;
+    const double d1 = P.n[1] > 0 ? tot[3] / P.n[1] : 0.0;
+    const double temp = static_cast<double>(*P.temp);
+    P.out[0] = static_cast<float>(0.5 * (l0 + l1));
+    P.out[1] = static_cast<float>(-0.5 * (d0 + d1) / temp);
+    P.out[2] = static_cast<float>(l0);
+    P.out[3] = static_cast<float>(l1);
+  }
+}
+
+// --------------------------------------------------------------------------------
+// topk_finalize: one warp per query row.
+//   1. merge the per-chunk candidate lists of EpiTopK into the row's best KP (approximate scores)
+//   2. emit the top-k (score, column)
+//   3. optional exact Recall support: for every ground-truth column g of the row compute the exact
+//      score t_g (fp32 dot of the original inputs) and decide rank_g = #{j : t_j > t_g} from the
+//      candidate list, re-scoring only candidates whose approximate score is within the rigorous
+//      error bound eps of t_g.  rank = min_g rank_g, as image_Retrieval_caption.py:274-278.
+//      If the list cannot decide (GT score inside the band of the list's last entry while fewer
+//      than kRankCap definitely-greater items are known) the row is flagged for exact_rank_rows.
+// --------------------------------------------------------------------------------
+constexpr int kRankCap = 10;  // Recall@1/5/10 only ever asks whether rank < 10
+
+struct TopkFinalizeParams {
+  const float* cand_val;  // [n_rows][n_chunks][KP]
+  const int* cand_idx;
+  int n_rows, n_cols, n_chunks, KP, k;
+  float* topk_val;  // [n_rows][k]
+  int* topk_idx;
+  // exact recall (all optional; gt_off == nullptr disables)
+  const int* gt_off;  // CSR [n_rows + 1]
+  const int* gt_ids;
+  const void* rows_x;  // original row operand  [n_rows][D]  (fp32 or 16-bit)
+  const void* cols_x;  // original col operand  [n_cols][D]
+  long long ld_rows, ld_cols;
+  int D;
+  int x_dtype;  // 0 fp32, 1 fp16, 2 bf16
+  const float* rn_hi;       // per-row norms of the 16-bit row operand and of its rounding residual
+  const float* rn_lo;
+  const float* col_stats;   // kStatWords of the column operand
+  float acc_slack;          // fp32 accumulation slack coefficient (times ||hi_r|| ||hi_c||max)
+  int* rank;                // [n_rows]  exact when < kRankCap (else a lower bound >= kRankCap)
+  int* flag;                // [n_rows]  1: undecided, needs exact_rank_rows
+  float* gt_score;          // [nnz] exact score of every ground-truth pair (optional)
+};
+
+__device__ __forceinline__ float load_x(const void* base, long long off, int dtype) {
+  if (dtype == 0) return __ldg(reinterpret_cast<const float*>(base) + off);
+  const uint16_t u = __ldg(reinterpret_cast<const uint16_t*>(base) + off);
+  return dtype == 1 ? f16_to_32<0>(u) : f16_to_32<1>(u);
+}
+
+// exact fp32 dot of row r of rows_x with row c of cols_x, cooperatively by one warp
+__device__ __forceinline__ float warp_dot(const void* rows_x, long long ld_rows, int r, const void* cols_x,
+                                          long long ld_cols, int c, int D, int dtype, int lane) {
+  float s = 0.f;
+  for (int d = lane; d < D; d += 32)
+    s = fmaf(load_x(rows_x, static_cast<long long>(r) * ld_rows + d, dtype),
+             load_x(cols_x, static_cast<long long>(c) * ld_cols + d, dtype), s);
+  return warp_sum(s);
+}
+
+__global__ void topk_finalize_kernel(const TopkFinalizeParams P) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= P.n_rows) return;
+  const int total = P.n_chunks * P.KP;
+  const float* cv = P.cand_val + static_cast<long long>(row) * total;
+  const int* ci = P.cand_idx + static_cast<long long>(row) * total;
+  // Each lane keeps up to 8 candidates (total <= 256) in registers; selection by repeated warp argmax.
+  float v[8];
+  int id[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const int e = lane + 32 * t;
+    v[t] = (e < total) ? cv[e] : -CUDART_INF_F;
+    id[t] = (e < total) ? ci[e] : -1;
+    if (id[t] < 0) v[t] = -CUDART_INF_F;
+  }
+  // merged list kept by lane l < KP: (mv, mi)
+  float mv = -CUDART_INF_F;
+  int mi = -1;
+  const int KP = P.KP;
+  for (int s = 0; s < KP; ++s) {
+    float bv = -CUDART_INF_F;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      if (id[t] >= 0 && (v[t] > bv || (v[t] == bv && id[t] < bi))) {
+        bv = v[t];
+        bi = id[t];
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) {
+        bv = ov;
+        bi = oi;
+      }
+    }
+    if (bi == 0x7fffffff) break;  // exhausted (warp-uniform)
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      if (id[t] == bi) id[t] = -1;  // a column appears once per row
+    if (lane == s) {
+      mv = bv;
+      mi = bi;
+    }
+  }
+  if (lane < P.k) {
+    P.topk_val[static_cast<long long>(row) * P.k + lane] = mv;
+    P.topk_idx[static_cast<long long>(row) * P.k + lane] = mi;
+  }
+  if (P.gt_off == nullptr) return;
+
+  // ---- exact rank of the ground truth
+  const int m_cnt = __popc(__ballot_sync(0xffffffffu, mi >= 0));  // list length
+  const bool exhaustive = m_cnt < KP || P.n_cols <= KP;           // every column is in the list
+  const float v_last = __shfl_sync(0xffffffffu, mv, KP - 1);
+  const float ch = P.col_stats[0], cl = P.col_stats[1];
+  const float rh = P.rn_hi[row], rl = P.rn_lo[row];
+  const float eps = rl * ch + rh * cl + rl * cl + P.acc_slack * rh * ch;
+  int best = 0x7fffffff;
+  int undecided = 0;
+  const int g0 = P.gt_off[row], g1 = P.gt_off[row + 1];
+  for (int gi = g0; gi < g1; ++gi) {
+    const int g = P.gt_ids[gi];
+    const float tg = warp_dot(P.rows_x, P.ld_rows, row, P.cols_x, P.ld_cols, g, P.D, P.x_dtype, lane);
+    if (P.gt_score != nullptr && lane == 0) P.gt_score[gi] = tg;
+    const bool in_list = (lane < KP) && (mi >= 0) && (mi != g);
+    const bool def_gt = in_list && (mv > tg + eps);
+    const bool amb = in_list && !def_gt && (mv >= tg - eps);
+    int cnt = __popc(__ballot_sync(0xffffffffu, def_gt));
+    unsigned amb_mask = __ballot_sync(0xffffffffu, amb);
+    const bool gt_inside = exhaustive || (tg - eps > v_last);  // nothing outside the list can beat it
+    if (!gt_inside && cnt < kRankCap) {
+      undecided = 1;  // cannot bound the competitors outside the list
+      continue;
+    }
+    if (gt_inside) {
+      while (amb_mask) {  // re-score the ambiguous candidates exactly
+        const int src = __ffs(amb_mask) - 1;
+        amb_mask &= amb_mask - 1;
+        const int j = __shfl_sync(0xffffffffu, mi, src);
+        const float tj = warp_dot(P.rows_x, P.ld_rows, row, P.cols_x, P.ld_cols, j, P.D, P.x_dtype, lane);
+        cnt += (tj > tg) ? 1 : 0;
+      }
+    }
+    best = min(best, cnt);
+  }
+  if (lane == 0) {
+    // a decided GT with rank < cap makes undecided siblings irrelevant only if it already has rank 0
+    const int f = (undecided && best > 0) ? 1 : 0;
+    P.rank[row] = (best == 0x7fffffff) ? kRankCap : best;
+    P.flag[row] = f;
+  }
+}
+
+// Exact fallback for flagged rows: rank = min_g #{j : t_j > t_g} with every score an fp32 dot.
+// One block per flagged row (grid-stride over rows; unflagged rows cost one load).
+__global__ void exact_rank_rows_kernel(const TopkFinalizeParams P) {
+  __shared__ float s_tg[16];
+  __shared__ int s_cnt[16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int row = blockIdx.x; row < P.n_rows; row += gridDim.x) {
+    if (P.flag[row] == 0) continue;  // block-uniform
+    const int g0 = P.gt_off[row];
+    const int ng = min(P.gt_off[row + 1] - g0, 16);
+    __syncthreads();
+    if (warp == 0) {
+      for (int gi = 0; gi < ng; ++gi) {
+        const float tg = warp_dot(P.rows_x, P.ld_rows, row, P.cols_x, P.ld_cols, P.gt_ids[g0 + gi],
+                                  P.D, P.x_dtype, lane);
+        if (lane == 0) {
+          s_tg[gi] = tg;
+          s_cnt[gi] = 0;
+        }
+      }
+    }
+    __syncthreads();
+    int cnt[16];
+#pragma unroll
+    for (int gi = 0; gi < 16; ++gi) cnt[gi] = 0;
+    for (int j = warp; j < P.n_cols; j += nw) {
+      const float tj = warp_dot(P.rows_x, P.ld_rows, row, P.cols_x, P.ld_cols, j, P.D, P.x_dtype, lane);
+#pragma unroll
+      for (int gi = 0; gi < 16; ++gi)
+        if (gi < ng && tj > s_tg[gi]) ++cnt[gi];
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int gi = 0; gi < 16; ++gi)
+        if (gi < ng && cnt[gi]) atomicAdd(&s_cnt[gi], cnt[gi]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int best = 0x7fffffff;
+      for (int gi = 0; gi < ng; ++gi) best = min(best, s_cnt[gi]);
+      P.rank[row] = best == 0x7fffffff ? kRankCap : best;
+      P.flag[row] = 0;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------
+// rank_rows / rank_cols: ranking of an already materialised fp32 score matrix (the drop-in
+// itm_eval, image_Retrieval_caption.py:261-295).  HBM-bound: one pass over the matrix.
+//   rank_rows: for row r, rank = min_{g in gt(r)} #{c : S[r][c] > S[r][g]}         (i2t)
+//   rank_cols: for column c, rank = min_{g in gt(c)} #{r : S[r][c] > S[g][c]}      (t2i read
+//              from the same row-major matrix; the reference's t2i matrix is its transpose view)
+// --------------------------------------------------------------------------------
+constexpr int kMaxGt = 16;
+
+__global__ void rank_rows_kernel(const float* __restrict__ S, long long ld, int R, int C,
+                                 const int* __restrict__ gt_off, const int* __restrict__ gt_ids,
+                                 int* __restrict__ rank) {
+  __shared__ float s_t[kMaxGt];
+  __shared__ int s_c[kMaxGt];
+  const int row = blockIdx.x;
+  if (row >= R) return;
+  const float* s = S + static_cast<long long>(row) * ld;
+  const int g0 = gt_off[row];
+  const int ng = min(gt_off[row + 1] - g0, kMaxGt);
+  if (threadIdx.x < ng) {
+    s_t[threadIdx.x] = s[gt_ids[g0 + threadIdx.x]];
+    s_c[threadIdx.x] = 0;
+  }
+  __syncthreads();
+  int cnt[kMaxGt];
+#pragma unroll
+  for (int g = 0; g < kMaxGt; ++g) cnt[g] = 0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float v = __ldg(s + c);
+#pragma unroll
+    for (int g = 0; g < kMaxGt; ++g)
+      if (g < ng && v > s_t[g]) ++cnt[g];
+  }
+#pragma unroll
+  for (int g = 0; g < kMaxGt; ++g) {
+    if (g < ng) {
+      int v = cnt[g];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_c[g], v);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int best = 0x7fffffff;
+    for (int g = 0; g < ng; ++g) best = min(best, s_c[g]);
+    rank[row] = best == 0x7fffffff ? C : best;
+  }
+}
+
+// One thread per column, rows split over blockIdx.y; partial counts combined with atomicAdd into
+// cnt[nnz] (zero-initialised), then rank_cols_min takes the min over each column's GT.
+__global__ void rank_cols_count_kernel(const float* __restrict__ S, long long ld, int R, int C,
+                                       const int* __restrict__ gt_off, const int* __restrict__ gt_ids,
+                                       int rows_per_block, int* __restrict__ cnt_nnz) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int g0 = gt_off[c];
+  const int ng = min(gt_off[c + 1] - g0, kMaxGt);
+  float t[kMaxGt];
+  int cnt[kMaxGt];
+#pragma unroll
+  for (int g = 0; g < kMaxGt; ++g) {
+    cnt[g] = 0;
+    t[g] = (g < ng) ? __ldg(S + static_cast<long long>(gt_ids[g0 + g]) * ld + c) : CUDART_INF_F;
+  }
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(R, r0 + rows_per_block);
+  for (int r = r0; r < r1; ++r) {
+    const float v = __ldg(S + static_cast<long long>(r) * ld + c);
+#pragma unroll
+    for (int g = 0; g < kMaxGt; ++g) cnt[g] += (v > t[g]) ? 1 : 0;
+  }
+#pragma unroll
+  for (int g = 0; g < kMaxGt; ++g)
+    if (g < ng && cnt[g]) atomicAdd(cnt_nnz + g0 + g, cnt[g]);
+}
+
+__global__ void rank_cols_min_kernel(int C, int R, const int* __restrict__ gt_off,
+                                     const int* __restrict__ cnt_nnz, int* __restrict__ rank) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  int best = 0x7fffffff;
+  const int g1 = min(gt_off[c + 1], gt_off[c] + kMaxGt);
+  for (int g = gt_off[c]; g < g1; ++g) best = min(best, cnt_nnz[g]);
+  rank[c] = best == 0x7fffffff ? R : best;
+}
+
+// Recall@1/5/10 counts from ranks: out[0..2] += #{rank < 1, 5, 10}.
+__global__ void recall_count_kernel(const int* __restrict__ rank, int n, int* __restrict__ out) {
+  int c1 = 0, c5 = 0, c10 = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int r = rank[i];
+    c1 += r < 1;
+    c5 += r < 5;
+    c10 += r < 10;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+    c5 += __shfl_xor_sync(0xffffffffu, c5, o);
+    c10 += __shfl_xor_sync(0xffffffffu, c10, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (c1) atomicAdd(out + 0, c1);
+    if (c5) atomicAdd(out + 1, c5);
+    if (c10) atomicAdd(out + 2, c10);
+  }
+}
+
+// --------------------------------------------------------------------------------
+// double_sim (video_Retrieval_caption_double_sim.py:87-91,170-179)
+//   C = max_n Cn ; global min / max of S and of C ; fused = w1 * norm(S) + w2 * norm(C)
+//   norm(x) = -(( -x - min(-x)) / max(-x - min(-x))) == (x - max x) / (max x - min x)
+// mm[0..3] = ordered-uint {max S, min S, max C, min C}; init {0, ~0, 0, ~0}.
+// --------------------------------------------------------------------------------
+__global__ void capmax_minmax_kernel(const float* __restrict__ S, const float* __restrict__ Cn,
+                                     float* __restrict__ Cmax, int n_cap, long long numel,
+                                     unsigned* __restrict__ mm) {
+  float smax = -CUDART_INF_F, smin = CUDART_INF_F, cmax = -CUDART_INF_F, cmin = CUDART_INF_F;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < numel;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float s = S[i];
+    smax = fmaxf(smax, s);
+    smin = fminf(smin, s);
+    if (Cn != nullptr) {
+      float c = Cn[i];
+      for (int k = 1; k < n_cap; ++k) c = fmaxf(c, Cn[static_cast<long long>(k) * numel + i]);
+      Cmax[i] = c;
+      cmax = fmaxf(cmax, c);
+      cmin = fminf(cmin, c);
+    }
+  }
+  smax = warp_max(smax);
+  smin = warp_min(smin);
+  cmax = warp_max(cmax);
+  cmin = warp_min(cmin);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(mm + 0, f32_ordered(smax));
+    atomicMin(mm + 1, f32_ordered(smin));
+    if (Cn != nullptr) {
+      atomicMax(mm + 2, f32_ordered(cmax));
+      atomicMin(mm + 3, f32_ordered(cmin));
+    }
+  }
+}
+
+__global__ void mm_init_kernel(unsigned* mm) {
+  if (threadIdx.x < 4) mm[threadIdx.x] = (threadIdx.x & 1) ? 0xffffffffu : 0u;
+}
+
+// mode 1: norm fusion, mode 2: raw fusion (image_Retrieval_caption.py:244-246).
+// Same fp32 operation order as the reference (no FMA contraction).
+__global__ void fuse_scores_kernel(float* __restrict__ S, const float* __restrict__ Cmax, long long numel,
+                                   const unsigned* __restrict__ mm, float w1, float w2, int mode) {
+  float smax = 0.f, sden = 1.f, cmax = 0.f, cden = 1.f;
+  if (mode == 1) {
+    smax = ordered_f32(mm[0]);
+    sden = __fsub_rn(smax, ordered_f32(mm[1]));
+    cmax = ordered_f32(mm[2]);
+    cden = __fsub_rn(cmax, ordered_f32(mm[3]));
+  }
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < numel;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float a = S[i], b = Cmax[i];
+    if (mode == 1) {
+      a = -__fdiv_rn(__fsub_rn(smax, a), sden);
+      b = -__fdiv_rn(__fsub_rn(cmax, b), cden);
+    }
+    S[i] = __fadd_rn(__fmul_rn(w1, a), __fmul_rn(w2, b));
+  }
+}
+
+}  // namespace leccr
