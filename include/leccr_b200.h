@@ -51,7 +51,7 @@ extern "C" {
 #define LECCR_FUSE_RAW 2  /* image_Retrieval_caption.py:244-246        */
 
 #define LECCR_STAT_WORDS 4 /* floats per tensor written by leccr_prep: max|hi row|, max|residual row|, max|x|, bad flag */
-#define LECCR_TOPK_KP 16   /* candidates kept per (row, column chunk) by the streaming top-k */
+#define LECCR_TOPK_KP 16   /* list length behind the top-k / Recall decision (k <= 16) */
 #define LECCR_RANK_CAP 10  /* ranks >= this are reported as lower bounds (Recall@1/5/10 only needs < 10) */
 
 typedef void* leccr_stream_t; /* cudaStream_t */
@@ -86,12 +86,11 @@ int leccr_transpose16(const void* src16, int64_t n, int D, int64_t ld_src, void*
  * Replaces: score_matrix_i2t = image_embeds @ text_embeds.t()   image_Retrieval_caption.py:151
  *           c_sim = caption_embeds.reshape(-1,d) @ text_embeds.T video_Retrieval_caption_double_sim.py:174
  * With X3 operands (K = 3D) the product is fp32-accurate; with HI operands it carries the 16-bit
- * rounding of the inputs.  k_splits > 1 accumulates split-K partials with red.add into S, which the
- * caller must have zeroed; scale_dev (optional device scalar) is multiplied into scale.
+ * rounding of the inputs.  scale_dev (optional device scalar) is multiplied into scale.
  * ------------------------------------------------------------------------------------------ */
 int leccr_sim_f32(const void* rows16, int64_t ld_rows, const void* cols16, int64_t ld_cols, int64_t n_rows,
                   int64_t n_cols, int K, int fmt, float* S, int64_t ld_S, float scale,
-                  const float* scale_dev, int k_splits, leccr_stream_t stream);
+                  const float* scale_dev, leccr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * leccr_sim_topk: fused similarity + streaming per-row top-k (+ exact Recall ranks) for one or two
@@ -146,7 +145,7 @@ int leccr_infonce_fwd(const void* a16, const void* b16, int64_t ld16, const int6
                       int fmt, const float* temp, float* out, float* lse2, float* rcnt,
                       int tiles_per_chunk, void* workspace, size_t workspace_bytes,
                       leccr_stream_t stream);
-size_t leccr_infonce_bwd_workspace(int64_t n, int64_t row_count);
+size_t leccr_infonce_bwd_workspace(int64_t n, int64_t row_count, int D);
 int leccr_infonce_bwd(const void* a16, const void* b16, int64_t ld16, const void* aT16, const void* bT16,
                       int64_t ldT, const int64_t* idx, int64_t n, int D, int fmt, const float* temp,
                       const float* lse2, const float* rcnt, int64_t row_begin, int64_t row_count,

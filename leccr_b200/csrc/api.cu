@@ -122,10 +122,15 @@ int fill_problem(SimProblem& P, const void* rows16, int64_t ld_rows, const void*
   return LECCR_OK;
 }
 
-constexpr int kStages = 4;
+// As many pipeline stages as fit beside the epilogue's own shared memory (227 KB per CTA).
+template <class Epi>
+constexpr int stages_for() {
+  return sim_gemm_smem_bytes<Epi, 4>() <= 232448 ? 4 : 3;
+}
 
 template <class Epi>
 int launch_gemm(const SimLaunch& L, const typename Epi::Params& EP, cudaStream_t stream) {
+  constexpr int kStages = stages_for<Epi>();
   auto kern = sim_gemm_kernel<Epi, kStages>;
   constexpr size_t smem = sim_gemm_smem_bytes<Epi, kStages>();
   static_assert(smem <= 232448, "exceeds the 227 KB shared memory limit of sm_100");
@@ -137,7 +142,7 @@ int launch_gemm(const SimLaunch& L, const typename Epi::Params& EP, cudaStream_t
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(sim_gemm_kernel)");
   if (L.n_items <= 0) return LECCR_OK;
   const int grid = std::min(L.n_items, num_sms());
-  kern<<<grid, kGemmThreads, smem, stream>>>(L, EP);
+  kern<<<grid, gemm_threads(Epi::kWGs), smem, stream>>>(L, EP);
   LAUNCH_CHECK("sim_gemm_kernel");
   return LECCR_OK;
 }
@@ -182,12 +187,22 @@ int leccr_prep(const float* src, int64_t n, int D, int64_t ld_src, int normalize
   const int wpb = 8;
   const unsigned grid = static_cast<unsigned>((n + wpb - 1) / wpb);
   uint16_t* dst = static_cast<uint16_t*>(dst16);
-  if (fmt == LECCR_FMT_F16)
+  const bool vec = (D % 128 == 0) && D <= 1024 && (ld_src % 4 == 0) && (ld_dst % 4 == 0) &&
+                   (reinterpret_cast<uintptr_t>(src) % 16 == 0) && (reinterpret_cast<uintptr_t>(dst16) % 8 == 0);
+  if (vec) {
+    if (fmt == LECCR_FMT_F16)
+      prep_rows_vec_kernel<0><<<grid, wpb * 32, 0, stream>>>(src, ld_src, (int)n, D, normalize, layout, dst,
+                                                            ld_dst, rn_hi, rn_lo, stats);
+    else
+      prep_rows_vec_kernel<1><<<grid, wpb * 32, 0, stream>>>(src, ld_src, (int)n, D, normalize, layout, dst,
+                                                            ld_dst, rn_hi, rn_lo, stats);
+  } else if (fmt == LECCR_FMT_F16) {
     prep_rows_kernel<0><<<grid, wpb * 32, 0, stream>>>(src, ld_src, (int)n, D, normalize, layout, dst, ld_dst,
                                                       rn_hi, rn_lo, stats);
-  else
+  } else {
     prep_rows_kernel<1><<<grid, wpb * 32, 0, stream>>>(src, ld_src, (int)n, D, normalize, layout, dst, ld_dst,
                                                       rn_hi, rn_lo, stats);
+  }
   LAUNCH_CHECK("prep_rows_kernel");
   return LECCR_OK;
 }
@@ -220,49 +235,93 @@ int leccr_transpose16(const void* src16, int64_t n, int D, int64_t ld_src, void*
 }
 
 // ------------------------------------------------------------------------------------ sim_f32
+// Shared by leccr_sim_f32 and the gradient products: up to two problems, optional split-K into
+// partial planes `parts` ([k_splits][n_rows * ld_out] per problem) followed by a fixed-order reduce.
+struct StoreProblem {
+  const void* rows16;
+  const void* cols16;
+  int64_t ld_rows, ld_cols, n_rows, n_cols;
+  float* out;
+  int64_t ld_out;
+  float* parts;  // split-K partial planes (nullptr when k_splits <= 1)
+};
+
+static int launch_store(const StoreProblem* sp, int n_prob, int K, int fmt, float scale, const float* scale_dev,
+                        const float* div_dev, int k_splits, cudaStream_t stream) {
+  SimLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.n_prob = n_prob;
+  L.fmt = fmt;
+  L.k_chunks = (K + BK - 1) / BK;
+  EpiStore::Params EP;
+  memset(&EP, 0, sizeof(EP));
+  const bool split = k_splits > 1;
+  if (split) {
+    L.kc_per_split = (L.k_chunks + k_splits - 1) / k_splits;
+    L.k_splits = (L.k_chunks + L.kc_per_split - 1) / L.kc_per_split;
+    if (L.k_splits < 2) {  // keep the split decode (all column tiles per item) with one plane
+      L.k_splits = 2;
+      L.kc_per_split = L.k_chunks;
+    }
+  }
+  int item_base = 0;
+  int n_planes = 1;
+  for (int p = 0; p < n_prob; ++p) {
+    Plan pl;
+    if (split) {
+      pl = plan_problem(sp[p].n_cols, 0, sp[p].n_rows, 1 << 30);
+      pl.n_chunks = (L.k_chunks + L.kc_per_split - 1) / L.kc_per_split;
+      n_planes = pl.n_chunks;
+    } else {
+      int64_t tiles = 0;
+      for (int q = 0; q < n_prob; ++q)
+        tiles += ((sp[q].n_rows + BM - 1) / BM) * ((sp[q].n_cols + BN - 1) / BN);
+      pl = plan_problem(sp[p].n_cols, 0, sp[p].n_rows, auto_tiles_per_chunk(tiles, 1));
+    }
+    int rc = fill_problem(L.prob[p], sp[p].rows16, sp[p].ld_rows, sp[p].cols16, sp[p].ld_cols, sp[p].n_rows,
+                          sp[p].n_cols, K, fmt, pl, item_base);
+    if (rc != LECCR_OK) return rc;
+    item_base += pl.row_blocks * pl.n_chunks;
+    EP.out[p] = split ? sp[p].parts : sp[p].out;
+    EP.ld[p] = sp[p].ld_out;
+    EP.scale[p] = scale;
+    EP.scale_ptr[p] = scale_dev;
+    EP.div_ptr[p] = div_dev;
+    EP.split_stride[p] = split ? sp[p].n_rows * sp[p].ld_out : 0;
+  }
+  L.n_items = item_base;
+  int rc = launch_gemm<EpiStore>(L, EP, stream);
+  if (rc != LECCR_OK) return rc;
+  if (split) {
+    for (int p = 0; p < n_prob; ++p) {
+      const long long plane = sp[p].n_rows * sp[p].ld_out;
+      const unsigned g = static_cast<unsigned>(std::min<long long>((plane + 255) / 256, 4LL * num_sms()));
+      splitk_reduce_kernel<<<g, 256, 0, stream>>>(sp[p].parts, n_planes, plane, sp[p].out);
+      LAUNCH_CHECK("splitk_reduce_kernel");
+    }
+  }
+  return LECCR_OK;
+}
+
 int leccr_sim_f32(const void* rows16, int64_t ld_rows, const void* cols16, int64_t ld_cols, int64_t n_rows,
                   int64_t n_cols, int K, int fmt, float* S, int64_t ld_S, float scale, const float* scale_dev,
-                  int k_splits, leccr_stream_t stream_) {
+                  leccr_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (rows16 == nullptr || cols16 == nullptr || S == nullptr || n_rows <= 0 || n_cols <= 0 || K <= 0 ||
       bad_fmt(fmt) || ld_S < n_cols)
     return LECCR_ERR_ARG;
   int rc = leccr_check_device();
   if (rc != LECCR_OK) return rc;
-  SimLaunch L;
-  memset(&L, 0, sizeof(L));
-  L.n_prob = 1;
-  L.fmt = fmt;
-  L.k_chunks = (K + BK - 1) / BK;
-  Plan pl;
-  if (k_splits > 1) {
-    L.kc_per_split = (L.k_chunks + k_splits - 1) / k_splits;
-    L.k_splits = (L.k_chunks + L.kc_per_split - 1) / L.kc_per_split;
-    pl = plan_problem(n_cols, 0, n_rows, 1 << 30);
-    pl.n_chunks = L.k_splits;
-    if (L.k_splits == 1) L.k_splits = 0;
-  } else {
-    const int64_t tiles = ((n_rows + BM - 1) / BM) * ((n_cols + BN - 1) / BN);
-    pl = plan_problem(n_cols, 0, n_rows, auto_tiles_per_chunk(tiles, 1));
-  }
-  rc = fill_problem(L.prob[0], rows16, ld_rows, cols16, ld_cols, n_rows, n_cols, K, fmt, pl, 0);
-  if (rc != LECCR_OK) return rc;
-  L.n_items = pl.row_blocks * pl.n_chunks;
-  EpiStore::Params EP;
-  memset(&EP, 0, sizeof(EP));
-  EP.out[0] = S;
-  EP.ld[0] = ld_S;
-  EP.scale[0] = scale;
-  EP.scale_ptr[0] = scale_dev;
-  EP.accumulate = L.k_splits > 1 ? 1 : 0;
-  return launch_gemm<EpiStore>(L, EP, stream);
+  StoreProblem sp = {rows16, cols16, ld_rows, ld_cols, n_rows, n_cols, S, ld_S, nullptr};
+  return launch_store(&sp, 1, K, fmt, scale, scale_dev, nullptr, 1, stream);
 }
 
 // ------------------------------------------------------------------------------------ sim_topk
-// Work decomposition of a top-k launch.  The per-row candidate merge holds n_chunks * KP <= 256
-// candidates, so a row's columns are split into at most kMaxTopkChunks chunks.  Each problem gets a
+// Work decomposition of a top-k launch.  topk_finalize holds 2 * n_chunks candidates per lane,
+// so a row's columns are split into at most kMaxTopkChunks chunks.  Each problem gets a
 // share of ~4 work items per SM proportional to its tile count.
-constexpr int kMaxTopkChunks = 256 / LECCR_TOPK_KP;
+constexpr int kTopkWGs = EpiTopK<LECCR_TOPK_KP>::kWGs;
+constexpr int kMaxTopkChunks = kMaxChunks / kTopkWGs;
 
 static int topk_plan(const leccr_topk_problem* probs, int n_prob, int tiles_per_chunk, Plan* plans) {
   int64_t total_tiles = 0;
@@ -292,8 +351,9 @@ size_t leccr_sim_topk_workspace(const leccr_topk_problem* probs, int n_prob, int
   if (topk_plan(probs, n_prob, tiles_per_chunk, plans) != LECCR_OK) return 0;
   size_t bytes = 0;
   for (int p = 0; p < n_prob; ++p) {
-    const size_t cand = static_cast<size_t>(probs[p].n_rows) * plans[p].n_chunks * LECCR_TOPK_KP;
-    bytes += align256(cand * 4) * 2 + align256(static_cast<size_t>(probs[p].n_rows) * 4);
+    const size_t lists = static_cast<size_t>(probs[p].n_rows) * plans[p].n_chunks * kTopkWGs;
+    bytes += align256(lists * kListCap * 4) * 2 + align256(lists * 4) +
+             align256(static_cast<size_t>(probs[p].n_rows) * 4 + 16);
   }
   return bytes;
 }
@@ -330,6 +390,7 @@ int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   float* cand_val[2];
   int* cand_idx[2];
+  int* cand_cnt[2];
   int* flag[2];
   int item_base = 0;
   for (int p = 0; p < n_prob; ++p) {
@@ -338,16 +399,20 @@ int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
                       plans[p], item_base);
     if (rc != LECCR_OK) return rc;
     item_base += plans[p].row_blocks * plans[p].n_chunks;
-    const size_t cand = static_cast<size_t>(q.n_rows) * plans[p].n_chunks * LECCR_TOPK_KP;
+    const size_t lists = static_cast<size_t>(q.n_rows) * plans[p].n_chunks * kTopkWGs;
     cand_val[p] = reinterpret_cast<float*>(ws);
-    ws += align256(cand * 4);
+    ws += align256(lists * kListCap * 4);
     cand_idx[p] = reinterpret_cast<int*>(ws);
-    ws += align256(cand * 4);
-    flag[p] = reinterpret_cast<int*>(ws);
-    ws += align256(static_cast<size_t>(q.n_rows) * 4);
+    ws += align256(lists * kListCap * 4);
+    cand_cnt[p] = reinterpret_cast<int*>(ws);
+    ws += align256(lists * 4);
+    flag[p] = reinterpret_cast<int*>(ws);  // [0] count, [4..] list of undecided rows
+    ws += align256(static_cast<size_t>(q.n_rows) * 4 + 16);
+    if (q.gt_off != nullptr) CUDA_TRY(cudaMemsetAsync(flag[p], 0, 16, stream));
     EP.out_val[p] = cand_val[p];
     EP.out_idx[p] = cand_idx[p];
-    EP.n_chunks[p] = plans[p].n_chunks;
+    EP.out_cnt[p] = cand_cnt[p];
+    EP.n_sub[p] = plans[p].n_chunks * kTopkWGs;
   }
   L.n_items = item_base;
   rc = launch_gemm<EpiTopK<LECCR_TOPK_KP>>(L, EP, stream);
@@ -359,9 +424,10 @@ int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
     memset(&F, 0, sizeof(F));
     F.cand_val = cand_val[p];
     F.cand_idx = cand_idx[p];
+    F.cand_cnt = cand_cnt[p];
     F.n_rows = static_cast<int>(q.n_rows);
     F.n_cols = static_cast<int>(q.n_cols);
-    F.n_chunks = plans[p].n_chunks;
+    F.n_chunks = plans[p].n_chunks * kTopkWGs;
     F.KP = LECCR_TOPK_KP;
     F.k = k;
     F.topk_val = q.topk_val;
@@ -380,14 +446,14 @@ int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
     // fp32 accumulation of K products in the tensor core: 2 ulp per product, conservatively
     F.acc_slack = 2.0f * 1.1920929e-7f * static_cast<float>(D);
     F.rank = q.rank;
-    F.flag = flag[p];
+    F.flag_count = flag[p];
+    F.flag_list = flag[p] + 4;
     F.gt_score = q.gt_score;
-    const int wpb = 8;
-    const unsigned grid = static_cast<unsigned>((q.n_rows + wpb - 1) / wpb);
-    topk_finalize_kernel<<<grid, wpb * 32, 0, stream>>>(F);
+    const unsigned grid = static_cast<unsigned>((q.n_rows + kFinalizeWarps - 1) / kFinalizeWarps);
+    topk_finalize_kernel<<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
     LAUNCH_CHECK("topk_finalize_kernel");
     if (q.gt_off != nullptr) {
-      const unsigned g2 = static_cast<unsigned>(std::min<int64_t>(q.n_rows, 4LL * num_sms()));
+      const unsigned g2 = static_cast<unsigned>(std::min<int64_t>(q.n_rows, 2LL * num_sms()));
       exact_rank_rows_kernel<<<g2, 256, 0, stream>>>(F);
       LAUNCH_CHECK("exact_rank_rows_kernel");
       if (q.recall_counts != nullptr) {
@@ -410,7 +476,7 @@ static Plan infonce_plan(int64_t n, int tiles_per_chunk) {
 size_t leccr_infonce_fwd_workspace(int64_t n, int tiles_per_chunk) {
   if (n <= 0) return 0;
   const Plan pl = infonce_plan(n, tiles_per_chunk);
-  return 2 * align256(static_cast<size_t>(n) * pl.n_chunks * 5 * 4);
+  return 2 * align256(static_cast<size_t>(n) * pl.n_chunks * EpiLse::kWGs * 5 * 4) + 256;
 }
 
 int leccr_infonce_fwd(const void* a16, const void* b16, int64_t ld16, const int64_t* idx, int64_t n, int D,
@@ -436,16 +502,19 @@ int leccr_infonce_fwd(const void* a16, const void* b16, int64_t ld16, const int6
   rc = fill_problem(L.prob[1], b16, ld16, a16, ld16, n, n, D, fmt, pl, items);
   if (rc != LECCR_OK) return rc;
   L.n_items = 2 * items;
-  const size_t part_bytes = align256(static_cast<size_t>(n) * pl.n_chunks * 5 * 4);
+  const int n_sub = pl.n_chunks * EpiLse::kWGs;
+  const size_t part_bytes = align256(static_cast<size_t>(n) * n_sub * 5 * 4);
   float* part0 = static_cast<float*>(workspace);
   float* part1 = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + part_bytes);
+  double* scratch = reinterpret_cast<double*>(static_cast<uint8_t*>(workspace) + 2 * part_bytes);
+  CUDA_TRY(cudaMemsetAsync(scratch, 0, 64, stream));
   EpiLse::Params EP;
   memset(&EP, 0, sizeof(EP));
   EP.temp = temp;
   for (int p = 0; p < 2; ++p) {
     EP.idx_rows[p] = reinterpret_cast<const long long*>(idx);
     EP.idx_cols[p] = reinterpret_cast<const long long*>(idx);
-    EP.n_chunks[p] = pl.n_chunks;
+    EP.n_sub[p] = n_sub;
   }
   EP.part[0] = part0;
   EP.part[1] = part1;
@@ -456,23 +525,33 @@ int leccr_infonce_fwd(const void* a16, const void* b16, int64_t ld16, const int6
   F.part[0] = part0;
   F.part[1] = part1;
   F.n[0] = F.n[1] = static_cast<int>(n);
-  F.nch[0] = F.nch[1] = pl.n_chunks;
+  F.nch[0] = F.nch[1] = n_sub;
+  F.scratch = scratch;
   F.lse2[0] = lse2;
   F.lse2[1] = lse2 + n;
   F.rcnt[0] = rcnt;
   F.rcnt[1] = rcnt + n;
   F.temp = temp;
   F.out = out;
-  infonce_finalize_kernel<<<1, 1024, 0, stream>>>(F);
+  infonce_finalize_kernel<<<static_cast<unsigned>((2 * n + 255) / 256), 256, 0, stream>>>(F);
   LAUNCH_CHECK("infonce_finalize_kernel");
   return LECCR_OK;
 }
 
 static int64_t round_up8(int64_t x) { return (x + 7) & ~static_cast<int64_t>(7); }
 
-size_t leccr_infonce_bwd_workspace(int64_t n, int64_t row_count) {
-  if (n <= 0 || row_count <= 0) return 0;
-  return 2 * align256(static_cast<size_t>(row_count) * round_up8(n) * 2);
+// split-K factor of the gradient products: fill the machine, at least 2 K-chunks per split
+static int bwd_splits(int k_chunks, int row_blocks) {
+  const int want = std::max(1, num_sms() / std::max(1, 2 * row_blocks));
+  return std::max(1, std::min(want, (k_chunks + 1) / 2));
+}
+
+size_t leccr_infonce_bwd_workspace(int64_t n, int64_t row_count, int D) {
+  if (n <= 0 || row_count <= 0 || D <= 0) return 0;
+  const int k_chunks = static_cast<int>((n + BK - 1) / BK);
+  const int row_blocks = static_cast<int>((row_count + BM - 1) / BM);
+  const size_t parts = 2 * static_cast<size_t>(bwd_splits(k_chunks, row_blocks)) * row_count * D * 4;
+  return 2 * align256(static_cast<size_t>(row_count) * round_up8(n) * 2) + align256(parts);
 }
 
 int leccr_infonce_bwd(const void* a16, const void* b16, int64_t ld16, const void* aT16, const void* bT16,
@@ -487,7 +566,7 @@ int leccr_infonce_bwd(const void* a16, const void* b16, int64_t ld16, const void
     return LECCR_ERR_ARG;
   int rc = leccr_check_device();
   if (rc != LECCR_OK) return rc;
-  if (workspace == nullptr || workspace_bytes < leccr_infonce_bwd_workspace(n, row_count))
+  if (workspace == nullptr || workspace_bytes < leccr_infonce_bwd_workspace(n, row_count, D))
     return LECCR_ERR_WORKSPACE;
   const int64_t ldS = round_up8(n);
   const size_t strip_bytes = align256(static_cast<size_t>(row_count) * ldS * 2);
@@ -530,39 +609,18 @@ int leccr_infonce_bwd(const void* a16, const void* b16, int64_t ld16, const void
     if (rc != LECCR_OK) return rc;
   }
   // 2. dA_loc = G'[loc,:] B / (2 n temp),  dB_loc = G'[:,loc]^T A / (2 n temp): split-K products
-  CUDA_TRY(cudaMemsetAsync(dA, 0, static_cast<size_t>(row_count) * D * 4, stream));
-  CUDA_TRY(cudaMemsetAsync(dB, 0, static_cast<size_t>(row_count) * D * 4, stream));
   {
-    SimLaunch L;
-    memset(&L, 0, sizeof(L));
-    L.n_prob = 2;
-    L.fmt = fmt;
-    L.k_chunks = static_cast<int>((n + BK - 1) / BK);
-    Plan pl = plan_problem(D, 0, row_count, 1 << 30);
-    int splits = std::max(1, std::min(L.k_chunks, (2 * num_sms()) / std::max(1, 2 * pl.row_blocks)));
-    L.kc_per_split = (L.k_chunks + splits - 1) / splits;
-    L.k_splits = (L.k_chunks + L.kc_per_split - 1) / L.kc_per_split;
-    pl.n_chunks = L.k_splits;
-    const int items = pl.row_blocks * pl.n_chunks;
-    if (L.k_splits == 1) {
-      L.k_splits = 2;  // keep the split-K decode (all column tiles per item) with a single split
-      L.kc_per_split = L.k_chunks;
-    }
-    rc = fill_problem(L.prob[0], strip0, ldS, bT16, ldT, row_count, D, static_cast<int>(n), fmt, pl, 0);
-    if (rc != LECCR_OK) return rc;
-    rc = fill_problem(L.prob[1], strip1, ldS, aT16, ldT, row_count, D, static_cast<int>(n), fmt, pl, items);
-    if (rc != LECCR_OK) return rc;
-    L.n_items = 2 * items;
-    EpiStore::Params EP;
-    memset(&EP, 0, sizeof(EP));
-    EP.out[0] = dA;
-    EP.out[1] = dB;
-    EP.ld[0] = EP.ld[1] = D;
-    EP.scale[0] = EP.scale[1] = 1.0f / (2.0f * static_cast<float>(n));
-    EP.scale_ptr[0] = EP.scale_ptr[1] = grad_out;
-    EP.div_ptr[0] = EP.div_ptr[1] = temp;
-    EP.accumulate = 1;
-    rc = launch_gemm<EpiStore>(L, EP, stream);
+    const int k_chunks = static_cast<int>((n + BK - 1) / BK);
+    const int row_blocks = static_cast<int>((row_count + BM - 1) / BM);
+    const int splits = bwd_splits(k_chunks, row_blocks);
+    float* parts0 = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 2 * strip_bytes);
+    float* parts1 = parts0 + static_cast<size_t>(splits) * row_count * D;
+    StoreProblem sp[2] = {
+        {strip0, bT16, ldS, ldT, row_count, D, dA, D, parts0},
+        {strip1, aT16, ldS, ldT, row_count, D, dB, D, parts1},
+    };
+    rc = launch_store(sp, 2, static_cast<int>(n), fmt, 1.0f / (2.0f * static_cast<float>(n)), grad_out, temp,
+                      splits, stream);
     if (rc != LECCR_OK) return rc;
   }
   return LECCR_OK;

@@ -1,11 +1,13 @@
 // Epilogue policies for sim_gemm_kernel (gemm_sm100.cuh).  Each epilogue thread owns one row of the
 // 128 x 256 accumulator tile, so the row-wise reductions of the reference
-//   - np.argsort(score)[::-1] per row            image_Retrieval_caption.py:268,289
+//   - np.argsort(score)[::-1] per row               image_Retrieval_caption.py:268,289
 //   - F.log_softmax(logits, dim=1) / cross_entropy  models/xvlm.py:279-290
 // become thread-local streaming reductions over the column tiles of a work item.
+// Everything a thread does per element is branch-free or warp-uniform; the only per-thread
+// divergence is the rare list maintenance of the top-k epilogue, and that contains no collectives.
 #pragma once
-#include <cuda_fp16.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math_constants.h>
 #include "gemm_sm100.cuh"
 
@@ -14,10 +16,38 @@ namespace leccr {
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
+// Walk the 256 accumulator columns of this thread's row in chunks of 32, with the TMEM load of
+// the next chunk in flight while the current one is processed.  f(v, col, n_valid) must be
+// warp-uniform in its use of collectives.  n_limit: first column index that does not exist.
+template <class F>
+__device__ __forceinline__ void for_each_chunk(uint32_t taddr, int col0, int n_limit, F&& f) {
+  const int nch = min(BN / 32, (n_limit - col0 + 31) / 32);  // warp-uniform
+  if (nch <= 0) return;
+  float va[32], vb[32];
+  tmem_ld_32x32(taddr, va);
+  tmem_wait_ld_regs(va);
+#pragma unroll 1
+  for (int ch = 0; ch < nch; ch += 2) {
+    const bool has_b = ch + 1 < nch;
+    const bool has_a2 = ch + 2 < nch;
+    if (has_b) tmem_ld_32x32(taddr + (ch + 1) * 32, vb);
+    f(va, col0 + ch * 32);
+    if (has_b) {
+      tmem_wait_ld_regs(vb);
+      if (has_a2) tmem_ld_32x32(taddr + (ch + 2) * 32, va);
+      f(vb, col0 + (ch + 1) * 32);
+      if (has_a2) tmem_wait_ld_regs(va);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
-// EpiStore: materialise S (fp32), optionally scaled and/or accumulated (split-K partial sums).
+// EpiStore: materialise S (fp32), optionally scaled; in split-K mode each split writes its own
+// partial plane (out + split * split_stride) and splitk_reduce_kernel sums them in a fixed order.
 // Used for the reference's small score matrices (image_Retrieval_caption.py:151) and for the
 // gradient products dA = G B, dB = G^T A of the contrastive backward.
+// Each warp transposes its 32 x 32 sub-tile through shared memory so global stores are full
+// 128-byte lines.
 // ------------------------------------------------------------------------------------------
 struct EpiStore {
   struct Params {
@@ -26,9 +56,11 @@ struct EpiStore {
     float scale[2];
     const float* scale_ptr[2];  // optional device scalar multiplied into scale (upstream grad)
     const float* div_ptr[2];    // optional device scalar divided out of scale (temperature)
-    int accumulate;             // 1: red.add (split-K), 0: plain store
+    long long split_stride[2];  // elements between split-K partial planes (0 when not split)
   };
-  static constexpr int kSmemBytes = 0;
+  static constexpr int kWGs = 2;
+  static constexpr int kTileLd = 33;
+  static constexpr int kSmemBytes = 4 * 32 * kTileLd * 4;
   struct State {};
   __device__ static void begin(State&, const Params&, const ItemCtx&) {}
   __device__ static void end(State&, const Params&, const ItemCtx&) {}
@@ -36,164 +68,234 @@ struct EpiStore {
     float scale = P.scale[c.p];
     if (P.scale_ptr[c.p] != nullptr) scale *= __ldg(P.scale_ptr[c.p]);
     if (P.div_ptr[c.p] != nullptr) scale /= __ldg(P.div_ptr[c.p]);
-    float* orow = P.out[c.p] + static_cast<long long>(c.row) * P.ld[c.p];
-    const bool vec_ok = ((P.ld[c.p] & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.out[c.p]) & 15) == 0);
-#pragma unroll 1
-    for (int cb = 0; cb < BN; cb += 32) {
-      const int col = col0 + cb;
-      if (col >= c.n_cols) break;  // warp-uniform
-      float v[32];
-      tmem_ld_32x32(taddr + cb, v);
-      tmem_wait_ld();
-      if (c.row < c.n_rows) {
-        if (P.accumulate) {
+    float* out = P.out[c.p] + static_cast<long long>(c.cc) * P.split_stride[c.p];  // cc == K split here
+    const long long ld = P.ld[c.p];
+    const uint32_t tbase = smem_u32(c.smem) + static_cast<uint32_t>(c.warp_q) * 32 * kTileLd * 4;
+    const int row0 = c.rb * BM + c.warp_q * 32;
+    const int lane = c.lane;
+    const int n_rows = c.n_rows, n_cols = c.n_cols;
+    for_each_chunk(taddr, col0, n_cols, [&](float(&v)[32], int col) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (col + e < c.n_cols) atomicAdd(orow + col + e, v[e] * scale);
-        } else if (vec_ok && col + 32 <= c.n_cols) {
-          float4* o4 = reinterpret_cast<float4*>(orow + col);
+      for (int e = 0; e < 32; ++e) sts_f32(tbase + (lane * kTileLd + e) * 4, v[e] * scale);
+      __syncwarp();
+      float* o = out + static_cast<long long>(row0) * ld + col + lane;
+      if (row0 + 32 <= n_rows && col + 32 <= n_cols) {  // interior: no bounds checks (warp-uniform)
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            o4[e] = make_float4(v[4 * e] * scale, v[4 * e + 1] * scale, v[4 * e + 2] * scale,
-                                v[4 * e + 3] * scale);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (col + e < c.n_cols) orow[col + e] = v[e] * scale;
+        for (int r = 0; r < 32; ++r) o[static_cast<long long>(r) * ld] = lds_f32(tbase + (r * kTileLd + lane) * 4);
+      } else {
+        const bool col_ok = col + lane < n_cols;
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+          const float x = lds_f32(tbase + (r * kTileLd + lane) * 4);
+          if (col_ok && row0 + r < n_rows) o[static_cast<long long>(r) * ld] = x;
         }
       }
-    }
+      __syncwarp();
+    });
   }
 };
 
 // ------------------------------------------------------------------------------------------
-// EpiTopK<KP>: streaming per-row top-KP of the approximate (16-bit operand) scores.
-// Common case per 8 columns: one max-reduce and one compare against the row's threshold.
-// Rare case: append to the row's list in shared memory; when a list is nearly full the warp
-// sorts that one row cooperatively (rank selection) and raises the row's threshold.
-// Output per (row, column chunk): KP (score, column) pairs sorted by score descending
-// (ties: lower column first), padded with (-inf, -1).
+// EpiTopK<KP>: streaming per-row candidates for the top-KP of the approximate (16-bit operand)
+// scores.  Per thread (= row): a threshold `thr` with the invariant "at least KP seen scores are
+// > thr (or thr = -inf)", and a list (shared memory, capacity C) of every seen score > thr.
+//   common case, per 8 columns : one max-reduce, one compare with thr
+//   rare                        : append (score, column) to the list
+//   when a list is nearly full  : raise thr by bisection on the score value until KP..KEEP of the
+//                                 listed scores exceed it, drop the rest.  Purely per-thread
+//                                 (no shuffles), so all 32 rows of a warp shrink side by side.
+// Nothing <= thr can belong to the row's top-KP, so the union of a row's lists over its column
+// chunks contains the exact top-KP of the approximate scores; topk_finalize selects them.
 // ------------------------------------------------------------------------------------------
 template <int KP>
 struct EpiTopK {
-  static constexpr int C = 32;  // list capacity per row == warp width (one entry per lane when sorting)
-  static_assert(KP <= 24, "KP must leave room for one 8-column group");
-  static constexpr int LDS = C + 1;  // +1 word: conflict-free both for per-thread append and per-row sort
+  static constexpr int kWGs = 1;         // the lists fill shared memory: one warpgroup
+  static constexpr int C = 64;           // list capacity
+  static constexpr int LDSW = C + 1;     // row pitch in words: conflict-free for per-thread and per-row access
+  static constexpr int TRIG = C - 8;     // a group of 8 columns must always fit
+  static constexpr int KEEP = 32;        // the exact (bisection) shrink stops once this few remain
+  static constexpr int JOIN = 48;        // rows at least this full shrink whenever any row of the warp must
+  static_assert(KP == 16 && C == 64, "quad_shrink assumes 16 strided quads of a 64-entry list");
+  static_assert(KP <= KEEP && KEEP < JOIN && JOIN <= TRIG, "inconsistent list policy");
   struct Params {
-    float* out_val[2];  // [n_rows][n_chunks][KP]
+    float* out_val[2];  // [n_rows][n_sub][C]
     int* out_idx[2];
-    int n_chunks[2];
+    int* out_cnt[2];    // [n_rows][n_sub]
+    int n_sub[2];       // partial lists per row: n_chunks * kWGs
   };
-  static constexpr int kSmemBytes = 2 * kEpiThreads * LDS * 4;
+  static constexpr int kSmemBytes = 2 * kEpiThreads * LDSW * 4;
   struct State {
     float thr;
     int cnt;
+    uint32_t vb, ib;  // shared-window addresses of this thread's value / index list
   };
 
-  __device__ static float* vals(const ItemCtx& c) { return reinterpret_cast<float*>(c.smem); }
-  __device__ static int* idxs(const ItemCtx& c) {
-    return reinterpret_cast<int*>(c.smem) + kEpiThreads * LDS;
-  }
-
-  __device__ static void begin(State& st, const Params&, const ItemCtx&) {
+  __device__ static void begin(State& st, const Params&, const ItemCtx& c) {
     st.thr = -CUDART_INF_F;
     st.cnt = 0;
+    st.vb = smem_u32(c.smem) + static_cast<uint32_t>(c.et) * LDSW * 4;
+    st.ib = st.vb + kEpiThreads * LDSW * 4;
   }
 
-  // Warp-cooperative: sort row `src_lane`'s list, keep the best KP.  Returns (via out params on
-  // every lane) the lane's element and its rank; the caller decides where the sorted list goes.
-  __device__ static void rank_row(const ItemCtx& c, int src_lane, int cnt_src, float& v, int& id,
-                                  int& rank) {
-    const int et_src = c.warp_q * 32 + src_lane;
-    const float* vr = vals(c) + et_src * LDS;
-    const int* ir = idxs(c) + et_src * LDS;
-    const bool have = c.lane < cnt_src;
-    v = have ? vr[c.lane] : -CUDART_INF_F;
-    id = have ? ir[c.lane] : -1;
-    rank = 0;
+  __device__ static int count_above(uint32_t vb, int n, float t) {
+    int cgt = 0;
+#pragma unroll 8
+    for (int s = 0; s < C; ++s) {
+      const float x = lds_f32(vb + s * 4);
+      cgt += (s < n && x > t) ? 1 : 0;
+    }
+    return cgt;
+  }
+  // The shrinks run rarely and are large: keep them out of line (one copy, small hot loop) and pass
+  // the state by value so it stays in registers.  Result: (thr bits << 32) | cnt.
+  __device__ static unsigned long long pack_state(float thr, int cnt) {
+    return (static_cast<unsigned long long>(__float_as_uint(thr)) << 32) | static_cast<unsigned>(cnt);
+  }
+
+  // Cheap, branch-free shrink: the minimum tau of the 16 maxima of the strided quads
+  // {k, k+16, k+32, k+48} has at least 16 listed scores >= tau, so it is a valid new threshold;
+  // keep the entries >= tau (typically ~24 of 64).  If that frees too little (adversarial order or
+  // ties) the exact bisection shrink takes over.
+  __device__ __noinline__ static unsigned long long quad_shrink(float thr_in, int n, uint32_t vb, uint32_t ib) {
+    float x[C];
 #pragma unroll
-    for (int l = 0; l < 32; ++l) {
-      const float ov = __shfl_sync(0xffffffffu, v, l);
-      rank += (ov > v || (ov == v && l < c.lane)) ? 1 : 0;  // slots are in arrival (column) order
+    for (int s = 0; s < C; ++s) {
+      x[s] = lds_f32(vb + s * 4);
+      if (s >= n) x[s] = -CUDART_INF_F;
     }
+    float tau = CUDART_INF_F;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      tau = fminf(tau, fmaxf(fmaxf(x[k], x[k + 16]), fmaxf(x[k + 32], x[k + 48])));
+    int j = 0;
+#pragma unroll
+    for (int s = 0; s < C; ++s) {
+      const int id = lds_s32(ib + s * 4);
+      if (x[s] >= tau) {  // -inf padding never passes: tau > -inf whenever n >= 49
+        sts_f32(vb + j * 4, x[s]);
+        sts_s32(ib + j * 4, id);
+        ++j;
+      }
+    }
+    const float thr = fmaxf(thr_in, tau);
+    const int cnt = (tau == -CUDART_INF_F) ? n : j;
+    if (cnt > JOIN) return shrink(thr, cnt, vb, ib);
+    return pack_state(thr, cnt);
   }
 
-  __device__ static void compact_row(State& st, const ItemCtx& c, int src_lane) {
-    __syncwarp();  // the owner's appends must be visible to the whole warp
-    const int cnt_src = __shfl_sync(0xffffffffu, st.cnt, src_lane);
-    float v;
-    int id, rank;
-    rank_row(c, src_lane, cnt_src, v, id, rank);
-    __syncwarp();
-    const int et_src = c.warp_q * 32 + src_lane;
-    if (rank < KP) {
-      vals(c)[et_src * LDS + rank] = v;
-      idxs(c)[et_src * LDS + rank] = id;
+  __device__ __noinline__ static unsigned long long shrink(float thr_in, int n, uint32_t vb, uint32_t ib) {
+    float vmax = -CUDART_INF_F, vmin = CUDART_INF_F;
+#pragma unroll 8
+    for (int s = 0; s < C; ++s) {
+      const float x = lds_f32(vb + s * 4);
+      if (s < n) {
+        vmax = fmaxf(vmax, x);
+        vmin = fminf(vmin, x);
+      }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, rank == KP - 1);
-    const float new_thr = __shfl_sync(0xffffffffu, v, __ffs(m) - 1);
-    __syncwarp();
-    if (c.lane == src_lane) {
-      st.thr = new_thr;
-      st.cnt = KP;
+    // keys: lo_k has c_lo >= KP listed scores above it, hi_k has c_hi < KP
+    uint32_t lo_k = f32_key(thr_in), hi_k = f32_key(vmax);
+    int c_lo = n, c_hi = 0;
+    bool first = thr_in == -CUDART_INF_F;  // -inf .. vmin is empty: probe vmin first
+#pragma unroll 1
+    for (int it = 0; it < 40; ++it) {
+      if (c_lo <= KEEP || hi_k - lo_k <= 1u) break;
+      uint32_t mid_k = lo_k + ((hi_k - lo_k) >> 1);
+      if (first) {
+        const uint32_t vk = f32_key(vmin);
+        if (vk > lo_k && vk < hi_k) mid_k = vk;
+        first = false;
+      }
+      const int cm = count_above(vb, n, key_f32(mid_k));
+      if (cm >= KP) {
+        lo_k = mid_k;
+        c_lo = cm;
+      } else {
+        hi_k = mid_k;
+        c_hi = cm;
+      }
     }
+    // Normal: keep scores > lo.  Tie block (adjacent keys, more than KEEP equal scores at hi):
+    // keep scores > hi plus as many == hi as needed to hold KP; then thr = hi.
+    const bool tie = c_lo > KEEP;
+    const float lo = key_f32(lo_k);
+    const float keep_thr = tie ? key_f32(hi_k) : lo;
+    int quota = tie ? KP - c_hi : 0;
+    int j = 0;
+#pragma unroll 4
+    for (int s = 0; s < C; ++s) {
+      const float x = lds_f32(vb + s * 4);
+      const int id = lds_s32(ib + s * 4);
+      bool keep = s < n && x > keep_thr;
+      if (!keep && s < n && quota > 0 && x > lo) {
+        keep = true;
+        --quota;
+      }
+      if (keep) {
+        sts_f32(vb + j * 4, x);
+        sts_s32(ib + j * 4, id);
+        ++j;
+      }
+    }
+    return pack_state(keep_thr, j);
   }
 
   __device__ static void tile(State& st, const Params&, const ItemCtx& c, uint32_t taddr, int col0) {
-    float* myv = vals(c) + c.et * LDS;
-    int* myi = idxs(c) + c.et * LDS;
-#pragma unroll 1
-    for (int cb = 0; cb < BN; cb += 32) {
-      const int col = col0 + cb;
-      if (col >= c.n_cols) break;  // warp-uniform
-      float v[32];
-      tmem_ld_32x32(taddr + cb, v);
-      tmem_wait_ld();
-      if (col + 32 > c.n_cols) {  // ragged last columns (TMA zero-filled): exclude them
+    const int n_cols = c.n_cols;
+    for_each_chunk(taddr, col0, n_cols, [&](float(&v)[32], int col) {
+      if (col + 32 > n_cols) {  // ragged last columns (TMA zero-filled): exclude them
 #pragma unroll
         for (int e = 0; e < 32; ++e)
-          if (col + e >= c.n_cols) v[e] = -CUDART_INF_F;
+          if (col + e >= n_cols) v[e] = -CUDART_INF_F;
       }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        float m = fmaxf(fmaxf(fmaxf(v[8 * g], v[8 * g + 1]), fmaxf(v[8 * g + 2], v[8 * g + 3])),
-                        fmaxf(fmaxf(v[8 * g + 4], v[8 * g + 5]), fmaxf(v[8 * g + 6], v[8 * g + 7])));
-        if (m > st.thr) {
+        const float m = fmaxf(fmaxf(fmaxf(v[8 * g], v[8 * g + 1]), fmaxf(v[8 * g + 2], v[8 * g + 3])),
+                              fmaxf(fmaxf(v[8 * g + 4], v[8 * g + 5]), fmaxf(v[8 * g + 6], v[8 * g + 7])));
+        if (__any_sync(0xffffffffu, m > st.thr)) {  // warp-uniform: some row has a candidate here
+          const float thr = st.thr;
+          int cnt = st.cnt;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            if (v[8 * g + e] > st.thr) {
-              myv[st.cnt] = v[8 * g + e];
-              myi[st.cnt] = col + 8 * g + e;
-              ++st.cnt;
+          for (int e = 0; e < 8; ++e) {  // predicated appends, no divergence
+            const float x = v[8 * g + e];
+            sts_pair_if_gt(x, thr, st.vb + cnt * 4, st.ib + cnt * 4, col + 8 * g + e);
+            cnt += (x > thr) ? 1 : 0;
+          }
+          st.cnt = cnt;
+          if (__any_sync(0xffffffffu, cnt > TRIG)) {
+            if (cnt > JOIN) {
+              const unsigned long long r = quad_shrink(st.thr, cnt, st.vb, st.ib);
+              st.thr = __uint_as_float(static_cast<unsigned>(r >> 32));
+              st.cnt = static_cast<int>(r & 0xffffffffu);
             }
           }
         }
-        unsigned need = __ballot_sync(0xffffffffu, st.cnt > C - 8);
-        while (need) {
-          const int src = __ffs(need) - 1;
-          need &= need - 1;
-          compact_row(st, c, src);
-        }
       }
-    }
+    });
   }
 
+  // Dump the raw lists; rows of a warp are written one after another so stores coalesce.
   __device__ static void end(State& st, const Params& P, const ItemCtx& c) {
     __syncwarp();
-    const int nch = P.n_chunks[c.p];
+    const int nch = P.n_sub[c.p];
+    const uint32_t wbase = smem_u32(c.smem) + static_cast<uint32_t>(c.warp_q * 32) * LDSW * 4;
 #pragma unroll 1
     for (int src = 0; src < 32; ++src) {
       const int row = c.rb * BM + c.warp_q * 32 + src;
       if (row >= c.n_rows) break;  // warp-uniform
       const int cnt_src = __shfl_sync(0xffffffffu, st.cnt, src);
-      float v;
-      int id, rank;
-      rank_row(c, src, cnt_src, v, id, rank);
-      if (rank < KP) {
-        const long long o = (static_cast<long long>(row) * nch + c.cc) * KP + rank;
-        P.out_val[c.p][o] = v;
-        P.out_idx[c.p][o] = id;
+      const long long o = (static_cast<long long>(row) * nch + c.sub) * C;
+      const uint32_t vb = wbase + static_cast<uint32_t>(src) * LDSW * 4;
+      const uint32_t ib = vb + kEpiThreads * LDSW * 4;
+#pragma unroll
+      for (int h = 0; h < C / 32; ++h) {
+        const int s = c.lane + 32 * h;
+        if (s < cnt_src) {
+          P.out_val[c.p][o + s] = lds_f32(vb + s * 4);
+          P.out_idx[c.p][o + s] = lds_s32(ib + s * 4);
+        }
       }
+      if (c.lane == 0) P.out_cnt[c.p][static_cast<long long>(row) * nch + c.sub] = cnt_src;
     }
     __syncwarp();
   }
@@ -206,16 +308,18 @@ struct EpiTopK {
 //   pz = sum_j pos_ij z_ij, cnt = sum_j pos_ij,  pos_ij = (idx_i == idx_j)  (or i == j when idx is null)
 // written per (row, column chunk); infonce_finalize merges chunks and forms loss and dtemp.
 // Everything is kept in log2 units (zt = z * log2 e) so the exponentials are single EX2s.
+// The labels of a tile's 256 columns are staged in shared memory once per tile.
 // ------------------------------------------------------------------------------------------
 struct EpiLse {
   struct Params {
     const float* temp;             // device scalar (nn.Parameter self.temp, models/xvlm.py:177)
     const long long* idx_rows[2];  // may be null: identity labels
     const long long* idx_cols[2];
-    float* part[2];                // [n_rows][n_chunks][5] = m2, l, w2, pz2, cnt
-    int n_chunks[2];
+    float* part[2];                // [n_rows][n_sub][5] = m2, l, w2, pz2, cnt
+    int n_sub[2];                  // partials per row: n_chunks * kWGs
   };
-  static constexpr int kSmemBytes = 0;
+  static constexpr int kWGs = 2;
+  static constexpr int kSmemBytes = 2 * BN * 8;
   struct State {
     float m, l, w, pz, cnt, sc;
     long long my_idx;
@@ -232,42 +336,54 @@ struct EpiLse {
   }
   __device__ static void tile(State& st, const Params& P, const ItemCtx& c, uint32_t taddr, int col0) {
     const long long* ic = P.idx_cols[c.p];
-#pragma unroll 1
-    for (int cb = 0; cb < BN; cb += 32) {
-      const int col = col0 + cb;
-      if (col >= c.n_cols) break;  // warp-uniform
-      float v[32];
-      tmem_ld_32x32(taddr + cb, v);
-      tmem_wait_ld();
+    const int n_cols = c.n_cols;
+    const uint32_t sidx = smem_u32(c.smem) + ((c.tile_n >> (kWGs - 1)) & 1u) * BN * 8;
+    if (ic != nullptr) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = col0 + c.et + h * kEpiThreads;
+        sts_s64(sidx + (c.et + h * kEpiThreads) * 8, j < n_cols ? __ldg(ic + j) : 0);
+      }
+      epi_bar_sync(c.wg);  // one barrier per tile; the staging buffers alternate tile by tile
+    }
+    const bool ragged = col0 + BN > n_cols;
+    const float sc = st.sc;
+    const long long my = st.my_idx;
+    const int row = c.row;
+    for_each_chunk(taddr, col0, n_cols, [&](float(&v)[32], int col) {
       float mx = -CUDART_INF_F;
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
-        v[e] = (col + e < c.n_cols) ? v[e] * st.sc : -CUDART_INF_F;
+        v[e] *= sc;
+        if (ragged && col + e >= n_cols) v[e] = -CUDART_INF_F;
         mx = fmaxf(mx, v[e]);
       }
       const float m_new = fmaxf(st.m, mx);
-      const float corr = exp2f(st.m - m_new);  // exp2(-inf) = 0 on the first chunk
-      float l = 0.f, w = 0.f;
+      const float corr = ex2_approx(st.m - m_new);  // ex2(-inf) = 0 on the first chunk
+      float l[4] = {0.f, 0.f, 0.f, 0.f}, w[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
-        const float p = exp2f(v[e] - m_new);
-        l += p;
-        w = fmaf(p, (col + e < c.n_cols) ? v[e] : 0.f, w);
+        const float p = ex2_approx(v[e] - m_new);
+        l[e & 3] += p;
+        w[e & 3] = fmaf(p, (ragged && col + e >= n_cols) ? 0.f : v[e], w[e & 3]);
       }
-      st.l = fmaf(st.l, corr, l);
-      st.w = fmaf(st.w, corr, w);
+      st.l = fmaf(st.l, corr, (l[0] + l[1]) + (l[2] + l[3]));
+      st.w = fmaf(st.w, corr, (w[0] + w[1]) + (w[2] + w[3]));
       st.m = m_new;
       if (ic != nullptr) {
+        const uint32_t sa = sidx + (col - col0) * 8;
+        float pz[2] = {0.f, 0.f}, pc[2] = {0.f, 0.f};
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-          if (col + e < c.n_cols && __ldg(ic + col + e) == st.my_idx) {
-            st.pz += v[e];
-            st.cnt += 1.f;
-          }
+          const bool pos = lds_s64(sa + e * 8) == my && !(ragged && col + e >= n_cols);
+          pz[e & 1] += pos ? v[e] : 0.f;
+          pc[e & 1] += pos ? 1.f : 0.f;
         }
+        st.pz += pz[0] + pz[1];
+        st.cnt += pc[0] + pc[1];
       } else {
-        const int d = c.row - col;  // identity labels: only the diagonal element
-        if (d >= 0 && d < 32 && c.row < c.n_cols) {
+        const int d = row - col;  // identity labels: only the diagonal element
+        if (d >= 0 && d < 32 && row < n_cols) {
 #pragma unroll
           for (int e = 0; e < 32; ++e)
             if (e == d) {
@@ -276,11 +392,11 @@ struct EpiLse {
             }
         }
       }
-    }
+    });
   }
   __device__ static void end(State& st, const Params& P, const ItemCtx& c) {
     if (c.row < c.n_rows) {
-      float* o = P.part[c.p] + (static_cast<long long>(c.row) * P.n_chunks[c.p] + c.cc) * 5;
+      float* o = P.part[c.p] + (static_cast<long long>(c.row) * P.n_sub[c.p] + c.sub) * 5;
       o[0] = st.m;
       o[1] = st.l;
       o[2] = st.w;
@@ -296,7 +412,8 @@ struct EpiLse {
 //   G'_ij = softmax_row(z)_ij + softmax_col(z)_ij - pos_ij (1/cnt_i + 1/cnt_j)      in [-2, 2]
 // written as a 16-bit strip [local rows][n_cols] that feeds the gradient product on the tensor
 // cores; the 1/(2 N temp) factor is applied in that product's epilogue in fp32.
-// lse / rcnt are in log2 units / reciprocals, produced by infonce_finalize.
+// lse / rcnt are in log2 units / reciprocals, produced by infonce_finalize.  The column-side
+// label, lse and 1/cnt of a tile's 256 columns are staged in shared memory once per tile.
 // ------------------------------------------------------------------------------------------
 struct EpiGrad {
   struct Params {
@@ -313,7 +430,9 @@ struct EpiGrad {
     int nrow[2];                // rows in the strip
     int fmt;                    // 0 fp16, 1 bf16
   };
-  static constexpr int kSmemBytes = 0;
+  static constexpr int kWGs = 2;
+  static constexpr int kBufBytes = BN * 16;  // idx (8) + lse (4) + rcnt (4) per column
+  static constexpr int kSmemBytes = 2 * kBufBytes;
   struct State {
     float sc, lse, rc;
     long long my_idx;
@@ -332,33 +451,44 @@ struct EpiGrad {
   __device__ static void tile(State& st, const Params& P, const ItemCtx& c, uint32_t taddr, int col0) {
     const long long* ic = P.idx_cols[c.p];
     const float* lc = P.lse_cols[c.p];
-    const float* rc = P.rcnt_cols[c.p];
-    const long long ld = P.ld[c.p];
+    const float* rcp = P.rcnt_cols[c.p];
+    const int ld = static_cast<int>(P.ld[c.p]);
+    const int n_cols = c.n_cols;
+    const uint32_t sbuf = smem_u32(c.smem) + ((c.tile_n >> (kWGs - 1)) & 1u) * kBufBytes;
+    const uint32_t s_idx = sbuf, s_lse = sbuf + BN * 8, s_rc = sbuf + BN * 12;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int t = c.et + h * kEpiThreads;
+      const int j = col0 + t;
+      const bool in = j < n_cols;
+      sts_s64(s_idx + t * 8, in ? (ic != nullptr ? __ldg(ic + j) : static_cast<long long>(j)) : 0);
+      sts_f32(s_lse + t * 4, in ? __ldg(lc + j) : CUDART_INF_F);  // exp2(z - inf) = 0 for pad columns
+      sts_f32(s_rc + t * 4, in ? __ldg(rcp + j) : 0.f);
+    }
+    epi_bar_sync(c.wg);
     uint16_t* srow = reinterpret_cast<uint16_t*>(P.strip[c.p]) +
                      static_cast<long long>(c.row - P.row0[c.p]) * ld;
-#pragma unroll 1
-    for (int cb = 0; cb < BN; cb += 32) {
-      const int col = col0 + cb;
-      if (col >= ld) break;  // warp-uniform (ld = n_cols rounded up to 8; pad columns written as 0)
-      float v[32];
-      tmem_ld_32x32(taddr + cb, v);
-      tmem_wait_ld();
+    const bool ragged = col0 + BN > n_cols;
+    const float sc = st.sc, lse_r = st.lse, rc_r = st.rc;
+    const long long my = st.my_idx;
+    const bool ok = st.ok;
+    const int fmt = P.fmt;
+    // ld = n_cols rounded up to 8; pad columns are written as 0
+    for_each_chunk(taddr, col0, ld, [&](float(&v)[32], int col) {
+      const int cl = col - col0;
       uint32_t packed[16];
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
-        const int j = col + e;
-        float g = 0.f;
-        if (st.ok && j < c.n_cols) {
-          const float z = v[e] * st.sc;
-          g = exp2f(z - st.lse) + exp2f(z - __ldg(lc + j));
-          const long long cj = (ic != nullptr) ? __ldg(ic + j) : static_cast<long long>(j);
-          if (cj == st.my_idx) g -= st.rc + __ldg(rc + j);
-        }
+        const float z = v[e] * sc;
+        float g = ex2_approx(z - lse_r) + ex2_approx(z - lds_f32(s_lse + (cl + e) * 4));
+        const bool pos = lds_s64(s_idx + (cl + e) * 8) == my;
+        g -= pos ? (rc_r + lds_f32(s_rc + (cl + e) * 4)) : 0.f;
+        if (ragged && col + e >= n_cols) g = 0.f;
         v[e] = g;
       }
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
-        if (P.fmt == 0) {
+        if (fmt == 0) {
           __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
           packed[e] = *reinterpret_cast<uint32_t*>(&h);
         } else {
@@ -366,7 +496,7 @@ struct EpiGrad {
           packed[e] = *reinterpret_cast<uint32_t*>(&h);
         }
       }
-      if (st.ok) {
+      if (ok) {
         if (col + 32 <= ld) {
           uint4* o = reinterpret_cast<uint4*>(srow + col);  // ld % 8 == 0 and col % 32 == 0: 16-byte aligned
 #pragma unroll
@@ -379,7 +509,7 @@ struct EpiGrad {
               srow[col + e] = static_cast<uint16_t>((packed[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
         }
       }
-    }
+    });
   }
 };
 

@@ -5,8 +5,10 @@
 //
 // One persistent CTA per SM.  Warp 0 feeds shared memory with TMA (128-byte swizzle), warp 1
 // issues tcgen05.mma (128 x 256 x 16, fp32 accumulators in TMEM, two 256-column buffers so the
-// epilogue of tile t overlaps the MMAs of tile t+1), warps 2..5 are the epilogue: thread <-> one
-// row of the tile (TMEM lane), so every per-row reduction the reference performs
+// epilogue of tile t overlaps the MMAs of tile t+1), the remaining warps are the epilogue: one or
+// two warpgroups (Epi::kWGs); with two, warpgroup g drains the tiles whose TMEM buffer is g, so a
+// single warp per scheduler never has to keep pace with the tensor core alone.  Epilogue thread
+// <-> one row of the tile (TMEM lane), so every per-row reduction the reference performs
 // (top-k, log-sum-exp, min/max, label sums) is thread-local and the N x M matrix never has to
 // exist in HBM.  The epilogue is a policy class (see epilogues.cuh).
 //
@@ -21,8 +23,8 @@ constexpr int BM = 128;       // rows per tile   (TMEM lanes)
 constexpr int BN = 256;       // columns per tile (TMEM columns per accumulator buffer)
 constexpr int BK = 64;        // K elements per pipeline stage = one 128-byte swizzle atom
 constexpr int UMMA_K = 16;    // K per tcgen05.mma for 16-bit operands
-constexpr int kGemmThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kEpiThreads = 128;  // per epilogue warpgroup
+constexpr int gemm_threads(int wgs) { return 64 + kEpiThreads * wgs; }
 constexpr int kAStageBytes = BM * BK * 2;
 constexpr int kBStageBytes = BN * BK * 2;
 constexpr int kStageBytes = kAStageBytes + kBStageBytes;
@@ -55,12 +57,15 @@ struct ItemCtx {
   int p;        // problem index
   int rb;       // row block (absolute)
   int cc;       // column chunk
+  int sub;      // partial-result slot of this (chunk, warpgroup): cc * kWGs + wg
+  int wg;       // epilogue warpgroup
   int row;      // absolute row owned by this thread
   int n_rows, n_cols;
   int et;       // epilogue thread id 0..127 (== row within tile)
   int warp_q;   // TMEM lane quadrant of this warp
   int lane;
-  uint8_t* smem;  // epilogue-private shared memory (Epi::kSmemBytes)
+  uint32_t tile_n;  // running tile counter of this CTA (parity selects double buffers)
+  uint8_t* smem;    // epilogue-private shared memory (Epi::kSmemBytes)
 };
 
 __device__ __forceinline__ void decode_item(const SimLaunch& L, int item, int& p, int& rb, int& ct0,
@@ -85,15 +90,16 @@ __device__ __forceinline__ void decode_item(const SimLaunch& L, int item, int& p
 }
 
 template <class Epi, int kStages>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(gemm_threads(Epi::kWGs), 1)
 sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typename Epi::Params EP) {
   extern __shared__ uint8_t smem_raw[];
   // 128-byte swizzle atoms need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* stage_base = smem;
+  constexpr int kWGs = Epi::kWGs;
   uint8_t* epi_smem = smem + kStages * kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Epi::kSmemBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + kWGs * Epi::kSmemBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tfull_bar = bars + 2 * kStages;
@@ -191,12 +197,13 @@ sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typ
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps)
+    // ------------------------------------------------------------------ epilogue warpgroups
     ItemCtx c;
     c.warp_q = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
     c.lane = lane;
     c.et = c.warp_q * 32 + lane;
-    c.smem = epi_smem;
+    c.wg = (warp - 2) >> 2;
+    c.smem = epi_smem + c.wg * Epi::kSmemBytes;
     uint32_t tile_n = 0;
     typename Epi::State st;
     for (int item = blockIdx.x; item < L.n_items; item += gridDim.x) {
@@ -205,13 +212,16 @@ sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typ
       c.n_rows = L.prob[c.p].n_rows;
       c.n_cols = L.prob[c.p].n_cols;
       c.row = c.rb * BM + c.et;
+      c.sub = c.cc * kWGs + c.wg;
       Epi::begin(st, EP, c);
       for (int ct = ct0; ct < ct1; ++ct, ++tile_n) {
+        if (kWGs == 2 && (tile_n & 1u) != static_cast<uint32_t>(c.wg)) continue;
         const uint32_t buf = tile_n & 1u;
         const uint32_t use = tile_n >> 1;
         mbar_wait(&tfull_bar[buf], use & 1u, 400 + buf);
         tc_fence_after();
         const uint32_t taddr = tmem_base + buf * BN + (static_cast<uint32_t>(c.warp_q * 32) << 16);
+        c.tile_n = tile_n;
         Epi::tile(st, EP, c, taddr, ct * BN);
         tc_fence_before();
         mbar_arrive(&tempty_bar[buf]);
@@ -227,7 +237,8 @@ sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typ
 
 template <class Epi, int kStages>
 constexpr size_t sim_gemm_smem_bytes() {
-  return 1024 + static_cast<size_t>(kStages) * kStageBytes + Epi::kSmemBytes + (2 * kStages + 4) * 8 + 16;
+  return 1024 + static_cast<size_t>(kStages) * kStageBytes + Epi::kWGs * Epi::kSmemBytes +
+         (2 * kStages + 4) * 8 + 16;
 }
 
 }  // namespace leccr

@@ -116,6 +116,84 @@ __global__ void prep_rows_kernel(const float* __restrict__ src, long long ld_src
   }
 }
 
+// Fast path of prep_rows for D % 128 == 0, D <= 1024, 16-byte aligned rows: one warp per row, each
+// lane holds D/128 float4 in registers (one pass over HBM even when normalising), 8-byte stores.
+template <int FMT>
+__global__ void prep_rows_vec_kernel(const float* __restrict__ src, long long ld_src, int n, int D,
+                                     int normalize, int layout, uint16_t* __restrict__ dst,
+                                     long long ld_dst, float* __restrict__ rn_hi,
+                                     float* __restrict__ rn_lo, float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const int nv = D >> 7;  // float4 per lane
+  const float4* x4 = reinterpret_cast<const float4*>(src + static_cast<long long>(row) * ld_src);
+  float4 x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < nv) x[i] = __ldg(x4 + lane + 32 * i);
+  float inv = 1.f;
+  if (normalize) {
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) ss += x[i].x * x[i].x + x[i].y * x[i].y + x[i].z * x[i].z + x[i].w * x[i].w;
+    ss = warp_sum(ss);
+    inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  }
+  uint16_t* o = dst + static_cast<long long>(row) * ld_dst;
+  float nh = 0.f, nl = 0.f, amax = 0.f;
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i < nv) {
+      const float t[4] = {x[i].x * inv, x[i].y * inv, x[i].z * inv, x[i].w * inv};
+      uint16_t h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        h[j] = f32_to_16<FMT>(t[j]);
+        const float hf = f16_to_32<FMT>(h[j]);
+        float r = t[j] - hf;
+        bad |= !isfinite(hf);
+        amax = fmaxf(amax, fabsf(t[j]));
+        nh = fmaf(hf, hf, nh);
+        l[j] = 0;
+        if (layout != 0) {
+          l[j] = f32_to_16<FMT>(r);
+          r -= f16_to_32<FMT>(l[j]);
+        }
+        nl = fmaf(r, r, nl);
+      }
+      const int d = 4 * (lane + 32 * i);
+      const uint2 hv = make_uint2(h[0] | (static_cast<uint32_t>(h[1]) << 16), h[2] | (static_cast<uint32_t>(h[3]) << 16));
+      const uint2 lv = make_uint2(l[0] | (static_cast<uint32_t>(l[1]) << 16), l[2] | (static_cast<uint32_t>(l[3]) << 16));
+      *reinterpret_cast<uint2*>(o + d) = hv;
+      if (layout == 1) {
+        *reinterpret_cast<uint2*>(o + D + d) = lv;
+        *reinterpret_cast<uint2*>(o + 2 * D + d) = hv;
+      } else if (layout == 2) {
+        *reinterpret_cast<uint2*>(o + D + d) = hv;
+        *reinterpret_cast<uint2*>(o + 2 * D + d) = lv;
+      }
+    }
+  }
+  nh = warp_sum(nh);
+  nl = warp_sum(nl);
+  amax = warp_max(amax);
+  const unsigned anybad = __ballot_sync(0xffffffffu, bad);
+  if (lane == 0) {
+    const float a = sqrtf(nh), b = sqrtf(nl);
+    if (rn_hi) rn_hi[row] = a;
+    if (rn_lo) rn_lo[row] = b;
+    if (stats) {
+      atomicMax(reinterpret_cast<unsigned*>(stats) + 0, __float_as_uint(a));
+      atomicMax(reinterpret_cast<unsigned*>(stats) + 1, __float_as_uint(b));
+      atomicMax(reinterpret_cast<unsigned*>(stats) + 2, __float_as_uint(amax));
+      if (anybad) atomicMax(reinterpret_cast<unsigned*>(stats) + 3, __float_as_uint(1.f));
+    }
+  }
+}
+
 // Row norms / maxima of an operand that is already 16-bit (e.g. a bf16-stored gallery).
 template <int FMT>
 __global__ void stats_rows16_kernel(const uint16_t* __restrict__ src, long long ld_src, int n, int D,
@@ -164,6 +242,17 @@ __global__ void transpose16_kernel(const uint16_t* __restrict__ src, long long l
   }
 }
 
+// Deterministic split-K reduction: out[i] = sum_s parts[s][i] in a fixed order.
+__global__ void splitk_reduce_kernel(const float* __restrict__ parts, int n_splits, long long plane,
+                                     float* __restrict__ out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < plane;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float acc = 0.f;
+    for (int sp = 0; sp < n_splits; ++sp) acc += parts[static_cast<long long>(sp) * plane + i];
+    out[i] = acc;
+  }
+}
+
 // --------------------------------------------------------------------------------
 // infonce_finalize: merge the per-chunk partials of EpiLse, emit per-row lse (log2 units) and
 // 1/cnt for the backward, and the scalars
@@ -178,33 +267,38 @@ struct FinalizeLseParams {
   float* lse2[2];
   float* rcnt[2];
   const float* temp;
-  float* out;  // [0] loss, [1] dtemp, [2] loss_p0, [3] loss_p1
+  float* out;        // [0] loss, [1] dtemp, [2] loss_p0, [3] loss_p1
+  double* scratch;   // [4] partial sums + ticket counter (as a 5th double slot), zeroed by the host side
 };
 
+// One thread per (orientation, row); block partial sums are combined with double atomics and the
+// last block to finish (ticket) writes the scalars.
 __global__ void infonce_finalize_kernel(const FinalizeLseParams P) {
-  __shared__ double red[4][32];
+  __shared__ double red[4][8];
+  __shared__ bool is_last;
   double acc[4] = {0.0, 0.0, 0.0, 0.0};  // loss_p0, loss_p1, dt_p0, dt_p1
-  for (int p = 0; p < 2; ++p) {
-    for (int r = threadIdx.x; r < P.n[p]; r += blockDim.x) {
-      const float* q = P.part[p] + static_cast<long long>(r) * P.nch[p] * 5;
-      float m = -CUDART_INF_F;
-      for (int c = 0; c < P.nch[p]; ++c) m = fmaxf(m, q[5 * c]);
-      float l = 0.f, w = 0.f, pz = 0.f, cnt = 0.f;
-      for (int c = 0; c < P.nch[p]; ++c) {
-        const float s = exp2f(q[5 * c] - m);
-        l = fmaf(q[5 * c + 1], s, l);
-        w = fmaf(q[5 * c + 2], s, w);
-        pz += q[5 * c + 3];
-        cnt += q[5 * c + 4];
-      }
-      const float lse2 = m + log2f(l);
-      const float rc = cnt > 0.f ? 1.f / cnt : 0.f;
-      P.lse2[p][r] = lse2;
-      P.rcnt[p][r] = rc;
-      // natural-log units: multiply log2-domain quantities by ln 2
-      acc[p] += 0.6931471805599453 * (static_cast<double>(lse2) - static_cast<double>(pz) * rc);
-      acc[2 + p] += 0.6931471805599453 * (static_cast<double>(w) / l - static_cast<double>(pz) * rc);
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = gid >= P.n[0] ? 1 : 0;
+  const int r = p ? gid - P.n[0] : gid;
+  if (r < P.n[p]) {
+    const float* q = P.part[p] + static_cast<long long>(r) * P.nch[p] * 5;
+    float m = -CUDART_INF_F;
+    for (int c = 0; c < P.nch[p]; ++c) m = fmaxf(m, q[5 * c]);
+    float l = 0.f, w = 0.f, pz = 0.f, cnt = 0.f;
+    for (int c = 0; c < P.nch[p]; ++c) {
+      const float s = exp2f(q[5 * c] - m);
+      l = fmaf(q[5 * c + 1], s, l);
+      w = fmaf(q[5 * c + 2], s, w);
+      pz += q[5 * c + 3];
+      cnt += q[5 * c + 4];
     }
+    const float lse2 = m + log2f(l);
+    const float rc = cnt > 0.f ? 1.f / cnt : 0.f;
+    P.lse2[p][r] = lse2;
+    P.rcnt[p][r] = rc;
+    // natural-log units: multiply log2-domain quantities by ln 2
+    acc[p] = 0.6931471805599453 * (static_cast<double>(lse2) - static_cast<double>(pz) * rc);
+    acc[2 + p] = 0.6931471805599453 * (static_cast<double>(w) / l - static_cast<double>(pz) * rc);
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int k = 0; k < 4; ++k) {
@@ -214,14 +308,24 @@ __global__ void infonce_finalize_kernel(const FinalizeLseParams P) {
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double tot[4] = {0, 0, 0, 0};
     const int nw = blockDim.x >> 5;
-    for (int k = 0; k < 4; ++k)
-      for (int w = 0; w < nw; ++w) tot[k] += red[k][w];
-    const double l0 = P.n[0] > 0 ? tot[0] / P.n[0] : 0.0;
-    const double l1 = P.n[1] > 0 ? tot[1] / P.n[1] : 0.0;
-    const double d0 = P.n[0] > 0 ? tot[2] / P.n[0] : 0.0;
-    const double d1 = P.n[1] > 0 ? tot[3] / P.n[1] : 0.0;
+    for (int k = 0; k < 4; ++k) {
+      double t = 0.0;
+      for (int w = 0; w < nw; ++w) t += red[k][w];
+      atomicAdd(P.scratch + k, t);
+    }
+    __threadfence();
+    const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(P.scratch + 4), 1u);
+    is_last = ticket == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    volatile double* sc = P.scratch;
+    const double l0 = P.n[0] > 0 ? sc[0] / P.n[0] : 0.0;
+    const double l1 = P.n[1] > 0 ? sc[1] / P.n[1] : 0.0;
+    const double d0 = P.n[0] > 0 ? sc[2] / P.n[0] : 0.0;
+    const double d1 = P.n[1] > 0 ? sc[3] / P.n[1] : 0.0;
     const double temp = static_cast<double>(*P.temp);
     P.out[0] = static_cast<float>(0.5 * (l0 + l1));
     P.out[1] = static_cast<float>(-0.5 * (d0 + d1) / temp);
@@ -232,7 +336,8 @@ __global__ void infonce_finalize_kernel(const FinalizeLseParams P) {
 
 // --------------------------------------------------------------------------------
 // topk_finalize: one warp per query row.
-//   1. merge the per-chunk candidate lists of EpiTopK into the row's best KP (approximate scores)
+//   1. select the row's best KP among the raw candidate lists EpiTopK left per column chunk
+//      (threshold by warp-wide bisection on the score, then a 32-wide rank sort)
 //   2. emit the top-k (score, column)
 //   3. optional exact Recall support: for every ground-truth column g of the row compute the exact
 //      score t_g (fp32 dot of the original inputs) and decide rank_g = #{j : t_j > t_g} from the
@@ -241,11 +346,15 @@ __global__ void infonce_finalize_kernel(const FinalizeLseParams P) {
 //      If the list cannot decide (GT score inside the band of the list's last entry while fewer
 //      than kRankCap definitely-greater items are known) the row is flagged for exact_rank_rows.
 // --------------------------------------------------------------------------------
-constexpr int kRankCap = 10;  // Recall@1/5/10 only ever asks whether rank < 10
+constexpr int kRankCap = 10;   // Recall@1/5/10 only ever asks whether rank < 10
+constexpr int kListCap = 64;    // == EpiTopK::C: two list entries per lane
+constexpr int kMaxChunks = 8;   // partial lists per row (column chunks x epilogue warpgroups)
+constexpr int kFinalizeWarps = 8;
 
 struct TopkFinalizeParams {
-  const float* cand_val;  // [n_rows][n_chunks][KP]
+  const float* cand_val;  // [n_rows][n_chunks][kListCap]
   const int* cand_idx;
+  const int* cand_cnt;    // [n_rows][n_chunks]
   int n_rows, n_cols, n_chunks, KP, k;
   float* topk_val;  // [n_rows][k]
   int* topk_idx;
@@ -262,7 +371,8 @@ struct TopkFinalizeParams {
   const float* col_stats;   // kStatWords of the column operand
   float acc_slack;          // fp32 accumulation slack coefficient (times ||hi_r|| ||hi_c||max)
   int* rank;                // [n_rows]  exact when < kRankCap (else a lower bound >= kRankCap)
-  int* flag;                // [n_rows]  1: undecided, needs exact_rank_rows
+  int* flag_list;           // rows the list could not decide (need exact_rank_rows)
+  int* flag_count;          // [1] zeroed before the launch
   float* gt_score;          // [nnz] exact score of every ground-truth pair (optional)
 };
 
@@ -270,6 +380,31 @@ __device__ __forceinline__ float load_x(const void* base, long long off, int dty
   if (dtype == 0) return __ldg(reinterpret_cast<const float*>(base) + off);
   const uint16_t u = __ldg(reinterpret_cast<const uint16_t*>(base) + off);
   return dtype == 1 ? f16_to_32<0>(u) : f16_to_32<1>(u);
+}
+
+// A row of the original operands held across a warp: lane l keeps elements 4*(l + 32 i) .. +3.
+// Fast path for fp32 with D % 128 == 0, D <= 512 and 16-byte aligned rows.
+struct RowRegs {
+  float4 q[4];
+};
+__device__ __forceinline__ bool vec_ok(const void* base, long long ld, int D, int dtype) {
+  return dtype == 0 && (D & 127) == 0 && D <= 512 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0;
+}
+__device__ __forceinline__ void load_row_regs(RowRegs& r, const void* base, long long ld, int row, int D, int lane) {
+  const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + static_cast<long long>(row) * ld);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r.q[i] = (i * 128 < D) ? __ldg(p + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ float dot_row_regs(const RowRegs& a, const RowRegs& b) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    s = fmaf(a.q[i].x, b.q[i].x, s);
+    s = fmaf(a.q[i].y, b.q[i].y, s);
+    s = fmaf(a.q[i].z, b.q[i].z, s);
+    s = fmaf(a.q[i].w, b.q[i].w, s);
+  }
+  return warp_sum(s);
 }
 
 // exact fp32 dot of row r of rows_x with row c of cols_x, cooperatively by one warp
@@ -282,54 +417,123 @@ __device__ __forceinline__ float warp_dot(const void* rows_x, long long ld_rows,
   return warp_sum(s);
 }
 
-__global__ void topk_finalize_kernel(const TopkFinalizeParams P) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(kFinalizeWarps * 32) topk_finalize_kernel(const TopkFinalizeParams P) {
+  __shared__ float s_val[kFinalizeWarps][32];
+  __shared__ int s_idx[kFinalizeWarps][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int row = blockIdx.x * kFinalizeWarps + wib;
   if (row >= P.n_rows) return;
-  const int total = P.n_chunks * P.KP;
-  const float* cv = P.cand_val + static_cast<long long>(row) * total;
-  const int* ci = P.cand_idx + static_cast<long long>(row) * total;
-  // Each lane keeps up to 8 candidates (total <= 256) in registers; selection by repeated warp argmax.
-  float v[8];
-  int id[8];
-#pragma unroll
-  for (int t = 0; t < 8; ++t) {
-    const int e = lane + 32 * t;
-    v[t] = (e < total) ? cv[e] : -CUDART_INF_F;
-    id[t] = (e < total) ? ci[e] : -1;
-    if (id[t] < 0) v[t] = -CUDART_INF_F;
-  }
-  // merged list kept by lane l < KP: (mv, mi)
-  float mv = -CUDART_INF_F;
-  int mi = -1;
   const int KP = P.KP;
-  for (int s = 0; s < KP; ++s) {
-    float bv = -CUDART_INF_F;
-    int bi = 0x7fffffff;
+  const int per_lane = 2 * P.n_chunks;  // two slots per partial list and lane
+  const long long cbase = static_cast<long long>(row) * P.n_chunks;
+  // all loads are issued before any is consumed: list lengths (one lane each), then every slot
+  const int my_cnt = lane < P.n_chunks ? __ldg(P.cand_cnt + cbase + lane) : 0;
+  float v[2 * kMaxChunks];
+  int id[2 * kMaxChunks];
 #pragma unroll
-    for (int t = 0; t < 8; ++t)
-      if (id[t] >= 0 && (v[t] > bv || (v[t] == bv && id[t] < bi))) {
-        bv = v[t];
-        bi = id[t];
-      }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > bv || (ov == bv && oi < bi)) {
-        bv = ov;
-        bi = oi;
-      }
-    }
-    if (bi == 0x7fffffff) break;  // exhausted (warp-uniform)
-#pragma unroll
-    for (int t = 0; t < 8; ++t)
-      if (id[t] == bi) id[t] = -1;  // a column appears once per row
-    if (lane == s) {
-      mv = bv;
-      mi = bi;
+  for (int t = 0; t < 2 * kMaxChunks; ++t) {
+    v[t] = -CUDART_INF_F;
+    id[t] = -1;
+    if (t < per_lane) {
+      v[t] = __ldg(P.cand_val + (cbase + (t >> 1)) * kListCap + lane + 32 * (t & 1));
+      id[t] = __ldg(P.cand_idx + (cbase + (t >> 1)) * kListCap + lane + 32 * (t & 1));
     }
   }
+  float gmax = -CUDART_INF_F, gmin = CUDART_INF_F;
+  int n_loc = 0;
+#pragma unroll
+  for (int t = 0; t < 2 * kMaxChunks; ++t) {
+    const int cnt_t = __shfl_sync(0xffffffffu, my_cnt, t >> 1);
+    if (t < per_lane && lane + 32 * (t & 1) < cnt_t) {
+      gmax = fmaxf(gmax, v[t]);
+      gmin = fminf(gmin, v[t]);
+      ++n_loc;
+    } else {
+      v[t] = -CUDART_INF_F;
+      id[t] = -1;
+    }
+  }
+  gmax = warp_max(gmax);
+  gmin = warp_min(gmin);
+  const int n_tot = __reduce_add_sync(0xffffffffu, n_loc);
+  // threshold: KP <= #{v > lo} <= 32 (or everything when there are at most 32 candidates)
+  uint32_t lo_k = f32_key(-CUDART_INF_F), hi_k = f32_key(gmax);
+  int c_lo = n_tot;
+  bool first = true;
+  for (int it = 0; it < 40; ++it) {
+    if (c_lo <= 32 || hi_k - lo_k <= 1u) break;
+    uint32_t mid_k = lo_k + ((hi_k - lo_k) >> 1);
+    if (first) {
+      const uint32_t vk = f32_key(gmin);
+      if (vk > lo_k && vk < hi_k) mid_k = vk;
+      first = false;
+    }
+    const float mid = key_f32(mid_k);
+    int cm = 0;
+#pragma unroll
+    for (int t = 0; t < 2 * kMaxChunks; ++t) cm += (id[t] >= 0 && v[t] > mid) ? 1 : 0;
+    cm = __reduce_add_sync(0xffffffffu, cm);
+    if (cm >= KP) {
+      lo_k = mid_k;
+      c_lo = cm;
+    } else {
+      hi_k = mid_k;
+    }
+  }
+  const bool tie = c_lo > 32;
+  const float lo = key_f32(lo_k);
+  const float keep_thr = tie ? key_f32(hi_k) : lo;
+  s_val[wib][lane] = -CUDART_INF_F;
+  s_idx[wib][lane] = -1;
+  __syncwarp();
+  int base = 0;
+  const unsigned lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int t = 0; t < 2 * kMaxChunks; ++t) {
+    const bool sel = id[t] >= 0 && v[t] > keep_thr;
+    const unsigned m = __ballot_sync(0xffffffffu, sel);
+    const int pos = base + __popc(m & lt_mask);
+    if (sel && pos < 32) {
+      s_val[wib][pos] = v[t];
+      s_idx[wib][pos] = id[t];
+    }
+    base += __popc(m);
+  }
+  if (tie) {  // more than 32 equal scores at the threshold: any of them completes the list
+#pragma unroll
+    for (int t = 0; t < 2 * kMaxChunks; ++t) {
+      const bool sel = id[t] >= 0 && !(v[t] > keep_thr) && v[t] > lo;
+      const unsigned m = __ballot_sync(0xffffffffu, sel);
+      const int pos = base + __popc(m & lt_mask);
+      if (sel && pos < 32) {
+        s_val[wib][pos] = v[t];
+        s_idx[wib][pos] = id[t];
+      }
+      base += __popc(m);
+    }
+  }
+  __syncwarp();
+  const float cv = s_val[wib][lane];
+  const int ci = s_idx[wib][lane];
+  int rk = 0;
+#pragma unroll
+  for (int l = 0; l < 32; ++l) {
+    const float ov = __shfl_sync(0xffffffffu, cv, l);
+    const int oi = __shfl_sync(0xffffffffu, ci, l);
+    // descending score; ties: lower column first; empty slots (idx -1) last
+    const bool before = (oi >= 0) && (ci < 0 || ov > cv || (ov == cv && oi < ci));
+    rk += (before && l != lane) ? 1 : 0;
+  }
+  if (ci < 0) rk = 32 + lane;  // keep empties out of the way
+  __syncwarp();
+  if (rk < 32) {
+    s_val[wib][rk] = cv;
+    s_idx[wib][rk] = ci;
+  }
+  __syncwarp();
+  const int n_sorted = __popc(__ballot_sync(0xffffffffu, ci >= 0));
+  float mv = (lane < n_sorted && lane < KP) ? s_val[wib][lane] : -CUDART_INF_F;
+  int mi = (lane < n_sorted && lane < KP) ? s_idx[wib][lane] : -1;
   if (lane < P.k) {
     P.topk_val[static_cast<long long>(row) * P.k + lane] = mv;
     P.topk_idx[static_cast<long long>(row) * P.k + lane] = mi;
@@ -346,9 +550,19 @@ __global__ void topk_finalize_kernel(const TopkFinalizeParams P) {
   int best = 0x7fffffff;
   int undecided = 0;
   const int g0 = P.gt_off[row], g1 = P.gt_off[row + 1];
+  const bool fast = vec_ok(P.rows_x, P.ld_rows, P.D, P.x_dtype) && vec_ok(P.cols_x, P.ld_cols, P.D, P.x_dtype);
+  RowRegs qrow;
+  if (fast) load_row_regs(qrow, P.rows_x, P.ld_rows, row, P.D, lane);
   for (int gi = g0; gi < g1; ++gi) {
     const int g = P.gt_ids[gi];
-    const float tg = warp_dot(P.rows_x, P.ld_rows, row, P.cols_x, P.ld_cols, g, P.D, P.x_dtype, lane);
+    float tg;
+    if (fast) {
+      RowRegs crow;
+      load_row_regs(crow, P.cols_x, P.ld_cols, g, P.D, lane);
+      tg = dot_row_regs(qrow, crow);
+    } else {
+      tg = warp_dot(P.rows_x, P.ld_rows, row, P.cols_x, P.ld_cols, g, P.D, P.x_dtype, lane);
+    }
     if (P.gt_score != nullptr && lane == 0) P.gt_score[gi] = tg;
     const bool in_list = (lane < KP) && (mi >= 0) && (mi != g);
     const bool def_gt = in_list && (mv > tg + eps);
@@ -365,28 +579,37 @@ __global__ void topk_finalize_kernel(const TopkFinalizeParams P) {
         const int src = __ffs(amb_mask) - 1;
         amb_mask &= amb_mask - 1;
         const int j = __shfl_sync(0xffffffffu, mi, src);
-        const float tj = warp_dot(P.rows_x, P.ld_rows, row, P.cols_x, P.ld_cols, j, P.D, P.x_dtype, lane);
+        float tj;
+        if (fast) {
+          RowRegs crow;
+          load_row_regs(crow, P.cols_x, P.ld_cols, j, P.D, lane);
+          tj = dot_row_regs(qrow, crow);
+        } else {
+          tj = warp_dot(P.rows_x, P.ld_rows, row, P.cols_x, P.ld_cols, j, P.D, P.x_dtype, lane);
+        }
         cnt += (tj > tg) ? 1 : 0;
       }
     }
     best = min(best, cnt);
   }
   if (lane == 0) {
-    // a decided GT with rank < cap makes undecided siblings irrelevant only if it already has rank 0
-    const int f = (undecided && best > 0) ? 1 : 0;
-    P.rank[row] = (best == 0x7fffffff) ? kRankCap : best;
-    P.flag[row] = f;
+    // a decided GT makes undecided siblings irrelevant only if it already has rank 0
+    const bool flagged = undecided && best > 0;
+    const int rk_out = (best == 0x7fffffff) ? kRankCap : best;
+    P.rank[row] = rk_out;
+    if (flagged) P.flag_list[atomicAdd(P.flag_count, 1)] = row;
   }
 }
 
 // Exact fallback for flagged rows: rank = min_g #{j : t_j > t_g} with every score an fp32 dot.
-// One block per flagged row (grid-stride over rows; unflagged rows cost one load).
+// One block per flagged row (grid-stride over the list; normally the list is empty).
 __global__ void exact_rank_rows_kernel(const TopkFinalizeParams P) {
   __shared__ float s_tg[16];
   __shared__ int s_cnt[16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int row = blockIdx.x; row < P.n_rows; row += gridDim.x) {
-    if (P.flag[row] == 0) continue;  // block-uniform
+  const int n_flagged = *P.flag_count;
+  for (int fi = blockIdx.x; fi < n_flagged; fi += gridDim.x) {
+    const int row = P.flag_list[fi];
     const int g0 = P.gt_off[row];
     const int ng = min(P.gt_off[row + 1] - g0, 16);
     __syncthreads();
@@ -420,7 +643,6 @@ __global__ void exact_rank_rows_kernel(const TopkFinalizeParams P) {
       int best = 0x7fffffff;
       for (int gi = 0; gi < ng; ++gi) best = min(best, s_cnt[gi]);
       P.rank[row] = best == 0x7fffffff ? kRankCap : best;
-      P.flag[row] = 0;
     }
   }
 }

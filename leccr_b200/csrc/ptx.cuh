@@ -40,13 +40,28 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return ok;
 }
-// Bounded wait: a protocol bug must not hang the GPU (a hung box is a lost round), so after
-// ~2 s of spinning the kernel reports where it was stuck and traps.
+// try_wait with a suspend-time hint: the thread sleeps in hardware (no issue slots burnt) until the
+// phase completes or ~hint_ns elapse.
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a protocol bug must not hang the GPU (a hung box is a lost round), so after a few
+// seconds of waiting the kernel reports where it was stuck and traps.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {  // try_wait itself suspends the thread for a HW-defined window
+    if (++spins > 200000000u) {
       printf("leccr: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag,
              (int)blockIdx.x, (int)threadIdx.x, parity);
       __trap();
@@ -164,6 +179,78 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
+}
+
+// tcgen05.wait::ld that also names the destination registers, so the compiler cannot schedule
+// their consumers above the wait.
+__device__ __forceinline__ void tmem_wait_ld_regs(float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]),
+                 "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]),
+                 "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]),
+                 "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]),
+                 "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+// Shared-memory accesses through 32-bit shared-window addresses (keeps LDS/STS instead of generic LD/ST).
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ long long lds_s64(uint32_t a) {
+  long long v;
+  asm volatile("ld.shared.s64 %0, [%1];" : "=l"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_s32(uint32_t a, int v) {
+  asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_s64(uint32_t a, long long v) {
+  asm volatile("st.shared.s64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+}
+// Barrier among the 128 threads of one epilogue warpgroup (barrier 0 is __syncthreads).
+__device__ __forceinline__ void epi_bar_sync(int wg) {
+  asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");
+}
+// exp2 on the SFU without the denormal fix-up sequence (arguments here are <= 0 or modest).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// if (x > thr) { list_v[slot] = x; list_i[slot] = idx; } as predicated stores (no branch).
+__device__ __forceinline__ void sts_pair_if_gt(float x, float thr, uint32_t addr_v, uint32_t addr_i, int idx) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.gt.f32 p, %0, %1;\n"
+      "@p st.shared.f32 [%2], %0;\n"
+      "@p st.shared.s32 [%3], %4;\n"
+      "}\n"
+      :
+      : "f"(x), "f"(thr), "r"(addr_v), "r"(addr_i), "r"(idx)
+      : "memory");
+}
+
+// Order-preserving float <-> uint32 key (any sign, +-inf included).
+__device__ __forceinline__ uint32_t f32_key(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_f32(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
 __device__ __forceinline__ float warp_max(float v) {

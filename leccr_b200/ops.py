@@ -100,7 +100,7 @@ def sim_matrix(rows: Operand, cols: Operand, scale: float = 1.0, out: Optional[t
     if out is None:
         out = torch.empty((rows.n, cols.n), dtype=torch.float32, device=rows.t16.device)
     N.check(lib.leccr_sim_f32(N.ptr(rows.t16), rows.t16.stride(0), N.ptr(cols.t16), cols.t16.stride(0), rows.n,
-                              cols.n, rows.K, rows.fmt, N.ptr(out), out.stride(0), float(scale), None, 0,
+                              cols.n, rows.K, rows.fmt, N.ptr(out), out.stride(0), float(scale), None,
                               N.stream_ptr()), "leccr_sim_f32")
     return out
 
@@ -202,7 +202,7 @@ def infonce_backward(a: Operand, b: Operand, aT: torch.Tensor, bT: torch.Tensor,
     dev = a.t16.device
     dA = torch.empty((row_count, a.D), dtype=torch.float32, device=dev)
     dB = torch.empty((row_count, a.D), dtype=torch.float32, device=dev)
-    ws_bytes = lib.leccr_infonce_bwd_workspace(a.n, row_count)
+    ws_bytes = lib.leccr_infonce_bwd_workspace(a.n, row_count, a.D)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     N.check(lib.leccr_infonce_bwd(N.ptr(a.t16), N.ptr(b.t16), a.t16.stride(0), N.ptr(aT), N.ptr(bT), aT.stride(0),
                                   N.ptr(idx), a.n, a.D, a.fmt, N.ptr(temp), N.ptr(lse2), N.ptr(rcnt), row_begin,

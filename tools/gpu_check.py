@@ -15,6 +15,36 @@ sys.path.insert(0, ROOT)
 GROUPS = ["gemm", "gemm_x3", "topk", "loss", "rank", "perf"]
 
 
+def g_ncu():
+    """Short workload for an ncu launch list: one of each hot launch."""
+    import torch
+    from leccr_b200 import ops, _native as N
+
+    n, m = 5000, 25000
+    img, txt = synth(n, m, 256, 3)
+    img, txt = img.cuda(), txt.cuda()
+    I, T = ops.prep(img, N.FMT_F16), ops.prep(txt, N.FMT_F16)
+    per = m // n
+    gi = ops.csr_from_lists([list(range(i * per, (i + 1) * per)) for i in range(n)], img.device)
+    gt = ops.csr_from_lists([[t // per] for t in range(m)], img.device)
+    for _ in range(2):
+        ops.sim_topk([(I, T, gi), (T, I, gt)], k=10)
+        ops.sim_topk([(I, T, None)], k=10)
+        out = ops.sim_matrix(I, T)
+    a, b = synth(4096, 4096, 256, 7, noise=0.5)
+    a, b = a.cuda(), b.cuda()
+    temp = torch.tensor(0.07, device="cuda")
+    idx = torch.randint(0, 2048, (4096,), device="cuda")
+    go = torch.tensor(1.0, device="cuda")
+    for _ in range(2):
+        A, B = ops.prep(a, N.FMT_F16), ops.prep(b, N.FMT_F16)
+        o, lse2, rcnt = ops.infonce_forward(A, B, idx, temp)
+        aT, bT = ops.transpose16(A), ops.transpose16(B)
+        ops.infonce_backward(A, B, aT, bT, idx, temp, lse2, rcnt, 0, 512, go)
+    torch.cuda.synchronize()
+    return True
+
+
 def synth(n, m, d, seed, noise=1.5):
     import torch
 
@@ -79,7 +109,7 @@ def g_topk():
     from leccr_b200 import ops, _native as N
 
     ok = True
-    for (n, m, d, tpc) in [(1000, 5000, 256, 0), (1000, 5000, 256, 2), (300, 700, 256, 1), (5000, 25000, 256, 0)]:
+    for (n, m, d, tpc) in [(1000, 5000, 256, 0), (1000, 5000, 256, 3), (300, 700, 256, 1), (5000, 25000, 256, 0)]:
         img, txt = synth(n, m, d, 3)
         img, txt = img.cuda(), txt.cuda()
         per = m // n
@@ -242,8 +272,12 @@ def g_perf():
             txt = txt.repeat((m + txt.shape[0] - 1) // txt.shape[0], 1)[:m]
         img, txt = img.cuda(), txt.cuda()
         I, T = ops.prep(img, N.FMT_F16), ops.prep(txt, N.FMT_F16)
-        for tpc in (0, 4, 8, 16, 32):
-            us = timeit(lambda: ops.sim_topk([(I, T, None), (T, I, None)], k=10, tiles_per_chunk=tpc))
+        for tpc in (0, 13, 25, 49, 98):
+            try:
+                us = timeit(lambda: ops.sim_topk([(I, T, None), (T, I, None)], k=10, tiles_per_chunk=tpc))
+            except Exception as e:
+                print(f"perf topk both n={n} m={m} tpc={tpc}: {e}")
+                continue
             fl = 2 * 2.0 * n * m * 256
             print(f"perf topk both n={n} m={m} tpc={tpc}: {us:.1f} us  {fl / us / 1e6:.1f} TFLOP/s")
         us = timeit(lambda: ops.sim_topk([(I, T, None)], k=10))
