@@ -11,3 +11,8 @@ The arithmetic lives in libleccr_b200.so (hand-written sm_100a CUDA behind a C A
 include/leccr_b200.h).  There is no CPU path: calls raise if the library or a B200 is missing.
 """
 __version__ = "0.1.0"
+
+from .allgather import AllGather, allgather  # noqa: E402,F401
+from .contrastive import contrastive_loss, get_contrastive_loss  # noqa: E402,F401
+from .evaluation import (double_sim_matrix, evaluation_coarse, evaluation_coarse_video, fused_eval,  # noqa: E402,F401
+                         itm_eval, prepare_gt, score_matrix)

@@ -45,6 +45,8 @@ _SIGNATURES = {
     "leccr_last_cuda_error": (ctypes.c_char_p, []),
     "leccr_abi_version": (c_int, []),
     "leccr_check_device": (c_int, []),
+    "leccr_profile_enable": (None, [c_int]),
+    "leccr_profile_read": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int)]),
     "leccr_prep": (c_int, [vp, i64, c_int, i64, c_int, c_int, c_int, vp, i64, vp, vp, vp, vp]),
     "leccr_stats16": (c_int, [vp, c_int, i64, c_int, i64, vp, vp, vp, vp]),
     "leccr_transpose16": (c_int, [vp, i64, c_int, i64, vp, i64, vp]),

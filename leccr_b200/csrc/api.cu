@@ -122,6 +122,13 @@ int fill_problem(SimProblem& P, const void* rows16, int64_t ld_rows, const void*
   return LECCR_OK;
 }
 
+// Optional timing of the tensor-core launches with CUDA events on the launch stream (bench.py's
+// roofline leg).  Off by default; when on, every sim_gemm_kernel launch is bracketed.
+bool g_profile = false;
+cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+double g_profile_ms = 0.0;
+int g_profile_launches = 0;
+
 // As many pipeline stages as fit beside the epilogue's own shared memory (227 KB per CTA).
 template <class Epi>
 constexpr int stages_for() {
@@ -142,8 +149,23 @@ int launch_gemm(const SimLaunch& L, const typename Epi::Params& EP, cudaStream_t
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(sim_gemm_kernel)");
   if (L.n_items <= 0) return LECCR_OK;
   const int grid = std::min(L.n_items, num_sms());
+  if (g_profile) {
+    if (g_ev0 == nullptr) {
+      CUDA_TRY(cudaEventCreate(&g_ev0));
+      CUDA_TRY(cudaEventCreate(&g_ev1));
+    }
+    CUDA_TRY(cudaEventRecord(g_ev0, stream));
+  }
   kern<<<grid, gemm_threads(Epi::kWGs), smem, stream>>>(L, EP);
   LAUNCH_CHECK("sim_gemm_kernel");
+  if (g_profile) {
+    CUDA_TRY(cudaEventRecord(g_ev1, stream));
+    CUDA_TRY(cudaEventSynchronize(g_ev1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, g_ev0, g_ev1));
+    g_profile_ms += ms;
+    ++g_profile_launches;
+  }
   return LECCR_OK;
 }
 
@@ -167,6 +189,18 @@ const char* leccr_strerror(int code) {
 }
 const char* leccr_last_cuda_error(void) { return g_cuda_err; }
 int leccr_abi_version(void) { return 1; }
+
+void leccr_profile_enable(int on) {
+  g_profile = on != 0;
+  g_profile_ms = 0.0;
+  g_profile_launches = 0;
+}
+int leccr_profile_read(double* total_ms, int* launches) {
+  if (total_ms == nullptr || launches == nullptr) return LECCR_ERR_ARG;
+  *total_ms = g_profile_ms;
+  *launches = g_profile_launches;
+  return LECCR_OK;
+}
 
 int leccr_check_device(void) {
   int dev = 0, major = 0;

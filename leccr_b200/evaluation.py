@@ -1,0 +1,243 @@
+"""Drop-ins for the reference's retrieval evaluation (the hot path's eval half).
+
+  itm_eval(scores_i2t, scores_t2i, txt2img, img2txt)            image_Retrieval_caption.py:261-317
+                                                                 == video_Retrieval_caption_double_sim.py:194-247
+  evaluation_coarse(model, data_loader, tokenizer, device, config)          image_Retrieval_caption.py:83-163
+  evaluation_coarse_video(model, data_loader, tokenizer, device, config, alpha=0.9)
+                                                                 video_Retrieval_caption_double_sim.py:94-190
+plus the additive
+  fused_eval(image_embeds, text_embeds, txt2img, img2txt, ...)   similarity + top-k + Recall@1/5/10 in one
+                                                                 tensor-core pass; N x M never reaches HBM.
+
+Ranking rule: rank(row) = min over the row's ground truth g of #{j : s_j > s_g}.  This equals the
+reference's np.argsort(score)[::-1] position whenever the row has no exactly tied scores (the reference
+leaves the order of ties to numpy's unstable sort).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _native as N
+from . import ops
+
+EVAL_KEYS = ('txt_r1', 'txt_r5', 'txt_r10', 'txt_r_mean', 'txt_sum_r', 'img_r1', 'img_r5', 'img_r10',
+             'img_r_mean', 'r_mean', 'img_sumr', 'sumr_avg', 'sumr_sum')
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise N.LeccrError("leccr_b200 has no CPU path: a CUDA device (B200) is required")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _to_device(x, dev, dtype=None):
+    """numpy / CPU tensor / CUDA tensor -> CUDA tensor (async H2D from pinned staging for host data)."""
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    if not x.is_cuda:
+        x = x.contiguous()
+        if not x.is_pinned():
+            try:
+                x = x.pin_memory()
+            except RuntimeError:
+                pass
+        x = x.to(dev, non_blocking=True)
+    if dtype is not None and x.dtype != dtype:
+        x = x.to(dtype)
+    return x
+
+
+def metrics_from_counts(c_i2t, n_i2t, c_t2i, n_t2i) -> dict:
+    """The 13-key dict of image_Retrieval_caption.py:281-316 from #{rank < 1, 5, 10} per direction."""
+    tr1, tr5, tr10 = (100.0 * int(c) / n_i2t for c in c_i2t)
+    ir1, ir5, ir10 = (100.0 * int(c) / n_t2i for c in c_t2i)
+    tr_mean = (tr1 + tr5 + tr10) / 3
+    ir_mean = (ir1 + ir5 + ir10) / 3
+    r_mean = (tr_mean + ir_mean) / 2
+    txt_sumr = tr1 + tr5 + tr10
+    img_sumr = ir1 + ir5 + ir10
+    sumr_avg = np.round((txt_sumr + img_sumr) / 6, 2)
+    return {'txt_r1': tr1, 'txt_r5': tr5, 'txt_r10': tr10, 'txt_r_mean': tr_mean, 'txt_sum_r': txt_sumr,
+            'img_r1': ir1, 'img_r5': ir5, 'img_r10': ir10, 'img_r_mean': ir_mean, 'r_mean': r_mean,
+            'img_sumr': img_sumr, 'sumr_avg': sumr_avg, 'sumr_sum': (txt_sumr + img_sumr)}
+
+
+def _gt_lists(txt2img, img2txt, n_img, n_txt):
+    return [list(img2txt[i]) for i in range(n_img)], [[txt2img[t]] for t in range(n_txt)]
+
+
+def _is_transpose_view(a: np.ndarray, b: np.ndarray) -> bool:
+    return (isinstance(a, np.ndarray) and isinstance(b, np.ndarray) and a.ndim == 2 and b.shape == a.shape[::-1]
+            and b.strides == a.strides[::-1] and np.shares_memory(a, b)
+            and b.__array_interface__['data'][0] == a.__array_interface__['data'][0])
+
+
+@torch.no_grad()
+def itm_eval(scores_i2t, scores_t2i, txt2img, img2txt):
+    """Drop-in for itm_eval: ranks every row on the GPU (one pass over the matrix per direction)."""
+    dev = _device()
+    n_img, n_txt = scores_i2t.shape
+    gi, gt = _gt_lists(txt2img, img2txt, n_img, n_txt)
+    S = _to_device(scores_i2t, dev, torch.float32)
+    r_i = ops.rank_rows(S, *ops.csr_from_lists(gi, dev))
+    if _is_transpose_view(scores_i2t, scores_t2i) or scores_t2i is None:
+        r_t = ops.rank_cols(S, *ops.csr_from_lists(gt, dev))  # the reference's t2i IS i2t.T (:152)
+    else:
+        St = _to_device(scores_t2i, dev, torch.float32)
+        r_t = ops.rank_rows(St, *ops.csr_from_lists(gt, dev))
+    c_i = ops.recall_counts(r_i).cpu().tolist()
+    c_t = ops.recall_counts(r_t).cpu().tolist()
+    return metrics_from_counts(c_i, n_img, c_t, n_txt)
+
+
+def _precise_operands(rows: torch.Tensor, cols: torch.Tensor, precision: str):
+    fmt = ops.fmt_of(precision)
+    if precision.endswith("x3"):
+        return ops.prep(rows, fmt, N.LAYOUT_X3_ROWS, want_stats=False), ops.prep(cols, fmt, N.LAYOUT_X3_COLS,
+                                                                                want_stats=False)
+    return ops.prep(rows, fmt, want_stats=False), ops.prep(cols, fmt, want_stats=False)
+
+
+@torch.no_grad()
+def score_matrix(image_embeds, text_embeds, scale: float = 1.0, precision: str = "f16x3") -> torch.Tensor:
+    """score_matrix_i2t = image_embeds @ text_embeds.t()  (image_Retrieval_caption.py:151) on the tensor
+    cores; the default split-precision operands make the product fp32-accurate."""
+    dev = _device()
+    a, b = _precise_operands(_to_device(image_embeds, dev, torch.float32), _to_device(text_embeds, dev, torch.float32),
+                             precision)
+    return ops.sim_matrix(a, b, scale)
+
+
+@torch.no_grad()
+def double_sim_matrix(image_embeds, text_embeds, caption_embeds, alpha: float, fusion: str = "norm",
+                      scale: float = 1.0, precision: str = "f16x3") -> torch.Tensor:
+    """alpha * f(S) + (1 - alpha) * f(max_n C_n)   (video_...double_sim.py:170-178 / image_...py:235-246)."""
+    dev = _device()
+    img = _to_device(image_embeds, dev, torch.float32)
+    txt = _to_device(text_embeds, dev, torch.float32)
+    cap = _to_device(caption_embeds, dev, torch.float32)
+    n_cap, n_vid, d = cap.shape
+    fmt = ops.fmt_of(precision)
+    x3 = precision.endswith("x3")
+    t_op = ops.prep(txt, fmt, N.LAYOUT_X3_COLS if x3 else N.LAYOUT_HI, want_stats=False)
+    i_op = ops.prep(img, fmt, N.LAYOUT_X3_ROWS if x3 else N.LAYOUT_HI, want_stats=False)
+    c_op = ops.prep(cap.reshape(n_cap * n_vid, d), fmt, N.LAYOUT_X3_ROWS if x3 else N.LAYOUT_HI, want_stats=False)
+    S = ops.sim_matrix(i_op, t_op)
+    Cn = ops.sim_matrix(c_op, t_op).view(n_cap, n_vid, txt.shape[0])
+    ops.double_sim_fuse(S, Cn, alpha, N.FUSE_NORM if fusion == "norm" else N.FUSE_RAW)
+    if scale != 1.0:
+        S.mul_(scale)
+    return S
+
+
+def _dist_scale(distributed: bool) -> float:
+    """The reference all-reduces (SUM) score matrices that every rank already holds in full
+    (image_Retrieval_caption.py:154-157), i.e. multiplies them by world_size; rankings are unaffected."""
+    if distributed and dist.is_available() and dist.is_initialized():
+        return float(dist.get_world_size())
+    return 1.0
+
+
+def _collect_text(model, texts, tokenizer, device, config):
+    embeds = []
+    bs = config['batch_size_test_text']
+    for i in range(0, len(texts), bs):
+        chunk = texts[i: min(len(texts), i + bs)]
+        tok = tokenizer(chunk, padding='max_length', truncation=True, max_length=config['max_tokens'],
+                        return_tensors="pt").to(device)
+        feat = model.get_text_embeds(tok.input_ids, tok.attention_mask)
+        embeds.append(model.get_features(text_embeds=feat))
+    return torch.cat(embeds, dim=0)
+
+
+def _caption_inputs(model, generated_captions, tokenizer, device, config, clip_tokenizer):
+    if config['caption_encoder_name'] == 'clip':
+        if clip_tokenizer is None:
+            raise N.LeccrError("caption_encoder_name == 'clip' needs the reference's clip.tokenize (pass clip_tokenizer)")
+        captions = clip_tokenizer(generated_captions).to(device)
+        return model.get_caption_embeds(captions), torch.zeros_like(captions).masked_fill_(captions == 0, 1).bool()
+    tok = tokenizer(generated_captions, padding='max_length', truncation=True, max_length=config['max_tokens'],
+                    return_tensors="pt").to(device)
+    return model.get_caption_embeds(tok.input_ids, tok.attention_mask), ~tok.attention_mask.bool()
+
+
+@torch.no_grad()
+def evaluation_coarse(model, data_loader, tokenizer, device, config, distributed=False, clip_tokenizer=None):
+    """Drop-in for the image evaluation_coarse: encoders run as in the reference (they are out of scope),
+    the similarity stage (:147-163) runs on the tensor cores.  Returns (i2t, t2i) numpy, t2i a view of i2t.T."""
+    model.eval()
+    text_embeds = _collect_text(model, data_loader.dataset.text, tokenizer, device, config)
+    image_embeds = []
+    for image, generated_captions, img_id in data_loader:
+        image = image.to(device)
+        image_feat, _ = model.get_vision_embeds(image)
+        caption_embed, kpm = _caption_inputs(model, generated_captions, tokenizer, device, config, clip_tokenizer)
+        image_feat, _, _ = model.interaction_with_caption(image_embeds=image_feat, caption_embeds=caption_embed,
+                                                          key_padding_mask=kpm)
+        image_feat = image_feat.transpose(0, 1).contiguous()
+        image_embeds.append(model.get_features(image_embeds=image_feat))
+    image_embeds = torch.cat(image_embeds, dim=0)
+    i2t = score_matrix(image_embeds, text_embeds, _dist_scale(distributed)).cpu().numpy()
+    return i2t, i2t.T
+
+
+@torch.no_grad()
+def evaluation_coarse_video(model, data_loader, tokenizer, device, config, alpha=0.9, distributed=False,
+                            clip_tokenizer=None):
+    """Drop-in for the video evaluation_coarse with the double_sim fusion (:164-190)."""
+    model.eval()
+    text_embeds = _collect_text(model, data_loader.dataset.text, tokenizer, device, config)
+    image_embeds, caption_embeds = [], []
+    for video, mask_video, generated_captions, img_id in data_loader:
+        video = video.to(device)
+        mask_video = mask_video.to(device)
+        image_feat, image_atts = model.get_vision_embeds(video, mask_video)
+        caption_embed, kpm = _caption_inputs(model, generated_captions, tokenizer, device, config, clip_tokenizer)
+        image_feat, caption_embed, _ = model.interaction_with_caption(
+            image_embeds=image_feat, caption_embeds=caption_embed, key_padding_mask=kpm, video_mask=image_atts)
+        image_feat = image_feat.transpose(0, 1).contiguous()
+        image_embeds.append(model.get_features(image_embeds=image_feat, vis_mask=mask_video.unsqueeze(-1)))
+        caption_embeds.append(model.caption_proj1(caption_embed))
+    image_embeds = torch.cat(image_embeds, dim=0)
+    caption_embeds = torch.cat(caption_embeds, dim=1)
+    i2t = double_sim_matrix(image_embeds, text_embeds, caption_embeds, alpha, "norm",
+                            _dist_scale(distributed)).cpu().numpy()
+    return i2t, i2t.T
+
+
+@torch.no_grad()
+def prepare_gt(txt2img, img2txt, n_img, n_txt, device=None):
+    """Ground-truth maps (the dataset's txt2img / img2txt dicts) -> device CSR pair, reusable across calls."""
+    dev = device or _device()
+    gi, gt = _gt_lists(txt2img, img2txt, n_img, n_txt)
+    return ops.csr_from_lists(gi, dev), ops.csr_from_lists(gt, dev)
+
+
+@torch.no_grad()
+def fused_eval(image_embeds, text_embeds, txt2img=None, img2txt=None, k=10, precision="f16", tiles_per_chunk=0,
+               return_topk=True, gt=None):
+    """Similarity + per-row top-k + exact Recall@1/5/10 for both directions in one tensor-core launch.
+
+    image_embeds [N, D], text_embeds [M, D]: numpy / CPU / CUDA, fp32 (cast to 16-bit operands here) or
+    fp16 / bf16 (used as they are).  gt: optional prepare_gt(...) result (else built from the dicts).
+    Returns (eval dict with the reference's 13 keys, topk) where topk is
+    {'i2t': (val [N, k], idx [N, k]), 't2i': (val [M, k], idx [M, k])} CUDA tensors (approximate scores,
+    ties inside the 16-bit rounding may be ordered differently from fp32).
+    """
+    dev = _device()
+    img = _to_device(image_embeds, dev)
+    txt = _to_device(text_embeds, dev)
+    fmt = ops.fmt_of(precision)
+    I, T = ops.prep(img, fmt), ops.prep(txt, fmt)
+    if gt is None:
+        gt = prepare_gt(txt2img, img2txt, img.shape[0], txt.shape[0], dev)
+    r_i, r_t = ops.sim_topk([(I, T, gt[0]), (T, I, gt[1])], k=k, tiles_per_chunk=tiles_per_chunk)
+    # the step's single D2H read: 6 Recall counts + the two operand range flags (32 bytes)
+    host = torch.cat([r_i.recall_counts.float(), r_t.recall_counts.float(), I.stats[3:4], T.stats[3:4]]).cpu().tolist()
+    if host[6] != 0.0 or host[7] != 0.0:
+        raise N.LeccrError("embeddings overflow the fp16 operand format; call fused_eval(precision='bf16')")
+    counts = [[int(c) for c in host[0:3]], [int(c) for c in host[3:6]]]
+    ev = metrics_from_counts(counts[0], img.shape[0], counts[1], txt.shape[0])
+    if not return_topk:
+        return ev
+    return ev, {'i2t': (r_i.val, r_i.idx), 't2i': (r_t.val, r_t.idx)}

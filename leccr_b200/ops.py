@@ -80,6 +80,20 @@ def prep(x: torch.Tensor, fmt: int = N.FMT_F16, layout: int = N.LAYOUT_HI, norma
     return Operand(t16, fmt, layout, n, D, rn_hi, rn_lo, stats, x)
 
 
+def prep_into(x: torch.Tensor, dst: torch.Tensor, fmt: int, normalize: bool = False) -> torch.Tensor:
+    """Cast fp32 [n, D] into the (possibly strided) 16-bit view `dst` [n, D]; no statistics."""
+    _require_cuda(x, "x")
+    lib = N.load()
+    n, D = x.shape
+    if x.dtype != torch.float32 or dst.shape != x.shape or dst.stride(1) != 1:
+        raise N.LeccrError("prep_into needs fp32 [n, D] input and a row-major 16-bit destination view")
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    N.check(lib.leccr_prep(N.ptr(x), n, D, x.stride(0), int(normalize), fmt, N.LAYOUT_HI, N.ptr(dst), dst.stride(0),
+                           None, None, None, N.stream_ptr()), "leccr_prep")
+    return dst
+
+
 def transpose16(op: Operand) -> torch.Tensor:
     """[n, D] 16-bit -> [D, ld] with ld = n rounded up to 8 (zero padded)."""
     lib = N.load()

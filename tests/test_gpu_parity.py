@@ -1,0 +1,248 @@
+"""Parity of the CUDA path (through the Python drop-ins -> C ABI -> sm_100a kernels) with the oracle and
+with the reference's own outputs in tests/golden.  Needs a B200: run with `-m gpu`.
+
+Tolerances (north_star): Recall@K exactly equal; loss within 1e-3 relative; similarity within the stated
+16-bit tolerance (fp16 operands: |err| <= sum of row rounding-residual bounds, ~5e-4 on unit vectors;
+split-precision "x3" products: 2e-6); top-k indices identical except at ties inside that tolerance.
+"""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import leccr_b200
+from leccr_b200 import _native as N
+from leccr_b200 import ops, synth
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+EV_KEYS = leccr_b200.evaluation.EVAL_KEYS
+F16_TOL = 6e-4    # fp16 operands, unit vectors, D = 256
+X3_TOL = 2e-6     # split-precision product
+
+
+def ev_of(g, prefix):
+    return {k: float(g[f"{prefix}{k}"]) for k in EV_KEYS}
+
+
+def assert_ev_equal(got, want):
+    for k in EV_KEYS:
+        assert float(got[k]) == float(want[k]), (k, got[k], want[k])
+
+
+def test_native_library_is_loaded_and_device_ok():
+    lib = N.load()
+    assert lib.leccr_check_device() == 0
+
+
+# ----------------------------------------------------------------------------- similarity matrices
+def test_score_matrix_cfg1_against_oracle_and_golden(golden):
+    g = golden("baseline_configs.npz")
+    rs = synth.cfg1_multi30k()
+    want, _ = oracle.score_matrices(rs.image, rs.text)
+    got = leccr_b200.score_matrix(rs.image.numpy(), rs.text.numpy()).cpu().numpy()
+    assert got.shape == (1000, 5000) and got.dtype == np.float32
+    assert np.abs(got - want).max() < X3_TOL
+    assert np.abs(got[g["cfg1_rows"], g["cfg1_cols"]] - g["cfg1_vals"]).max() < X3_TOL
+    fast = leccr_b200.score_matrix(rs.image, rs.text, precision="f16").cpu().numpy()
+    assert np.abs(fast - want).max() < F16_TOL
+    bf = leccr_b200.score_matrix(rs.image, rs.text, precision="bf16").cpu().numpy()
+    assert np.abs(bf - want).max() < 8 * F16_TOL
+
+
+@pytest.mark.parametrize("n,m,d", [(1, 1, 64), (77, 1001, 128), (129, 257, 256), (300, 40, 64)])
+def test_score_matrix_ragged_shapes(n, m, d):
+    g = torch.Generator().manual_seed(n * 1000 + m)
+    a = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=-1)
+    b = torch.nn.functional.normalize(torch.randn(m, d, generator=g), dim=-1)
+    want, _ = oracle.score_matrices(a, b)
+    got = leccr_b200.score_matrix(a, b).cpu().numpy()
+    assert np.abs(got - want).max() < X3_TOL
+
+
+def test_double_sim_cfg4(golden):
+    g = golden("baseline_configs.npz")
+    rs = synth.cfg4_msrvtt()
+    want_i2t, want_t2i = oracle.double_sim_matrices(rs.image, rs.text, rs.caption, alpha=0.9)
+    got = leccr_b200.double_sim_matrix(rs.image, rs.text, rs.caption, 0.9, "norm").cpu().numpy()
+    assert np.abs(got - want_i2t).max() < 2e-5  # norm_score divides by (max - min) ~ 1: same scale
+    assert np.abs(got[g["cfg4_rows"], g["cfg4_cols"]] - g["cfg4_vals"]).max() < 2e-5
+    assert got.max() <= 0.0 and got.min() >= -1.0 - 1e-6
+    ev = leccr_b200.itm_eval(got, got.T, rs.txt2img, rs.img2txt)
+    assert_ev_equal(ev, ev_of(g, "cfg4_ev_"))
+    raw = leccr_b200.double_sim_matrix(rs.image, rs.text, rs.caption, 0.8, "raw").cpu().numpy()
+    want_raw, _ = oracle.double_sim_matrices(rs.image, rs.text, rs.caption, alpha=0.8, fusion="raw")
+    assert np.abs(raw - want_raw).max() < 1e-5
+
+
+def test_double_sim_small_golden(golden):
+    g = golden("video_small.npz")
+    got = leccr_b200.double_sim_matrix(g["image"], g["text"], g["caption"], 0.9, "norm").cpu().numpy()
+    assert np.abs(got - g["i2t"]).max() < 2e-5
+    n = got.shape[0]
+    ev = leccr_b200.itm_eval(got, got.T, {t: t for t in range(n)}, {i: [i] for i in range(n)})
+    assert_ev_equal(ev, ev_of(g, "ev_"))
+
+
+# ----------------------------------------------------------------------------- itm_eval drop-in
+def test_itm_eval_dropin_on_reference_matrices(golden):
+    g = golden("image_small.npz")
+    i2t = g["i2t"]
+    n, m = i2t.shape
+    txt2img = {t: t // 5 for t in range(m)}
+    img2txt = {i: list(range(5 * i, 5 * i + 5)) for i in range(n)}
+    want = ev_of(g, "ev_")
+    assert_ev_equal(leccr_b200.itm_eval(i2t, i2t.T, txt2img, img2txt), want)                           # view
+    assert_ev_equal(leccr_b200.itm_eval(i2t, np.ascontiguousarray(i2t.T), txt2img, img2txt), want)    # copy
+
+
+def test_itm_eval_dropin_cfg1(golden):
+    g = golden("baseline_configs.npz")
+    rs = synth.cfg1_multi30k()
+    i2t, t2i = oracle.score_matrices(rs.image, rs.text)
+    assert_ev_equal(leccr_b200.itm_eval(i2t, t2i, rs.txt2img, rs.img2txt), ev_of(g, "cfg1_ev_"))
+
+
+# ----------------------------------------------------------------------------- fused sim + top-k + Recall
+def check_topk_against(scores, val, idx, k, tol):
+    """Indices identical except at ties inside the tolerance; values within the tolerance."""
+    want_v, want_i = oracle.topk(scores, k)
+    got_i = idx.cpu().numpy().astype(np.int64)
+    got_v = val.cpu().numpy()
+    true_at_got = np.take_along_axis(scores, got_i, 1)
+    assert np.abs(got_v - true_at_got).max() < tol
+    assert np.abs(true_at_got - want_v).max() < 2 * tol           # position by position within tolerance
+    differs = (got_i != want_i).any(axis=1)
+    assert differs.mean() < 0.2                                    # and mostly identical outright
+    for r in np.nonzero(differs)[0][:200]:
+        assert set(got_i[r]) - set(want_i[r]) == set() or (want_v[r, -1] - true_at_got[r].min()) < 2 * tol
+
+
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg2"])
+def test_fused_eval_recall_equals_reference(golden, cfg):
+    g = golden("baseline_configs.npz")
+    rs = synth.cfg1_multi30k() if cfg == "cfg1" else synth.cfg2_mscoco5k()
+    ev, topk = leccr_b200.fused_eval(rs.image.numpy(), rs.text.numpy(), rs.txt2img, rs.img2txt, k=10)
+    assert_ev_equal(ev, ev_of(g, f"{cfg}_ev_"))
+    i2t, t2i = oracle.score_matrices(rs.image, rs.text)
+    check_topk_against(i2t, *topk["i2t"], 10, F16_TOL)
+    rows = np.arange(0, t2i.shape[0], 7)
+    check_topk_against(np.ascontiguousarray(t2i[rows]), topk["t2i"][0][rows], topk["t2i"][1][rows], 10, F16_TOL)
+    ev_bf = leccr_b200.fused_eval(rs.image, rs.text, rs.txt2img, rs.img2txt, precision="bf16", return_topk=False)
+    assert_ev_equal(ev_bf, ev_of(g, f"{cfg}_ev_"))  # exactness does not depend on the operand format
+
+
+def test_fused_eval_small_golden_and_chunking(golden):
+    g = golden("image_small.npz")
+    n, m = g["i2t"].shape
+    txt2img = {t: t // 5 for t in range(m)}
+    img2txt = {i: list(range(5 * i, 5 * i + 5)) for i in range(n)}
+    for tpc in (0, 1):
+        ev = leccr_b200.fused_eval(g["image"], g["text"], txt2img, img2txt, tiles_per_chunk=tpc, return_topk=False)
+        assert_ev_equal(ev, ev_of(g, "ev_"))
+
+
+def test_fused_eval_ties_and_duplicates():
+    """Duplicate gallery rows give exactly tied scores: Recall must follow rank = #{strictly greater}."""
+    rs = synth.retrieval_set(200, 3, d=64, seed=21)
+    text = rs.text.clone()
+    text[1::3] = text[0::3]  # every image's 2nd caption duplicates its 1st
+    i2t, t2i = oracle.score_matrices(rs.image, text)
+    want = oracle.itm_eval_by_count(i2t, t2i, rs.txt2img, rs.img2txt)
+    ev = leccr_b200.fused_eval(rs.image, text, rs.txt2img, rs.img2txt, return_topk=False)
+    assert_ev_equal(ev, want)
+    assert_ev_equal(leccr_b200.itm_eval(i2t, t2i, rs.txt2img, rs.img2txt), want)
+
+
+def test_fused_eval_bf16_stored_gallery_sampled_rows():
+    """cfg5-style: bf16-stored gallery, many columns per row; sampled rows checked against the oracle."""
+    gal, qry, gt = synth.cfg5_gallery(200_000, 4096, device="cuda")
+    dev = gal.device
+    Q, G = ops.prep(qry), ops.prep(gal)
+    off = torch.arange(qry.shape[0] + 1, dtype=torch.int32, device=dev)
+    res, = ops.sim_topk([(Q, G, (off, gt.to(torch.int32)))], k=10)
+    rows = torch.arange(0, 4096, 64, device=dev)
+    s = (qry[rows].float().cpu() @ gal.float().cpu().t()).numpy()
+    gt_rows = gt[rows].cpu().numpy()
+    ranks = oracle.ranks_by_count(s, [[int(x)] for x in gt_rows])
+    got = res.rank[rows].cpu().numpy()
+    small = ranks < N.RANK_CAP
+    assert (got[small] == ranks[small]).all() and (got[~small] >= N.RANK_CAP).all()
+    check_topk_against(s, res.val[rows], res.idx[rows], 10, 1e-4)
+    all_ranks = res.rank.cpu().numpy()
+    assert res.recall_counts.tolist() == [int((all_ranks < c).sum()) for c in (1, 5, 10)]
+
+
+def test_argument_errors_are_loud():
+    rs = synth.retrieval_set(16, 2, d=64, seed=2)
+    with pytest.raises(N.LeccrError):
+        leccr_b200.fused_eval(rs.image, rs.text, rs.txt2img, rs.img2txt, k=17)          # k > LECCR_TOPK_KP
+    with pytest.raises(N.LeccrError):
+        ops.prep(torch.zeros(4, 36, device="cuda"))                                        # D % 8 != 0
+    with pytest.raises(N.LeccrError):
+        leccr_b200.fused_eval(rs.image * 1e6, rs.text, rs.txt2img, rs.img2txt)           # fp16 overflow flagged
+    lib = N.load()
+    a = ops.prep(rs.image.cuda())
+    out = torch.empty(16, 16, device="cuda")
+    rc = lib.leccr_sim_f32(a.t16.data_ptr() + 2, 64, a.t16.data_ptr(), 64, 16, 16, 64, 0, out.data_ptr(), 16, 1.0,
+                           None, None)
+    assert rc == -2  # LECCR_ERR_ALIGN
+
+
+# ----------------------------------------------------------------------------- contrastive loss
+def run_loss(image, text, idx, temp, rows=None):
+    me = types.SimpleNamespace(embed_dim=image.shape[1], temp=torch.nn.Parameter(torch.tensor(temp, device="cuda")))
+    a = image.cuda().requires_grad_(True)
+    b = text.cuda().requires_grad_(True)
+    loss = leccr_b200.get_contrastive_loss(me, a, b, None if idx is None else idx.cuda())
+    loss.backward()
+    return loss.item(), a.grad.cpu(), b.grad.cpu(), me.temp.grad.item()
+
+
+def test_contrastive_small_against_reference(golden):
+    g = golden("contrastive_small.npz")
+    a, b, idx, temp = torch.from_numpy(g["image"]), torch.from_numpy(g["text"]), torch.from_numpy(g["idx"]), float(g["temp"])
+    for name, ix in (("noidx", None), ("idx", idx)):
+        loss, da, db, dt = run_loss(a, b, ix, temp)
+        want = float(g[f"{name}_loss"])
+        assert abs(loss - want) <= 1e-3 * abs(want)
+        ga, gb = torch.from_numpy(g[f"{name}_dA"]), torch.from_numpy(g[f"{name}_dB"])
+        assert (da - ga).norm() <= 2e-3 * ga.norm() and (db - gb).norm() <= 2e-3 * gb.norm()
+        assert abs(dt - float(g[f"{name}_dtemp"])) <= 2e-3 * abs(float(g[f"{name}_dtemp"]))
+
+
+@pytest.mark.parametrize("with_idx", [False, True])
+def test_contrastive_cfg3(golden, with_idx):
+    g = golden("baseline_configs.npz")
+    cb = synth.cfg3_itc()
+    name = "idx" if with_idx else "noidx"
+    loss, da, db, dt = run_loss(cb.image, cb.text, cb.idx if with_idx else None, cb.temp)
+    want = float(g[f"cfg3_{name}_loss"])
+    assert abs(loss - want) <= 1e-3 * abs(want)
+    assert abs(dt - float(g[f"cfg3_{name}_dtemp"])) <= 2e-3 * abs(float(g[f"cfg3_{name}_dtemp"]))
+    _, ra, rb, _ = oracle.contrastive_loss_and_grads(cb.image, cb.text, cb.temp, cb.idx if with_idx else None,
+                                                     dtype=torch.float64)
+    assert (da.double() - ra).norm() <= 2e-3 * ra.norm() and (db.double() - rb).norm() <= 2e-3 * rb.norm()
+    assert abs(da.norm().item() - float(g[f"cfg3_{name}_dA_norm"])) <= 2e-3 * float(g[f"cfg3_{name}_dA_norm"])
+
+
+def test_contrastive_local_rows_of_a_larger_gather():
+    """The backward kernel for rank r's rows [r*B, (r+1)*B): emulate the 8-rank layout on one GPU."""
+    cb = synth.cfg3_itc(1024, d=256, seed=9)
+    temp = torch.tensor(0.07, device="cuda")
+    a, b = ops.prep(cb.image.cuda(), want_stats=False), ops.prep(cb.text.cuda(), want_stats=False)
+    idx = cb.idx.cuda()
+    out, lse2, rcnt = ops.infonce_forward(a, b, idx, temp)
+    aT, bT = ops.transpose16(a), ops.transpose16(b)
+    go = torch.tensor(1.0, device="cuda")
+    ref_loss, _, _, ref_dt = oracle.contrastive_loss_and_grads(cb.image, cb.text, 0.07, cb.idx, dtype=torch.float64)
+    assert abs(out[0].item() - ref_loss.item()) <= 1e-3 * abs(ref_loss.item())
+    assert abs(out[1].item() - ref_dt.item()) <= 2e-3 * abs(ref_dt.item())
+    for rank, bsz in ((0, 128), (3, 128), (7, 128), (1, 100)):
+        dA, dB = ops.infonce_backward(a, b, aT, bT, idx, temp, lse2, rcnt, rank * bsz, bsz, go)
+        _, ra, rb, _ = oracle.contrastive_loss_and_grads(cb.image, cb.text, 0.07, cb.idx, rank=rank, batch_size=bsz,
+                                                         dtype=torch.float64)
+        assert (dA.cpu().double() - ra).norm() <= 2e-3 * ra.norm()
+        assert (dB.cpu().double() - rb).norm() <= 2e-3 * rb.norm()

@@ -1,0 +1,144 @@
+"""CPU-side checks: the C-ABI library loads and exports what include/leccr_b200.h declares, the host
+logic around it, and the N>1 plumbing over gloo (world_size 2).  No compute calls without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from leccr_b200 import _native as N
+from leccr_b200 import evaluation, ops, synth
+from oracle import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "leccr_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(leccr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = N.load()
+    names = declared_symbols()
+    assert len(names) >= 18
+    for name in names:
+        assert hasattr(lib, name), name
+    assert sorted(N.EXPORTS) == names, "ctypes signatures and header disagree"
+    assert lib.leccr_abi_version() == 1
+    assert b"sm_100" in lib.leccr_strerror(-3)
+
+
+def test_topk_problem_struct_matches_header():
+    # 21 fields; pointer / int64 / int layout must be what the C struct has (x86-64: 8-byte slots)
+    assert [f[0] for f in N.TopkProblem._fields_][:6] == ["rows16", "cols16", "ld_rows16", "ld_cols16", "n_rows", "n_cols"]
+    import ctypes
+
+    assert ctypes.sizeof(N.TopkProblem) == 21 * 8
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")
+def test_no_cpu_fallback():
+    rs = synth.retrieval_set(8, 2, d=64, seed=1)
+    with pytest.raises(N.LeccrError):
+        evaluation.fused_eval(rs.image, rs.text, rs.txt2img, rs.img2txt)
+    with pytest.raises(N.LeccrError):
+        evaluation.itm_eval(np.zeros((2, 2), np.float32), np.zeros((2, 2), np.float32), {0: 0, 1: 1}, {0: [0], 1: [1]})
+    with pytest.raises(N.LeccrError):
+        ops.prep(rs.image)
+    lib = N.load()
+    assert lib.leccr_check_device() != 0  # no device: refuses
+
+
+def test_metrics_from_counts_matches_reference_arithmetic():
+    want = oracle.metrics_from_recalls(100.0 * 552 / 1000, 100.0 * 841 / 1000, 100.0 * 921 / 1000,
+                                       100.0 * 1419 / 5000, 100.0 * 2517 / 5000, 100.0 * 3074 / 5000)
+    got = evaluation.metrics_from_counts([552, 841, 921], 1000, [1419, 2517, 3074], 5000)
+    assert got == want and tuple(got) == evaluation.EVAL_KEYS
+
+
+def test_transpose_view_detection():
+    a = np.zeros((3, 5), np.float32)
+    assert evaluation._is_transpose_view(a, a.T)
+    assert not evaluation._is_transpose_view(a, np.ascontiguousarray(a.T))
+    assert not evaluation._is_transpose_view(a, np.zeros((5, 3), np.float32))
+
+
+def test_csr_from_lists():
+    off, ids = ops.csr_from_lists([[3, 4], [], [7]], "cpu")
+    assert off.tolist() == [0, 2, 2, 3] and ids.tolist() == [3, 4, 7] and off.dtype == torch.int32
+
+
+def test_synth_is_deterministic():
+    a, b = synth.cfg1_multi30k(), synth.cfg1_multi30k()
+    assert torch.equal(a.image, b.image) and torch.equal(a.text, b.text)
+    assert a.img2txt[7] == [35, 36, 37, 38, 39] and a.txt2img[36] == 7
+    assert torch.allclose(a.image.norm(dim=1), torch.ones(1000), atol=1e-5)
+    c = synth.cfg4_msrvtt()
+    assert c.caption.shape == (2, 1000, 256)
+
+
+def _allgather_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    from leccr_b200.allgather import allgather
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(5)
+    full = torch.randn(world * 3, 4, generator=g)
+    x = full[rank * 3:(rank + 1) * 3].clone().requires_grad_(True)
+    out = allgather(x, rank, world)
+    w = torch.arange(out.numel(), dtype=torch.float32).view_as(out)
+    (out * w).sum().backward()
+    idx = torch.arange(rank * 3, (rank + 1) * 3).view(-1, 1)
+    idx_all = allgather(idx, rank, world)
+    q.put((rank, torch.equal(out.detach(), full), torch.equal(x.grad, w[rank * 3:(rank + 1) * 3]),
+           idx_all.view(-1).tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_allgather_two_ranks_gloo():
+    """models/xvlm.py:50-67 semantics: rank-ordered concat forward, own slice backward, no reduction."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_allgather_worker, args=(r, 2, 29611, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    for rank, fwd_ok, bwd_ok, idx_all in res:
+        assert fwd_ok and bwd_ok and idx_all == list(range(6))
+
+
+def test_query_sharding_covers_everything():
+    from leccr_b200 import sharding
+
+    for n, w in ((100000, 8), (5000, 3), (7, 4), (1, 2)):
+        spans = [sharding.shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
+
+
+def test_merge_topk_lists_matches_global_topk():
+    from leccr_b200 import sharding
+
+    g = torch.Generator().manual_seed(3)
+    scores = torch.randn(17, 400, generator=g)
+    k = 10
+    parts_v, parts_i = [], []
+    for (b, e) in (sharding.shard_range(400, r, 4) for r in range(4)):
+        v, i = torch.topk(scores[:, b:e], k, dim=1)
+        parts_v.append(v)
+        parts_i.append(i + b)
+    mv, mi = sharding.merge_topk(torch.stack(parts_v), torch.stack(parts_i), k)
+    wv, wi = torch.topk(scores, k, dim=1)
+    assert torch.equal(mv, wv) and torch.equal(mi, wi)

@@ -1,0 +1,108 @@
+"""The oracle (oracle/oracle.py) against the reference's own outputs (tests/golden, made by
+oracle/make_golden.py from /root/reference).  CPU only."""
+import numpy as np
+import torch
+
+from leccr_b200 import synth
+from oracle import oracle
+
+EV_KEYS = ('txt_r1', 'txt_r5', 'txt_r10', 'txt_r_mean', 'txt_sum_r', 'img_r1', 'img_r5', 'img_r10',
+           'img_r_mean', 'r_mean', 'img_sumr', 'sumr_avg', 'sumr_sum')
+
+
+def ev_of(g, prefix):
+    return {k: float(g[f"{prefix}{k}"]) for k in EV_KEYS}
+
+
+def assert_ev_equal(got, want):
+    assert set(got) == set(EV_KEYS)
+    for k in EV_KEYS:
+        assert float(got[k]) == want[k], (k, got[k], want[k])
+
+
+def test_image_small(golden):
+    g = golden("image_small.npz")
+    img, txt = torch.from_numpy(g["image"]), torch.from_numpy(g["text"])
+    i2t, t2i = oracle.score_matrices(img, txt)
+    np.testing.assert_allclose(i2t, g["i2t"], rtol=0, atol=1e-6)
+    assert bool(g["t2i_is_view"]) and not t2i.flags["C_CONTIGUOUS"] and np.shares_memory(i2t, t2i)
+    n, m = i2t.shape
+    txt2img = {t: t // 5 for t in range(m)}
+    img2txt = {i: list(range(5 * i, 5 * i + 5)) for i in range(n)}
+    want = ev_of(g, "ev_")
+    assert_ev_equal(oracle.itm_eval(g["i2t"], g["i2t"].T, txt2img, img2txt), want)
+    assert_ev_equal(oracle.itm_eval_by_count(g["i2t"], g["i2t"].T, txt2img, img2txt), want)
+
+
+def test_video_small(golden):
+    g = golden("video_small.npz")
+    img, txt, cap = (torch.from_numpy(g[k]) for k in ("image", "text", "caption"))
+    i2t, t2i = oracle.double_sim_matrices(img, txt, cap, alpha=0.9, fusion="norm")
+    np.testing.assert_allclose(i2t, g["i2t"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(t2i, g["t2i"], rtol=0, atol=1e-6)
+    assert i2t.max() <= 0.0 and i2t.min() >= -1.0 - 1e-6
+    n = i2t.shape[0]
+    want = ev_of(g, "ev_")
+    assert_ev_equal(oracle.itm_eval(g["i2t"], g["t2i"], {t: t for t in range(n)}, {i: [i] for i in range(n)}), want)
+    gi = golden("image_small.npz")
+    np.testing.assert_array_equal(oracle.norm_score(torch.from_numpy(gi["i2t"])).numpy(), g["norm_of_image_i2t"])
+
+
+def test_contrastive_small(golden):
+    g = golden("contrastive_small.npz")
+    a, b, idx, temp = torch.from_numpy(g["image"]), torch.from_numpy(g["text"]), torch.from_numpy(g["idx"]), float(g["temp"])
+    for name, ix in (("noidx", None), ("idx", idx)):
+        loss, da, db, dt = oracle.contrastive_loss_and_grads(a, b, temp, ix)
+        assert abs(loss.item() - float(g[f"{name}_loss"])) < 1e-6
+        np.testing.assert_allclose(da.numpy(), g[f"{name}_dA"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(db.numpy(), g[f"{name}_dB"], rtol=1e-5, atol=1e-7)
+        assert abs(dt.item() - float(g[f"{name}_dtemp"])) <= 1e-5 * abs(float(g[f"{name}_dtemp"]))
+    # two ranks: every rank sees the same loss / dtemp and its own slice of the gradients (AllGather.backward)
+    bs = a.shape[0] // 2
+    for r in range(2):
+        loss, da, db, dt = oracle.contrastive_loss_and_grads(a, b, temp, idx, rank=r, batch_size=bs)
+        assert abs(loss.item() - float(g[f"w2_r{r}_loss"])) < 1e-6
+        np.testing.assert_allclose(da.numpy(), g[f"w2_r{r}_dA"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(db.numpy(), g[f"w2_r{r}_dB"], rtol=1e-5, atol=1e-7)
+        assert abs(dt.item() - float(g[f"w2_r{r}_dtemp"])) <= 1e-5 * abs(float(g[f"w2_r{r}_dtemp"]))
+
+
+def test_cfg1_multi30k(golden):
+    g = golden("baseline_configs.npz")
+    rs = synth.cfg1_multi30k()
+    i2t, t2i = oracle.score_matrices(rs.image, rs.text)
+    np.testing.assert_allclose(i2t[g["cfg1_rows"], g["cfg1_cols"]], g["cfg1_vals"], rtol=0, atol=1e-6)
+    want = ev_of(g, "cfg1_ev_")
+    assert_ev_equal(oracle.itm_eval(i2t, t2i, rs.txt2img, rs.img2txt), want)
+    assert_ev_equal(oracle.itm_eval_by_count(i2t, t2i, rs.txt2img, rs.img2txt), want)
+    _, order = oracle.topk(i2t[g["cfg1_top10_rows"]], 10)
+    np.testing.assert_array_equal(order, g["cfg1_top10"])
+
+
+def test_cfg2_mscoco5k(golden):
+    g = golden("baseline_configs.npz")
+    rs = synth.cfg2_mscoco5k()
+    i2t, t2i = oracle.score_matrices(rs.image, rs.text)
+    np.testing.assert_allclose(i2t[g["cfg2_rows"], g["cfg2_cols"]], g["cfg2_vals"], rtol=0, atol=1e-6)
+    assert_ev_equal(oracle.itm_eval_by_count(i2t, t2i, rs.txt2img, rs.img2txt), ev_of(g, "cfg2_ev_"))
+
+
+def test_cfg4_msrvtt_double_sim(golden):
+    g = golden("baseline_configs.npz")
+    rs = synth.cfg4_msrvtt()
+    i2t, t2i = oracle.double_sim_matrices(rs.image, rs.text, rs.caption, alpha=0.9)
+    np.testing.assert_allclose(i2t[g["cfg4_rows"], g["cfg4_cols"]], g["cfg4_vals"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(t2i[g["cfg4_cols"], g["cfg4_rows"]], g["cfg4_vals_t2i"], rtol=0, atol=1e-6)
+    assert_ev_equal(oracle.itm_eval(i2t, t2i, rs.txt2img, rs.img2txt), ev_of(g, "cfg4_ev_"))
+
+
+def test_cfg3_itc(golden):
+    g = golden("baseline_configs.npz")
+    cb = synth.cfg3_itc()
+    for name, ix in (("noidx", None), ("idx", cb.idx)):
+        loss, da, db, dt = oracle.contrastive_loss_and_grads(cb.image, cb.text, cb.temp, ix)
+        assert abs(loss.item() - float(g[f"cfg3_{name}_loss"])) <= 2e-6 * abs(float(g[f"cfg3_{name}_loss"]))
+        assert abs(dt.item() - float(g[f"cfg3_{name}_dtemp"])) <= 1e-4 * abs(float(g[f"cfg3_{name}_dtemp"]))
+        np.testing.assert_allclose(da[:8].numpy(), g[f"cfg3_{name}_dA_rows"], rtol=1e-4, atol=1e-8)
+        np.testing.assert_allclose(db[:8].numpy(), g[f"cfg3_{name}_dB_rows"], rtol=1e-4, atol=1e-8)
+        assert abs(da.norm().item() - float(g[f"cfg3_{name}_dA_norm"])) <= 1e-4 * float(g[f"cfg3_{name}_dA_norm"])
