@@ -145,7 +145,7 @@ sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typ
         const CUtensorMap* tmc = &L.prob[p].tm_cols;
         for (int ct = ct0; ct < ct1; ++ct) {
           for (int kc = kc0; kc < kc1; ++kc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + stage);
+            mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + stage, 64);
             uint8_t* sa = stage_base + stage * kStageBytes;
             uint8_t* sb = sa + kAStageBytes;
             mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
@@ -172,7 +172,7 @@ sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typ
         for (int ct = ct0; ct < ct1; ++ct, ++tile_n) {
           const uint32_t buf = tile_n & 1u;
           const uint32_t use = tile_n >> 1;
-          mbar_wait(&tempty_bar[buf], (use & 1u) ^ 1u, 200 + buf);
+          mbar_wait(&tempty_bar[buf], (use & 1u) ^ 1u, 200 + buf, 64);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * BN;
           for (int kc = kc0; kc < kc1; ++kc) {
@@ -218,7 +218,7 @@ sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typ
         if (kWGs == 2 && (tile_n & 1u) != static_cast<uint32_t>(c.wg)) continue;
         const uint32_t buf = tile_n & 1u;
         const uint32_t use = tile_n >> 1;
-        mbar_wait(&tfull_bar[buf], use & 1u, 400 + buf);
+        mbar_wait(&tfull_bar[buf], use & 1u, 400 + buf, 32);
         tc_fence_after();
         const uint32_t taddr = tmem_base + buf * BN + (static_cast<uint32_t>(c.warp_q * 32) << 16);
         c.tile_n = tile_n;

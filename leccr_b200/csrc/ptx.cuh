@@ -56,12 +56,15 @@ __device__ __forceinline__ uint32_t mbar_try_wait_hint(uint64_t* bar, uint32_t p
   return ok;
 }
 // Bounded wait: a protocol bug must not hang the GPU (a hung box is a lost round), so after a few
-// seconds of waiting the kernel reports where it was stuck and traps.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+// seconds of waiting the kernel reports where it was stuck and traps.  backoff_ns > 0 sleeps between
+// polls: the waiting role warps share their schedulers with epilogue warps and must not steal issue
+// slots from them (use 0 only where wake-up latency matters more).
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag, uint32_t backoff_ns = 0) {
   if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {  // try_wait itself suspends the thread for a HW-defined window
-    if (++spins > 200000000u) {
+  while (!mbar_try_wait(bar, parity)) {
+    if (backoff_ns) __nanosleep(backoff_ns);
+    if (++spins > 100000000u) {
       printf("leccr: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag,
              (int)blockIdx.x, (int)threadIdx.x, parity);
       __trap();
