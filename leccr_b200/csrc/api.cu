@@ -3,6 +3,7 @@
 #include "../../include/leccr_b200.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -354,8 +355,19 @@ int leccr_sim_f32(const void* rows16, int64_t ld_rows, const void* cols16, int64
 // Work decomposition of a top-k launch.  topk_finalize holds 2 * n_chunks candidates per lane,
 // so a row's columns are split into at most kMaxTopkChunks chunks.  Each problem gets a
 // share of ~4 work items per SM proportional to its tile count.
-constexpr int kTopkWGs = EpiTopK<LECCR_TOPK_KP>::kWGs;
-constexpr int kMaxTopkChunks = kMaxChunks / kTopkWGs;
+// Two epilogue shapes (see EpiTopK): one warpgroup with 64-entry lists, or two with 32-entry lists.
+using TopK1 = EpiTopK<LECCR_TOPK_KP, 64, 1>;
+using TopK2 = EpiTopK<LECCR_TOPK_KP, 32, 2>;
+constexpr int kMaxTopkChunks = 8;  // topk_finalize holds n_chunks * kWGs * (C / 32) <= 16 slots per lane
+
+static bool topk_two_wgs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LECCR_TOPK_WGS");
+    v = (e != nullptr && atoi(e) == 1) ? 0 : 1;
+  }
+  return v == 1;
+}
 
 static int topk_plan(const leccr_topk_problem* probs, int n_prob, int tiles_per_chunk, Plan* plans) {
   int64_t total_tiles = 0;
@@ -385,9 +397,10 @@ size_t leccr_sim_topk_workspace(const leccr_topk_problem* probs, int n_prob, int
   if (topk_plan(probs, n_prob, tiles_per_chunk, plans) != LECCR_OK) return 0;
   size_t bytes = 0;
   for (int p = 0; p < n_prob; ++p) {
-    const size_t lists = static_cast<size_t>(probs[p].n_rows) * plans[p].n_chunks * kTopkWGs;
-    bytes += align256(lists * kListCap * 4) * 2 + align256(lists * 4) +
-             align256(static_cast<size_t>(probs[p].n_rows) * 4 + 16);
+    // either shape: n_chunks * kWGs lists of C entries = n_chunks * 64 entries per row
+    const size_t lists = static_cast<size_t>(probs[p].n_rows) * plans[p].n_chunks * 2;
+    bytes += align256(lists * 32 * 4) * 2 + align256(lists * 4) +
+             align256(static_cast<size_t>(probs[p].n_rows) * 4 + 16) + align256(static_cast<size_t>(probs[p].n_rows) * 4);
   }
   return bytes;
 }
@@ -419,8 +432,13 @@ int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
   L.n_prob = n_prob;
   L.fmt = fmt;
   L.k_chunks = (D + BK - 1) / BK;
-  EpiTopK<LECCR_TOPK_KP>::Params EP;
+  const bool two = topk_two_wgs();
+  const int wgs = two ? 2 : 1;
+  const int cap = two ? TopK2::C : TopK1::C;
+  TopK1::Params EP;  // both shapes share the parameter layout
+  static_assert(sizeof(TopK1::Params) == sizeof(TopK2::Params), "parameter layouts must agree");
   memset(&EP, 0, sizeof(EP));
+  if (const char* dbg = getenv("LECCR_TOPK_DEBUG")) EP.debug_mode = atoi(dbg);  // measurement aid only
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   float* cand_val[2];
   int* cand_idx[2];
@@ -433,23 +451,34 @@ int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
                       plans[p], item_base);
     if (rc != LECCR_OK) return rc;
     item_base += plans[p].row_blocks * plans[p].n_chunks;
-    const size_t lists = static_cast<size_t>(q.n_rows) * plans[p].n_chunks * kTopkWGs;
+    const size_t lists = static_cast<size_t>(q.n_rows) * plans[p].n_chunks * 2;
     cand_val[p] = reinterpret_cast<float*>(ws);
-    ws += align256(lists * kListCap * 4);
+    ws += align256(lists * 32 * 4);
     cand_idx[p] = reinterpret_cast<int*>(ws);
-    ws += align256(lists * kListCap * 4);
+    ws += align256(lists * 32 * 4);
     cand_cnt[p] = reinterpret_cast<int*>(ws);
     ws += align256(lists * 4);
     flag[p] = reinterpret_cast<int*>(ws);  // [0] count, [4..] list of undecided rows
     ws += align256(static_cast<size_t>(q.n_rows) * 4 + 16);
     if (q.gt_off != nullptr) CUDA_TRY(cudaMemsetAsync(flag[p], 0, 16, stream));
+    if (plans[p].n_chunks > 1 || two) {  // every owner of a row cooperates through a shared threshold
+      EP.row_thr[p] = reinterpret_cast<unsigned*>(ws);
+      CUDA_TRY(cudaMemsetAsync(ws, 0, static_cast<size_t>(q.n_rows) * 4, stream));
+    }
+    ws += align256(static_cast<size_t>(q.n_rows) * 4);
     EP.out_val[p] = cand_val[p];
     EP.out_idx[p] = cand_idx[p];
     EP.out_cnt[p] = cand_cnt[p];
-    EP.n_sub[p] = plans[p].n_chunks * kTopkWGs;
+    EP.n_sub[p] = plans[p].n_chunks * wgs;
   }
   L.n_items = item_base;
-  rc = launch_gemm<EpiTopK<LECCR_TOPK_KP>>(L, EP, stream);
+  if (two) {
+    TopK2::Params EP2;
+    memcpy(&EP2, &EP, sizeof(EP2));
+    rc = launch_gemm<TopK2>(L, EP2, stream);
+  } else {
+    rc = launch_gemm<TopK1>(L, EP, stream);
+  }
   if (rc != LECCR_OK) return rc;
 
   for (int p = 0; p < n_prob; ++p) {
@@ -461,7 +490,8 @@ int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
     F.cand_cnt = cand_cnt[p];
     F.n_rows = static_cast<int>(q.n_rows);
     F.n_cols = static_cast<int>(q.n_cols);
-    F.n_chunks = plans[p].n_chunks * kTopkWGs;
+    F.n_chunks = plans[p].n_chunks * wgs;
+    F.list_cap = cap;
     F.KP = LECCR_TOPK_KP;
     F.k = k;
     F.topk_val = q.topk_val;

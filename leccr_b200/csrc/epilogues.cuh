@@ -107,31 +107,38 @@ struct EpiStore {
 // Nothing <= thr can belong to the row's top-KP, so the union of a row's lists over its column
 // chunks contains the exact top-KP of the approximate scores; topk_finalize selects them.
 // ------------------------------------------------------------------------------------------
-template <int KP>
+// Two shapes: <16, 64, 1> one warpgroup with 64-entry lists, <16, 32, 2> two warpgroups (alternate
+// tiles) with 32-entry lists; in both the lists take 66 KB of shared memory.  The two threads that own
+// the same row (and the CTAs that own other column chunks of it) cooperate through row_thr.
+template <int KP, int C_, int WGS>
 struct EpiTopK {
-  static constexpr int kWGs = 1;         // the lists fill shared memory: one warpgroup
-  static constexpr int C = 64;           // list capacity
+  static constexpr int kWGs = WGS;
+  static constexpr int C = C_;           // list capacity
   static constexpr int LDSW = C + 1;     // row pitch in words: conflict-free for per-thread and per-row access
   static constexpr int TRIG = C - 8;     // a group of 8 columns must always fit
-  static constexpr int KEEP = 32;        // the exact (bisection) shrink stops once this few remain
-  static constexpr int JOIN = 48;        // rows at least this full shrink whenever any row of the warp must
-  static_assert(KP == 16 && C == 64, "quad_shrink assumes 16 strided quads of a 64-entry list");
+  static constexpr int G = C / 16;       // strided group size of the cheap shrink (16 groups)
+  static constexpr int KEEP = C / 2 > KP ? C / 2 : KP + 2;  // the exact (bisection) shrink stops once this few remain
+  static constexpr int JOIN = C == 64 ? 48 : 22;  // rows at least this full shrink whenever any row of the warp must
+  static_assert(KP == 16 && (C == 64 || C == 32), "the cheap shrink takes 16 strided groups of a 32/64-entry list");
   static_assert(KP <= KEEP && KEEP < JOIN && JOIN <= TRIG, "inconsistent list policy");
   struct Params {
     float* out_val[2];  // [n_rows][n_sub][C]
     int* out_idx[2];
     int* out_cnt[2];    // [n_rows][n_sub]
     int n_sub[2];       // partial lists per row: n_chunks * kWGs
+    unsigned* row_thr[2];  // [n_rows] shared per-row threshold keys (zeroed per launch), or null
+    int debug_mode;     // measurement aid: 1 = threshold +inf (filter only), 2 = skip the tile entirely
   };
   static constexpr int kSmemBytes = 2 * kEpiThreads * LDSW * 4;
+  static constexpr int kIdxOff = kEpiThreads * LDSW * 4;  // byte offset from a value slot to its index slot
   struct State {
     float thr;
     int cnt;
     uint32_t vb, ib;  // shared-window addresses of this thread's value / index list
   };
 
-  __device__ static void begin(State& st, const Params&, const ItemCtx& c) {
-    st.thr = -CUDART_INF_F;
+  __device__ static void begin(State& st, const Params& P, const ItemCtx& c) {
+    st.thr = P.debug_mode == 1 ? CUDART_INF_F : -CUDART_INF_F;
     st.cnt = 0;
     st.vb = smem_u32(c.smem) + static_cast<uint32_t>(c.et) * LDSW * 4;
     st.ib = st.vb + kEpiThreads * LDSW * 4;
@@ -165,22 +172,27 @@ struct EpiTopK {
     }
     float tau = CUDART_INF_F;
 #pragma unroll
-    for (int k = 0; k < 16; ++k)
-      tau = fminf(tau, fmaxf(fmaxf(x[k], x[k + 16]), fmaxf(x[k + 32], x[k + 48])));
+    for (int k = 0; k < 16; ++k) {
+      float gm = x[k];
+#pragma unroll
+      for (int q = 1; q < G; ++q) gm = fmaxf(gm, x[k + 16 * q]);
+      tau = fminf(tau, gm);
+    }
+    // an adopted (shared) threshold may already exceed tau: then everything below it is dead too
+    const float te = fmaxf(tau, thr_in);
     int j = 0;
 #pragma unroll
     for (int s = 0; s < C; ++s) {
       const int id = lds_s32(ib + s * 4);
-      if (x[s] >= tau) {  // -inf padding never passes: tau > -inf whenever n >= 49
+      if (x[s] >= te) {  // -inf padding never passes unless te = -inf (n < 16: nothing to do)
         sts_f32(vb + j * 4, x[s]);
         sts_s32(ib + j * 4, id);
         ++j;
       }
     }
-    const float thr = fmaxf(thr_in, tau);
-    const int cnt = (tau == -CUDART_INF_F) ? n : j;
-    if (cnt > JOIN) return shrink(thr, cnt, vb, ib);
-    return pack_state(thr, cnt);
+    const int cnt = (te == -CUDART_INF_F) ? n : j;
+    if (cnt > JOIN) return shrink(te, cnt, vb, ib);
+    return pack_state(te, cnt);
   }
 
   __device__ __noinline__ static unsigned long long shrink(float thr_in, int n, uint32_t vb, uint32_t ib) {
@@ -240,19 +252,34 @@ struct EpiTopK {
     return pack_state(keep_thr, j);
   }
 
-  __device__ static void tile(State& st, const Params&, const ItemCtx& c, uint32_t taddr, int col0) {
+  __device__ static void tile(State& st, const Params& P, const ItemCtx& c, uint32_t taddr, int col0) {
     const int n_cols = c.n_cols;
+    if (P.debug_mode == 2) return;
+    // A threshold proven valid by ANY column chunk of this row (>= 16 scores of the row are at least
+    // that large) is valid for every chunk: adopt the best one published so far.  Stale reads are fine.
+    unsigned* shared_thr = (P.row_thr[c.p] != nullptr && c.row < c.n_rows) ? P.row_thr[c.p] + c.row : nullptr;
+    if (shared_thr != nullptr) {
+      const unsigned k = *reinterpret_cast<volatile unsigned*>(shared_thr);
+      if (k > f32_key(st.thr)) st.thr = key_f32(k);
+    }
     for_each_chunk(taddr, col0, n_cols, [&](float(&v)[32], int col) {
       if (col + 32 > n_cols) {  // ragged last columns (TMA zero-filled): exclude them
 #pragma unroll
         for (int e = 0; e < 32; ++e)
           if (col + e >= n_cols) v[e] = -CUDART_INF_F;
       }
+      // level 1: one max over the whole 32-column chunk; on long rows almost every chunk ends here
+      float gm[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        gm[g] = fmaxf(fmaxf(fmaxf(v[8 * g], v[8 * g + 1]), fmaxf(v[8 * g + 2], v[8 * g + 3])),
+                      fmaxf(fmaxf(v[8 * g + 4], v[8 * g + 5]), fmaxf(v[8 * g + 6], v[8 * g + 7])));
+      const float cm = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+      if (!__any_sync(0xffffffffu, cm > st.thr)) return;  // warp-uniform
+      // level 2: per group of 8 columns
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const float m = fmaxf(fmaxf(fmaxf(v[8 * g], v[8 * g + 1]), fmaxf(v[8 * g + 2], v[8 * g + 3])),
-                              fmaxf(fmaxf(v[8 * g + 4], v[8 * g + 5]), fmaxf(v[8 * g + 6], v[8 * g + 7])));
-        if (__any_sync(0xffffffffu, m > st.thr)) {  // warp-uniform: some row has a candidate here
+        if (__any_sync(0xffffffffu, gm[g] > st.thr)) {  // warp-uniform: some row has a candidate here
           const float thr = st.thr;
           int cnt = st.cnt;
 #pragma unroll
@@ -267,6 +294,7 @@ struct EpiTopK {
               const unsigned long long r = quad_shrink(st.thr, cnt, st.vb, st.ib);
               st.thr = __uint_as_float(static_cast<unsigned>(r >> 32));
               st.cnt = static_cast<int>(r & 0xffffffffu);
+              if (shared_thr != nullptr) atomicMax(shared_thr, f32_key(st.thr));
             }
           }
         }

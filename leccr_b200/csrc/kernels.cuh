@@ -347,15 +347,15 @@ __global__ void infonce_finalize_kernel(const FinalizeLseParams P) {
 //      than kRankCap definitely-greater items are known) the row is flagged for exact_rank_rows.
 // --------------------------------------------------------------------------------
 constexpr int kRankCap = 10;   // Recall@1/5/10 only ever asks whether rank < 10
-constexpr int kListCap = 64;    // == EpiTopK::C: two list entries per lane
-constexpr int kMaxChunks = 8;   // partial lists per row (column chunks x epilogue warpgroups)
+constexpr int kMaxSlots = 16;   // candidate slots per lane in topk_finalize: n_lists * (list_cap / 32) <= 16
 constexpr int kFinalizeWarps = 8;
 
 struct TopkFinalizeParams {
-  const float* cand_val;  // [n_rows][n_chunks][kListCap]
+  const float* cand_val;  // [n_rows][n_chunks][list_cap]
   const int* cand_idx;
   const int* cand_cnt;    // [n_rows][n_chunks]
   int n_rows, n_cols, n_chunks, KP, k;
+  int list_cap;           // 32 or 64 (EpiTopK::C)
   float* topk_val;  // [n_rows][k]
   int* topk_idx;
   // exact recall (all optional; gt_off == nullptr disables)
@@ -424,27 +424,29 @@ __global__ void __launch_bounds__(kFinalizeWarps * 32) topk_finalize_kernel(cons
   const int row = blockIdx.x * kFinalizeWarps + wib;
   if (row >= P.n_rows) return;
   const int KP = P.KP;
-  const int per_lane = 2 * P.n_chunks;  // two slots per partial list and lane
+  const int sh = P.list_cap >> 6;             // slots per list and lane: 1 (cap 32) or 2 (cap 64), as a shift
+  const int per_lane = P.n_chunks << sh;
   const long long cbase = static_cast<long long>(row) * P.n_chunks;
   // all loads are issued before any is consumed: list lengths (one lane each), then every slot
   const int my_cnt = lane < P.n_chunks ? __ldg(P.cand_cnt + cbase + lane) : 0;
-  float v[2 * kMaxChunks];
-  int id[2 * kMaxChunks];
+  float v[kMaxSlots];
+  int id[kMaxSlots];
 #pragma unroll
-  for (int t = 0; t < 2 * kMaxChunks; ++t) {
+  for (int t = 0; t < kMaxSlots; ++t) {
     v[t] = -CUDART_INF_F;
     id[t] = -1;
     if (t < per_lane) {
-      v[t] = __ldg(P.cand_val + (cbase + (t >> 1)) * kListCap + lane + 32 * (t & 1));
-      id[t] = __ldg(P.cand_idx + (cbase + (t >> 1)) * kListCap + lane + 32 * (t & 1));
+      const long long o = (cbase + (t >> sh)) * P.list_cap + lane + 32 * (t & sh);
+      v[t] = __ldg(P.cand_val + o);
+      id[t] = __ldg(P.cand_idx + o);
     }
   }
   float gmax = -CUDART_INF_F, gmin = CUDART_INF_F;
   int n_loc = 0;
 #pragma unroll
-  for (int t = 0; t < 2 * kMaxChunks; ++t) {
-    const int cnt_t = __shfl_sync(0xffffffffu, my_cnt, t >> 1);
-    if (t < per_lane && lane + 32 * (t & 1) < cnt_t) {
+  for (int t = 0; t < kMaxSlots; ++t) {
+    const int cnt_t = __shfl_sync(0xffffffffu, my_cnt, t >> sh);
+    if (t < per_lane && lane + 32 * (t & sh) < cnt_t) {
       gmax = fmaxf(gmax, v[t]);
       gmin = fminf(gmin, v[t]);
       ++n_loc;
@@ -471,7 +473,7 @@ __global__ void __launch_bounds__(kFinalizeWarps * 32) topk_finalize_kernel(cons
     const float mid = key_f32(mid_k);
     int cm = 0;
 #pragma unroll
-    for (int t = 0; t < 2 * kMaxChunks; ++t) cm += (id[t] >= 0 && v[t] > mid) ? 1 : 0;
+    for (int t = 0; t < kMaxSlots; ++t) cm += (id[t] >= 0 && v[t] > mid) ? 1 : 0;
     cm = __reduce_add_sync(0xffffffffu, cm);
     if (cm >= KP) {
       lo_k = mid_k;
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(kFinalizeWarps * 32) topk_finalize_kernel(cons
   int base = 0;
   const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
-  for (int t = 0; t < 2 * kMaxChunks; ++t) {
+  for (int t = 0; t < kMaxSlots; ++t) {
     const bool sel = id[t] >= 0 && v[t] > keep_thr;
     const unsigned m = __ballot_sync(0xffffffffu, sel);
     const int pos = base + __popc(m & lt_mask);
@@ -501,7 +503,7 @@ __global__ void __launch_bounds__(kFinalizeWarps * 32) topk_finalize_kernel(cons
   }
   if (tie) {  // more than 32 equal scores at the threshold: any of them completes the list
 #pragma unroll
-    for (int t = 0; t < 2 * kMaxChunks; ++t) {
+    for (int t = 0; t < kMaxSlots; ++t) {
       const bool sel = id[t] >= 0 && !(v[t] > keep_thr) && v[t] > lo;
       const unsigned m = __ballot_sync(0xffffffffu, sel);
       const int pos = base + __popc(m & lt_mask);

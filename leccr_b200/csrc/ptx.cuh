@@ -233,6 +233,24 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// if (x > thr) { *addr = x; *(addr + IDX_OFF) = idx_base + E; addr += 4; }  -- 5 predicated
+// instructions, no branch; the running address replaces a separate counter.
+template <int IDX_OFF, int E>
+__device__ __forceinline__ void append_if_gt(float x, float thr, uint32_t& addr, int idx_base) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .s32 t;\n"
+      "setp.gt.f32 p, %1, %2;\n"
+      "add.s32 t, %3, %5;\n"
+      "@p st.shared.f32 [%0], %1;\n"
+      "@p st.shared.s32 [%0+%4], t;\n"
+      "@p add.u32 %0, %0, 4;\n"
+      "}\n"
+      : "+r"(addr)
+      : "f"(x), "f"(thr), "r"(idx_base), "n"(IDX_OFF), "n"(E)
+      : "memory");
+}
 // if (x > thr) { list_v[slot] = x; list_i[slot] = idx; } as predicated stores (no branch).
 __device__ __forceinline__ void sts_pair_if_gt(float x, float thr, uint32_t addr_v, uint32_t addr_i, int idx) {
   asm volatile(
