@@ -130,6 +130,41 @@ cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 double g_profile_ms = 0.0;
 int g_profile_launches = 0;
 
+// Development aid (LECCR_STAGE_PROFILE=1): events between the launches of one C-ABI call, printed by
+// leccr_profile_read.  Not used by the product path.
+struct StageMark {
+  const char* name;
+  cudaEvent_t ev;
+};
+StageMark g_marks[64];
+int g_n_marks = 0;
+bool stage_profile_on() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LECCR_STAGE_PROFILE");
+    v = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+void prof_mark(const char* name, cudaStream_t stream) {
+  if (!stage_profile_on() || g_n_marks >= 64) return;
+  StageMark& m = g_marks[g_n_marks];
+  if (m.ev == nullptr) cudaEventCreate(&m.ev);
+  m.name = name;
+  cudaEventRecord(m.ev, stream);
+  ++g_n_marks;
+}
+void prof_dump() {
+  if (!stage_profile_on() || g_n_marks == 0) return;
+  cudaEventSynchronize(g_marks[g_n_marks - 1].ev);
+  for (int i = 1; i < g_n_marks; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_marks[i - 1].ev, g_marks[i].ev);
+    fprintf(stderr, "  stage %-28s %8.1f us\n", g_marks[i].name, ms * 1e3f);
+  }
+  g_n_marks = 0;
+}
+
 // As many pipeline stages as fit beside the epilogue's own shared memory (227 KB per CTA).
 template <class Epi>
 constexpr int stages_for() {
@@ -200,6 +235,7 @@ int leccr_profile_read(double* total_ms, int* launches) {
   if (total_ms == nullptr || launches == nullptr) return LECCR_ERR_ARG;
   *total_ms = g_profile_ms;
   *launches = g_profile_launches;
+  prof_dump();
   return LECCR_OK;
 }
 
@@ -222,6 +258,7 @@ int leccr_prep(const float* src, int64_t n, int D, int64_t ld_src, int normalize
   const int wpb = 8;
   const unsigned grid = static_cast<unsigned>((n + wpb - 1) / wpb);
   uint16_t* dst = static_cast<uint16_t*>(dst16);
+  prof_mark("prep:begin", stream);
   const bool vec = (D % 128 == 0) && D <= 1024 && (ld_src % 4 == 0) && (ld_dst % 4 == 0) &&
                    (reinterpret_cast<uintptr_t>(src) % 16 == 0) && (reinterpret_cast<uintptr_t>(dst16) % 8 == 0);
   if (vec) {
@@ -239,6 +276,7 @@ int leccr_prep(const float* src, int64_t n, int D, int64_t ld_src, int normalize
                                                       rn_hi, rn_lo, stats);
   }
   LAUNCH_CHECK("prep_rows_kernel");
+  prof_mark("prep", stream);
   return LECCR_OK;
 }
 
@@ -363,8 +401,8 @@ constexpr int kMaxTopkChunks = 8;  // topk_finalize holds n_chunks * kWGs * (C /
 static bool topk_two_wgs() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("LECCR_TOPK_WGS");
-    v = (e != nullptr && atoi(e) == 1) ? 0 : 1;
+    const char* e = getenv("LECCR_TOPK_WGS");  // measurement aid: 2 selects the two-warpgroup shape
+    v = (e != nullptr && atoi(e) == 2) ? 1 : 0;
   }
   return v == 1;
 }
@@ -380,6 +418,8 @@ static int topk_plan(const leccr_topk_problem* probs, int n_prob, int tiles_per_
     if (tpc <= 0) {
       const double share = 4.0 * num_sms() * static_cast<double>(row_blocks * col_tiles) / static_cast<double>(total_tiles);
       int64_t chunks = static_cast<int64_t>(share / static_cast<double>(row_blocks) + 0.5);
+      // (More chunks than load balance needs do not pay: later chunks inherit a threshold from the
+      // earlier ones, but a stale one, and the total number of list inserts per row grows.)
       chunks = std::max<int64_t>(1, std::min<int64_t>(chunks, std::min<int64_t>(kMaxTopkChunks, col_tiles)));
       tpc = static_cast<int>((col_tiles + chunks - 1) / chunks);
     }
@@ -472,6 +512,7 @@ int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
     EP.n_sub[p] = plans[p].n_chunks * wgs;
   }
   L.n_items = item_base;
+  prof_mark("topk:begin", stream);
   if (two) {
     TopK2::Params EP2;
     memcpy(&EP2, &EP, sizeof(EP2));
@@ -480,6 +521,7 @@ int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
     rc = launch_gemm<TopK1>(L, EP, stream);
   }
   if (rc != LECCR_OK) return rc;
+  prof_mark("topk:gemm", stream);
 
   for (int p = 0; p < n_prob; ++p) {
     const leccr_topk_problem& q = probs[p];
@@ -516,14 +558,17 @@ int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
     const unsigned grid = static_cast<unsigned>((q.n_rows + kFinalizeWarps - 1) / kFinalizeWarps);
     topk_finalize_kernel<<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
     LAUNCH_CHECK("topk_finalize_kernel");
+    prof_mark("topk:finalize", stream);
     if (q.gt_off != nullptr) {
       const unsigned g2 = static_cast<unsigned>(std::min<int64_t>(q.n_rows, 2LL * num_sms()));
       exact_rank_rows_kernel<<<g2, 256, 0, stream>>>(F);
       LAUNCH_CHECK("exact_rank_rows_kernel");
+      prof_mark("topk:exact_rank", stream);
       if (q.recall_counts != nullptr) {
         const unsigned g3 = static_cast<unsigned>(std::min<int64_t>((q.n_rows + 255) / 256, 2LL * num_sms()));
         recall_count_kernel<<<g3, 256, 0, stream>>>(q.rank, static_cast<int>(q.n_rows), q.recall_counts);
         LAUNCH_CHECK("recall_count_kernel");
+        prof_mark("topk:recall_count", stream);
       }
     }
   }

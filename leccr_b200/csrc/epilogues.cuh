@@ -268,18 +268,20 @@ struct EpiTopK {
         for (int e = 0; e < 32; ++e)
           if (col + e >= n_cols) v[e] = -CUDART_INF_F;
       }
-      // level 1: one max over the whole 32-column chunk; on long rows almost every chunk ends here
       float gm[4];
 #pragma unroll
       for (int g = 0; g < 4; ++g)
         gm[g] = fmaxf(fmaxf(fmaxf(v[8 * g], v[8 * g + 1]), fmaxf(v[8 * g + 2], v[8 * g + 3])),
                       fmaxf(fmaxf(v[8 * g + 4], v[8 * g + 5]), fmaxf(v[8 * g + 6], v[8 * g + 7])));
-      const float cm = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
-      if (!__any_sync(0xffffffffu, cm > st.thr)) return;  // warp-uniform
-      // level 2: per group of 8 columns
+      // ONE warp collective decides the whole chunk: which of the four 8-column groups contain a
+      // candidate for some row (votes and branches are the latency that bounds this epilogue)
+      unsigned hm = (gm[0] > st.thr ? 1u : 0u) | (gm[1] > st.thr ? 2u : 0u) | (gm[2] > st.thr ? 4u : 0u) |
+                    (gm[3] > st.thr ? 8u : 0u);
+      hm = __reduce_or_sync(0xffffffffu, hm);
+      if (hm == 0u) return;  // warp-uniform; on long rows almost every chunk ends here
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        if (__any_sync(0xffffffffu, gm[g] > st.thr)) {  // warp-uniform: some row has a candidate here
+        if (hm & (1u << g)) {  // warp-uniform
           const float thr = st.thr;
           int cnt = st.cnt;
 #pragma unroll

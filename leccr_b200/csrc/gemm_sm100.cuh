@@ -72,9 +72,11 @@ __device__ __forceinline__ void decode_item(const SimLaunch& L, int item, int& p
                                             int& ct1, int& cc, int& kc0, int& kc1) {
   p = (L.n_prob > 1 && item >= L.prob[1].item_base) ? 1 : 0;
   const SimProblem& P = L.prob[p];
+  // chunk-major order: the column chunks of a row block are spread over successive waves, so later
+  // chunks start from the per-row thresholds the earlier ones have published (EpiTopK::row_thr)
   int local = item - P.item_base;
-  int r = local / P.n_chunks;
-  cc = local - r * P.n_chunks;
+  cc = local / P.row_blocks;
+  int r = local - cc * P.row_blocks;
   rb = P.row_block_begin + r;
   if (L.k_splits > 1) {
     ct0 = 0;

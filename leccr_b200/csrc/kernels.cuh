@@ -41,6 +41,31 @@ __device__ __forceinline__ float ordered_f32(unsigned u) {
 // Per-tensor statistics written by the prep kernels (all atomically max-combined; zero-init).
 //   [0] max_i ||hi_i||   [1] max_i ||x_i - hi_i||   [2] max |x|   [3] non-finite / fp16-overflow flag
 constexpr int kStatWords = 4;
+// max-combine a non-negative float into a per-tensor statistic.  Thousands of rows update the same
+// word, so look first: after the first few rows the atomic is almost never needed.
+__device__ __forceinline__ void stat_max(float* addr, float v) {
+  if (v > *reinterpret_cast<volatile float*>(addr)) atomicMax(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+}
+
+// Combine the per-row statistics of a block's warps in shared memory and publish once per block.
+// Every thread of the block must call this (rows past the end contribute zeros).
+__device__ __forceinline__ void publish_stats(float* stats, float a, float b, float amax, bool bad) {
+  __shared__ float s_st[4][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (stats == nullptr) return;  // uniform
+  if (lane == 0) {
+    s_st[0][warp] = a;
+    s_st[1][warp] = b;
+    s_st[2][warp] = amax;
+    s_st[3][warp] = bad ? 1.f : 0.f;
+  }
+  __syncthreads();
+  if (warp == 0 && lane < 4) {
+    float m = 0.f;
+    for (int w = 0; w < nw; ++w) m = fmaxf(m, s_st[lane][w]);
+    if (m > 0.f) stat_max(stats + lane, m);
+  }
+}
 
 // --------------------------------------------------------------------------------
 // prep_rows: fp32 rows -> 16-bit tensor-core operand.  One warp per row.
@@ -59,7 +84,10 @@ __global__ void prep_rows_kernel(const float* __restrict__ src, long long ld_src
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  if (row >= n) return;
+  if (row >= n) {
+    publish_stats(stats, 0.f, 0.f, 0.f, false);
+    return;
+  }
   const float* x = src + static_cast<long long>(row) * ld_src;
   float inv = 1.f;
   if (normalize) {
@@ -103,17 +131,12 @@ __global__ void prep_rows_kernel(const float* __restrict__ src, long long ld_src
   nl = warp_sum(nl);
   amax = warp_max(amax);
   const unsigned anybad = __ballot_sync(0xffffffffu, bad);
+  const float a = sqrtf(nh), b = sqrtf(nl);
   if (lane == 0) {
-    const float a = sqrtf(nh), b = sqrtf(nl);
     if (rn_hi) rn_hi[row] = a;
     if (rn_lo) rn_lo[row] = b;
-    if (stats) {
-      atomicMax(reinterpret_cast<unsigned*>(stats) + 0, __float_as_uint(a));
-      atomicMax(reinterpret_cast<unsigned*>(stats) + 1, __float_as_uint(b));
-      atomicMax(reinterpret_cast<unsigned*>(stats) + 2, __float_as_uint(amax));
-      if (anybad) atomicMax(reinterpret_cast<unsigned*>(stats) + 3, __float_as_uint(1.f));
-    }
   }
+  publish_stats(stats, a, b, amax, anybad != 0);
 }
 
 // Fast path of prep_rows for D % 128 == 0, D <= 1024, 16-byte aligned rows: one warp per row, each
@@ -125,7 +148,10 @@ __global__ void prep_rows_vec_kernel(const float* __restrict__ src, long long ld
                                      float* __restrict__ rn_lo, float* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= n) return;
+  if (row >= n) {
+    publish_stats(stats, 0.f, 0.f, 0.f, false);
+    return;
+  }
   const int nv = D >> 7;  // float4 per lane
   const float4* x4 = reinterpret_cast<const float4*>(src + static_cast<long long>(row) * ld_src);
   float4 x[8];
@@ -181,17 +207,12 @@ __global__ void prep_rows_vec_kernel(const float* __restrict__ src, long long ld
   nl = warp_sum(nl);
   amax = warp_max(amax);
   const unsigned anybad = __ballot_sync(0xffffffffu, bad);
+  const float a = sqrtf(nh), b = sqrtf(nl);
   if (lane == 0) {
-    const float a = sqrtf(nh), b = sqrtf(nl);
     if (rn_hi) rn_hi[row] = a;
     if (rn_lo) rn_lo[row] = b;
-    if (stats) {
-      atomicMax(reinterpret_cast<unsigned*>(stats) + 0, __float_as_uint(a));
-      atomicMax(reinterpret_cast<unsigned*>(stats) + 1, __float_as_uint(b));
-      atomicMax(reinterpret_cast<unsigned*>(stats) + 2, __float_as_uint(amax));
-      if (anybad) atomicMax(reinterpret_cast<unsigned*>(stats) + 3, __float_as_uint(1.f));
-    }
   }
+  publish_stats(stats, a, b, amax, anybad != 0);
 }
 
 // Row norms / maxima of an operand that is already 16-bit (e.g. a bf16-stored gallery).
@@ -201,7 +222,10 @@ __global__ void stats_rows16_kernel(const uint16_t* __restrict__ src, long long 
                                     float* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= n) return;
+  if (row >= n) {
+    publish_stats(stats, 0.f, 0.f, 0.f, false);
+    return;
+  }
   const uint16_t* x = src + static_cast<long long>(row) * ld_src;
   float nh = 0.f, amax = 0.f;
   bool bad = false;
@@ -214,16 +238,12 @@ __global__ void stats_rows16_kernel(const uint16_t* __restrict__ src, long long 
   nh = warp_sum(nh);
   amax = warp_max(amax);
   const unsigned anybad = __ballot_sync(0xffffffffu, bad);
+  const float a = sqrtf(nh);
   if (lane == 0) {
-    const float a = sqrtf(nh);
     if (rn_hi) rn_hi[row] = a;
     if (rn_lo) rn_lo[row] = 0.f;
-    if (stats) {
-      atomicMax(reinterpret_cast<unsigned*>(stats) + 0, __float_as_uint(a));
-      atomicMax(reinterpret_cast<unsigned*>(stats) + 2, __float_as_uint(amax));
-      if (anybad) atomicMax(reinterpret_cast<unsigned*>(stats) + 3, __float_as_uint(1.f));
-    }
   }
+  publish_stats(stats, a, 0.f, amax, anybad != 0);
 }
 
 // 16-bit transpose [n][D] -> [D][ldT] (operand of the gradient products: K runs over rows).

@@ -1,0 +1,51 @@
+"""Multi-GPU check (torchrun, NCCL): the contrastive drop-in on W ranks against the oracle on the
+concatenated batch, and the AllGather drop-in.  Development / gpu-box tool."""
+import os, sys, types
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as dist
+import leccr_b200
+from leccr_b200 import synth
+from oracle import oracle
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+B = 512
+cb = synth.cfg3_itc(B * world, 256, seed=7)
+ok = True
+for with_idx in (False, True):
+    me = types.SimpleNamespace(embed_dim=256, temp=torch.nn.Parameter(torch.tensor(cb.temp, device="cuda")))
+    a = cb.image[rank * B:(rank + 1) * B].cuda().requires_grad_(True)
+    b = cb.text[rank * B:(rank + 1) * B].cuda().requires_grad_(True)
+    idx = cb.idx[rank * B:(rank + 1) * B].cuda() if with_idx else None
+    loss = leccr_b200.get_contrastive_loss(me, a, b, idx)
+    loss.backward()
+    rl, ra, rb, rt = oracle.contrastive_loss_and_grads(cb.image, cb.text, cb.temp, cb.idx if with_idx else None,
+                                                       rank=rank, batch_size=B, dtype=torch.float64)
+    e = [abs(loss.item() - rl.item()) / abs(rl.item()), ((a.grad.cpu().double() - ra).norm() / ra.norm()).item(),
+         ((b.grad.cpu().double() - rb).norm() / rb.norm()).item(), abs(me.temp.grad.item() - rt.item()) / abs(rt.item())]
+    good = e[0] < 1e-3 and e[1] < 2e-3 and e[2] < 2e-3 and e[3] < 2e-3
+    ok &= good
+    print(f"rank {rank}/{world} idx={with_idx}: loss {loss.item():.6f} rel {e[0]:.1e} dA {e[1]:.1e} dB {e[2]:.1e} dtemp {e[3]:.1e} {'PASS' if good else 'FAIL'}", flush=True)
+x = torch.full((3, 4), float(rank), device="cuda", requires_grad=True)
+g = leccr_b200.allgather(x, rank, world)
+(g * torch.arange(g.numel(), device="cuda").view_as(g)).sum().backward()
+exp = torch.arange(world, device="cuda").repeat_interleave(3).view(-1, 1).expand(-1, 4).float()
+ok &= bool(torch.equal(g.detach(), exp)) and bool(torch.equal(x.grad, torch.arange(world * 12, device="cuda").view(-1, 4)[rank * 3:(rank + 1) * 3].float()))
+# timing of the training step (fwd + bwd) on this rank, max over ranks
+def step():
+    me.temp.grad = None
+    l = leccr_b200.get_contrastive_loss(me, a, b, idx)
+    l.backward()
+for _ in range(5): step()
+dist.barrier(); torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(20): step()
+e1.record(); torch.cuda.synchronize()
+t = torch.tensor([e0.elapsed_time(e1) / 20 * 1e3], device="cuda")
+dist.all_reduce(t, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print(f"contrastive fwd+bwd, B={B}/rank, N={B*world}: {t.item():.1f} us per step (max over ranks)  ALL {'PASS' if ok else 'FAIL'}")
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
