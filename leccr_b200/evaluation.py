@@ -241,3 +241,57 @@ def fused_eval(image_embeds, text_embeds, txt2img=None, img2txt=None, k=10, prec
     if not return_topk:
         return ev
     return ev, {'i2t': (r_i.val, r_i.idx), 't2i': (r_t.val, r_t.idx)}
+
+
+# ----------------------------------------------------------------------------- multi-GPU
+@torch.no_grad()
+def fused_eval_sharded(image_embeds, text_embeds, txt2img, img2txt, k=10, precision="f16", group=None):
+    """Query-sharded fused evaluation: every rank holds the full embedding sets (as in the reference, where
+    every rank evaluates everything, image_Retrieval_caption.py:453), ranks only ITS slice of the rows of
+    each direction, and the six Recall counts are summed with one all_reduce.  Returns the same dict on
+    every rank plus this rank's slices of the top-k lists."""
+    from . import sharding
+
+    dev = _device()
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    img = _to_device(image_embeds, dev)
+    txt = _to_device(text_embeds, dev)
+    fmt = ops.fmt_of(precision)
+    I, T = ops.prep(img, fmt), ops.prep(txt, fmt)
+    bi, ei = sharding.shard_range(img.shape[0], rank, world)
+    bt, et = sharding.shard_range(txt.shape[0], rank, world)
+    probs = []
+    if ei > bi:
+        probs.append((I.rows(bi, ei), T, ops.csr_from_lists([list(img2txt[i]) for i in range(bi, ei)], dev)))
+    if et > bt:
+        probs.append((T.rows(bt, et), I, ops.csr_from_lists([[txt2img[t]] for t in range(bt, et)], dev)))
+    res = ops.sim_topk(probs, k=k) if probs else []
+    counts = torch.zeros(6, dtype=torch.int32, device=dev)
+    j = 0
+    if ei > bi:
+        counts[0:3] = res[j].recall_counts
+        j += 1
+    if et > bt:
+        counts[3:6] = res[j].recall_counts
+    if world > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    c = counts.cpu().tolist()
+    ev = metrics_from_counts(c[0:3], img.shape[0], c[3:6], txt.shape[0])
+    return ev, {"rows_i2t": (bi, ei), "rows_t2i": (bt, et), "results": res}
+
+
+@torch.no_grad()
+def topk_gallery_sharded(queries, gallery_shard, shard_offset: int, k=10, precision="bf16", group=None):
+    """Row-partitioned gallery: every rank holds all queries and ITS gallery rows [shard_offset, ...).
+    Local fused similarity + top-k, global column = local + shard_offset, then one all-gather of the
+    (Q, k) lists and a merge (leccr_b200.sharding).  Returns the same (val, idx int64) on every rank."""
+    from . import sharding
+
+    dev = _device()
+    q = _to_device(queries, dev)
+    g = _to_device(gallery_shard, dev)
+    fmt = ops.fmt_of(precision)
+    Q, G = ops.prep(q, fmt, want_stats=False), ops.prep(g, fmt, want_stats=False)
+    res, = ops.sim_topk([(Q, G, None)], k=k)
+    return sharding.allgather_topk(res.val, res.idx.long() + shard_offset, k, group)

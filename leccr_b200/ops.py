@@ -45,6 +45,12 @@ class Operand:
     def x_dtype(self):
         return {torch.float32: N.F32, torch.float16: N.F16, torch.bfloat16: N.BF16}[self.x.dtype]
 
+    def rows(self, begin: int, end: int) -> "Operand":
+        """Rows [begin, end) as an operand of their own (views; the per-tensor stats stay the whole tensor's)."""
+        return Operand(self.t16[begin:end], self.fmt, self.layout, end - begin, self.D,
+                       None if self.rn_hi is None else self.rn_hi[begin:end],
+                       None if self.rn_lo is None else self.rn_lo[begin:end], self.stats, self.x[begin:end])
+
 
 def prep(x: torch.Tensor, fmt: int = N.FMT_F16, layout: int = N.LAYOUT_HI, normalize: bool = False,
          want_stats: bool = True) -> Operand:

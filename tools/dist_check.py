@@ -32,6 +32,22 @@ g = leccr_b200.allgather(x, rank, world)
 (g * torch.arange(g.numel(), device="cuda").view_as(g)).sum().backward()
 exp = torch.arange(world, device="cuda").repeat_interleave(3).view(-1, 1).expand(-1, 4).float()
 ok &= bool(torch.equal(g.detach(), exp)) and bool(torch.equal(x.grad, torch.arange(world * 12, device="cuda").view(-1, 4)[rank * 3:(rank + 1) * 3].float()))
+# ---- sharded evaluation against the reference's golden dict for cfg1 (queries split over the ranks)
+import numpy as np
+gold = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "baseline_configs.npz"))
+rs = synth.cfg1_multi30k()
+ev, _ = leccr_b200.fused_eval_sharded(rs.image, rs.text, rs.txt2img, rs.img2txt)
+ev_ok = all(float(ev[k_]) == float(gold[f"cfg1_ev_{k_}"]) for k_ in leccr_b200.evaluation.EVAL_KEYS)
+ok &= ev_ok
+# ---- row-partitioned gallery + NCCL merge against a single-GPU pass over the whole gallery
+gal, qry, _gt = synth.cfg5_gallery(40000, 512, device="cuda")
+from leccr_b200 import sharding, ops as _ops
+b0, e0 = sharding.shard_range(40000, rank, world)
+mv, mi = leccr_b200.topk_gallery_sharded(qry, gal[b0:e0], b0, k=10)
+full, = _ops.sim_topk([(_ops.prep(qry), _ops.prep(gal), None)], k=10)
+merge_ok = bool(torch.equal(mi, full.idx.long())) and bool(torch.equal(mv, full.val))
+ok &= merge_ok
+print(f"rank {rank}: sharded eval == golden {ev_ok}; gallery-partition merge == single pass {merge_ok}", flush=True)
 # timing of the training step (fwd + bwd) on this rank, max over ranks
 def step():
     me.temp.grad = None
