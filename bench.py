@@ -263,6 +263,7 @@ def run_ours(args, rank, world, local_rank):
         "recall_check": {k: ev[k] for k in ("txt_r1", "txt_r5", "txt_r10", "img_r1", "img_r5", "img_r10")},
     }
     if world == 1:
+        line["extras"] = extras_single_gpu(torch, ops, synth, lib, dev, peak)
         threads = os.cpu_count() or 1
         frac = 0.2
         cpu_path_sample(rs, 0.02, threads)
@@ -275,6 +276,68 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def extras_single_gpu(torch, ops, synth, lib, dev, peak):
+    """Secondary measurements reported beside the headline (not part of the driver's contract):
+    cfg3 (contrastive fwd+bwd at global batch 4096, this GPU playing rank 0 of 8) and the per-GPU share
+    of cfg5 under 8-way query sharding (12,500 bf16 queries x 1,000,000 bf16 gallery rows, top-10)."""
+    import ctypes
+
+    import torch.nn.functional as F
+
+    from leccr_b200 import _native as N
+
+    out = {}
+    # ---- cfg3: operands of all 4096 rows are "gathered" already; local rows [0, 512)
+    cb = synth.cfg3_itc()
+    a32, b32, idx = cb.image.to(dev), cb.text.to(dev), cb.idx.to(dev)
+    temp = torch.tensor(cb.temp, device=dev)
+    go = torch.tensor(1.0, device=dev)
+
+    def itc_step():
+        A, B = ops.prep(a32, want_stats=False), ops.prep(b32, want_stats=False)
+        o, lse2, rcnt = ops.infonce_forward(A, B, idx, temp)
+        aT, bT = ops.transpose16(A), ops.transpose16(B)
+        return ops.infonce_backward(A, B, aT, bT, idx, temp, lse2, rcnt, 0, 512, go)
+
+    for _ in range(5):
+        itc_step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        itc_step()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 20 * 1e3
+    flops = 2.0 * 2 * 4096 * 4096 * 256 + 2.0 * 2 * 2 * 512 * 4096 * 256  # fwd both orientations + strips + grads
+    out["contrastive_fwd_bwd"] = {"config": "cfg3: global batch 4096 (8 x 512), D=256, idx labels, rank 0's rows",
+                                  "us_per_step": us, "tflops": flops / us / 1e6, "frac_of_peak": flops / us / 1e6 / peak,
+                                  "includes": "fp32->fp16 cast of 2 x 4096 rows, forward, transposes, backward of 512 local rows"}
+    # ---- cfg5 per-GPU share (query sharding over 8 GPUs)
+    g = torch.Generator(device=dev).manual_seed(1237)
+    gal = F.normalize(torch.randn(1_000_000, 256, device=dev, generator=g), dim=-1).to(torch.bfloat16)
+    qry = F.normalize(torch.randn(12_500, 256, device=dev, generator=g), dim=-1).to(torch.bfloat16)
+    Q, G = ops.prep(qry), ops.prep(gal)
+    for _ in range(2):
+        ops.sim_topk([(Q, G, None)], k=10)
+    torch.cuda.synchronize()
+    lib.leccr_profile_enable(1)
+    for _ in range(3):
+        ops.sim_topk([(Q, G, None)], k=10)
+    torch.cuda.synchronize()
+    tot, cnt = ctypes.c_double(), ctypes.c_int()
+    lib.leccr_profile_read(ctypes.byref(tot), ctypes.byref(cnt))
+    lib.leccr_profile_enable(0)
+    ms = tot.value / max(1, cnt.value)
+    fl = 2.0 * 12_500 * 1_000_000 * 256
+    out["cfg5_per_gpu_share"] = {"config": "12,500 bf16 queries x 1,000,000 bf16 gallery rows, D=256, top-10 (1/8 of cfg5's queries)",
+                                 "kernel_ms": ms, "tflops": fl / ms / 1e9, "frac_of_peak": fl / ms / 1e9 / peak,
+                                 "queries_per_s_per_gpu": 12_500 / (ms * 1e-3)}
+    del gal, qry, Q, G
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():

@@ -479,6 +479,13 @@ int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
   static_assert(sizeof(TopK1::Params) == sizeof(TopK2::Params), "parameter layouts must agree");
   memset(&EP, 0, sizeof(EP));
   if (const char* dbg = getenv("LECCR_TOPK_DEBUG")) EP.debug_mode = atoi(dbg);  // measurement aid only
+  // shrink rounds start when a list holds more than `trig`; long chunks prefer fresher thresholds
+  // (fewer candidates pass), short ones fewer rounds (measured optimum is flat between 36 and 56)
+  EP.trig = two ? TopK2::TRIG : (plans[0].tiles_per_chunk >= 64 ? 40 : TopK1::TRIG);
+  if (const char* tg = getenv("LECCR_TOPK_TRIG")) EP.trig = std::min(EP.trig, std::max(LECCR_TOPK_KP + 4, atoi(tg)));
+  if (const char* dc = getenv("LECCR_TOPK_COUNTERS")) {  // measurement aid only: device address (hex) of 5 x u64
+    EP.debug_counters = reinterpret_cast<unsigned long long*>(strtoull(dc, nullptr, 16));
+  }
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   float* cand_val[2];
   int* cand_idx[2];

@@ -107,6 +107,43 @@ struct EpiStore {
 // Nothing <= thr can belong to the row's top-KP, so the union of a row's lists over its column
 // chunks contains the exact top-KP of the approximate scores; topk_finalize selects them.
 // ------------------------------------------------------------------------------------------
+// Compare-exchange and bitonic networks on register arrays (all indices are compile-time constants
+// after unrolling): branch-free, high ILP -- unlike counting loops they are not latency-bound.
+__device__ __forceinline__ void cex_desc(float& a, float& b) {
+  const float hi = fmaxf(a, b), lo = fminf(a, b);
+  a = hi;
+  b = lo;
+}
+template <int N>
+__device__ __forceinline__ void bitonic_merge_desc(float* a) {  // a bitonic -> sorted descending
+#pragma unroll
+  for (int j = N >> 1; j > 0; j >>= 1)
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if ((i ^ j) > i) cex_desc(a[i], a[i ^ j]);
+}
+template <int N>
+__device__ __forceinline__ void bitonic_sort_desc(float* a) {
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1)
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1)
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const int l = i ^ j;
+        if (l > i) {
+          if ((i & k) == 0) cex_desc(a[i], a[l]);
+          else cex_desc(a[l], a[i]);
+        }
+      }
+}
+// top-16 (as a set, in a[0..16)) of two descending-sorted 16-lists a, b; sorted again if `resort`
+__device__ __forceinline__ void top16_of_two(float* a, const float* b, bool resort) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = fmaxf(a[i], b[15 - i]);
+  if (resort) bitonic_merge_desc<16>(a);
+}
+
 // Two shapes: <16, 64, 1> one warpgroup with 64-entry lists, <16, 32, 2> two warpgroups (alternate
 // tiles) with 32-entry lists; in both the lists take 66 KB of shared memory.  The two threads that own
 // the same row (and the CTAs that own other column chunks of it) cooperate through row_thr.
@@ -117,8 +154,9 @@ struct EpiTopK {
   static constexpr int LDSW = C + 1;     // row pitch in words: conflict-free for per-thread and per-row access
   static constexpr int TRIG = C - 8;     // a group of 8 columns must always fit
   static constexpr int G = C / 16;       // strided group size of the cheap shrink (16 groups)
-  static constexpr int KEEP = C / 2 > KP ? C / 2 : KP + 2;  // the exact (bisection) shrink stops once this few remain
-  static constexpr int JOIN = C == 64 ? 48 : 22;  // rows at least this full shrink whenever any row of the warp must
+  static constexpr int KEEP = KP + 2;    // the bisection fallback stops once this few remain
+  static constexpr int JOIN = KP + 4;    // every row fuller than this shrinks whenever any row of the warp must:
+                                          // one round refreshes (nearly) all 32 thresholds, so rounds stay rare
   static_assert(KP == 16 && (C == 64 || C == 32), "the cheap shrink takes 16 strided groups of a 32/64-entry list");
   static_assert(KP <= KEEP && KEEP < JOIN && JOIN <= TRIG, "inconsistent list policy");
   struct Params {
@@ -128,6 +166,8 @@ struct EpiTopK {
     int n_sub[2];       // partial lists per row: n_chunks * kWGs
     unsigned* row_thr[2];  // [n_rows] shared per-row threshold keys (zeroed per launch), or null
     int debug_mode;     // measurement aid: 1 = threshold +inf (filter only), 2 = skip the tile entirely
+    unsigned long long* debug_counters;  // measurement aid: [chunks, hit chunks, hit groups, shrink rounds, appends]
+    int trig;           // a shrink round starts when some row of the warp holds more than this (<= TRIG)
   };
   static constexpr int kSmemBytes = 2 * kEpiThreads * LDSW * 4;
   static constexpr int kIdxOff = kEpiThreads * LDSW * 4;  // byte offset from a value slot to its index slot
@@ -135,11 +175,14 @@ struct EpiTopK {
     float thr;
     int cnt;
     uint32_t vb, ib;  // shared-window addresses of this thread's value / index list
+    unsigned dc[5];   // debug counters (per thread; lane 0's are warp-level events)
   };
 
   __device__ static void begin(State& st, const Params& P, const ItemCtx& c) {
     st.thr = P.debug_mode == 1 ? CUDART_INF_F : -CUDART_INF_F;
     st.cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) st.dc[i] = 0;
     st.vb = smem_u32(c.smem) + static_cast<uint32_t>(c.et) * LDSW * 4;
     st.ib = st.vb + kEpiThreads * LDSW * 4;
   }
@@ -159,10 +202,11 @@ struct EpiTopK {
     return (static_cast<unsigned long long>(__float_as_uint(thr)) << 32) | static_cast<unsigned>(cnt);
   }
 
-  // Cheap, branch-free shrink: the minimum tau of the 16 maxima of the strided quads
-  // {k, k+16, k+32, k+48} has at least 16 listed scores >= tau, so it is a valid new threshold;
-  // keep the entries >= tau (typically ~24 of 64).  If that frees too little (adversarial order or
-  // ties) the exact bisection shrink takes over.
+  // Branch-free shrink: tau = the exact 16th largest listed score, found with sorting networks in
+  // registers (sort the groups of 16, merge keeping the top 16); keep the entries >= tau, i.e. 16
+  // unless scores tie.  (A cheaper bound -- the minimum of 16 strided quad maxima -- keeps 36 of 64
+  // on average: the threshold then sits at the 36th best and twice as many later scores pass it.)
+  // Ties that leave the list too full fall through to the bisection shrink.
   __device__ __noinline__ static unsigned long long quad_shrink(float thr_in, int n, uint32_t vb, uint32_t ib) {
     float x[C];
 #pragma unroll
@@ -170,22 +214,28 @@ struct EpiTopK {
       x[s] = lds_f32(vb + s * 4);
       if (s >= n) x[s] = -CUDART_INF_F;
     }
-    float tau = CUDART_INF_F;
+    // exact 16th largest of the list: sort the C/16 groups of 16, merge keeping the top 16
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      float gm = x[k];
-#pragma unroll
-      for (int q = 1; q < G; ++q) gm = fmaxf(gm, x[k + 16 * q]);
-      tau = fminf(tau, gm);
+    for (int q = 0; q < G; ++q) bitonic_sort_desc<16>(x + 16 * q);
+    if (G == 4) {
+      top16_of_two(x, x + 16, true);
+      top16_of_two(x + 32, x + 48, true);
+      top16_of_two(x, x + 32, false);
+    } else {
+      top16_of_two(x, x + 16, false);
     }
+    float tau = x[0];
+#pragma unroll
+    for (int k = 1; k < 16; ++k) tau = fminf(tau, x[k]);
     // an adopted (shared) threshold may already exceed tau: then everything below it is dead too
     const float te = fmaxf(tau, thr_in);
     int j = 0;
-#pragma unroll
-    for (int s = 0; s < C; ++s) {
+#pragma unroll 8
+    for (int s = 0; s < C; ++s) {  // the network permuted x: re-read the list
+      const float xs = lds_f32(vb + s * 4);
       const int id = lds_s32(ib + s * 4);
-      if (x[s] >= te) {  // -inf padding never passes unless te = -inf (n < 16: nothing to do)
-        sts_f32(vb + j * 4, x[s]);
+      if (s < n && xs >= te) {
+        sts_f32(vb + j * 4, xs);
         sts_s32(ib + j * 4, id);
         ++j;
       }
@@ -278,20 +328,25 @@ struct EpiTopK {
       unsigned hm = (gm[0] > st.thr ? 1u : 0u) | (gm[1] > st.thr ? 2u : 0u) | (gm[2] > st.thr ? 4u : 0u) |
                     (gm[3] > st.thr ? 8u : 0u);
       hm = __reduce_or_sync(0xffffffffu, hm);
+      ++st.dc[0];
       if (hm == 0u) return;  // warp-uniform; on long rows almost every chunk ends here
+      ++st.dc[1];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         if (hm & (1u << g)) {  // warp-uniform
+          ++st.dc[2];
           const float thr = st.thr;
           int cnt = st.cnt;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {  // predicated appends, no divergence
+          for (int e = 0; e < 8; ++e) {  // predicated appends: straight-line code beats any branch here
             const float x = v[8 * g + e];
             sts_pair_if_gt(x, thr, st.vb + cnt * 4, st.ib + cnt * 4, col + 8 * g + e);
             cnt += (x > thr) ? 1 : 0;
           }
+          st.dc[4] += cnt - st.cnt;
           st.cnt = cnt;
-          if (__any_sync(0xffffffffu, cnt > TRIG)) {
+          if (__any_sync(0xffffffffu, cnt > P.trig)) {
+            ++st.dc[3];
             if (cnt > JOIN) {
               const unsigned long long r = quad_shrink(st.thr, cnt, st.vb, st.ib);
               st.thr = __uint_as_float(static_cast<unsigned>(r >> 32));
@@ -307,6 +362,13 @@ struct EpiTopK {
   // Dump the raw lists; rows of a warp are written one after another so stores coalesce.
   __device__ static void end(State& st, const Params& P, const ItemCtx& c) {
     __syncwarp();
+    if (P.debug_counters != nullptr) {
+      const unsigned app = __reduce_add_sync(0xffffffffu, st.dc[4]);
+      if (c.lane == 0) {
+        for (int i = 0; i < 4; ++i) atomicAdd(P.debug_counters + i, static_cast<unsigned long long>(st.dc[i]));
+        atomicAdd(P.debug_counters + 4, static_cast<unsigned long long>(app));
+      }
+    }
     const int nch = P.n_sub[c.p];
     const uint32_t wbase = smem_u32(c.smem) + static_cast<uint32_t>(c.warp_q * 32) * LDSW * 4;
 #pragma unroll 1
