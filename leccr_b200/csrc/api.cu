@@ -563,7 +563,11 @@ int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
     F.flag_list = flag[p] + 4;
     F.gt_score = q.gt_score;
     const unsigned grid = static_cast<unsigned>((q.n_rows + kFinalizeWarps - 1) / kFinalizeWarps);
-    topk_finalize_kernel<<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
+    const int slots = F.n_chunks * (cap / 32);
+    if (slots <= 2) topk_finalize_kernel<2><<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
+    else if (slots <= 4) topk_finalize_kernel<4><<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
+    else if (slots <= 8) topk_finalize_kernel<8><<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
+    else topk_finalize_kernel<kMaxSlots><<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
     LAUNCH_CHECK("topk_finalize_kernel");
     prof_mark("topk:finalize", stream);
     if (q.gt_off != nullptr) {

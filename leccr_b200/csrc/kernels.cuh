@@ -437,6 +437,9 @@ __device__ __forceinline__ float warp_dot(const void* rows_x, long long ld_rows,
   return warp_sum(s);
 }
 
+// SLOTS = candidate slots per lane this instantiation handles (>= n_lists * list_cap / 32): the
+// selection loops are fully unrolled over it, so short merges do not pay for long ones.
+template <int SLOTS>
 __global__ void __launch_bounds__(kFinalizeWarps * 32) topk_finalize_kernel(const TopkFinalizeParams P) {
   __shared__ float s_val[kFinalizeWarps][32];
   __shared__ int s_idx[kFinalizeWarps][32];
@@ -449,10 +452,10 @@ __global__ void __launch_bounds__(kFinalizeWarps * 32) topk_finalize_kernel(cons
   const long long cbase = static_cast<long long>(row) * P.n_chunks;
   // all loads are issued before any is consumed: list lengths (one lane each), then every slot
   const int my_cnt = lane < P.n_chunks ? __ldg(P.cand_cnt + cbase + lane) : 0;
-  float v[kMaxSlots];
-  int id[kMaxSlots];
+  float v[SLOTS];
+  int id[SLOTS];
 #pragma unroll
-  for (int t = 0; t < kMaxSlots; ++t) {
+  for (int t = 0; t < SLOTS; ++t) {
     v[t] = -CUDART_INF_F;
     id[t] = -1;
     if (t < per_lane) {
@@ -464,7 +467,7 @@ __global__ void __launch_bounds__(kFinalizeWarps * 32) topk_finalize_kernel(cons
   float gmax = -CUDART_INF_F, gmin = CUDART_INF_F;
   int n_loc = 0;
 #pragma unroll
-  for (int t = 0; t < kMaxSlots; ++t) {
+  for (int t = 0; t < SLOTS; ++t) {
     const int cnt_t = __shfl_sync(0xffffffffu, my_cnt, t >> sh);
     if (t < per_lane && lane + 32 * (t & sh) < cnt_t) {
       gmax = fmaxf(gmax, v[t]);
@@ -493,7 +496,7 @@ __global__ void __launch_bounds__(kFinalizeWarps * 32) topk_finalize_kernel(cons
     const float mid = key_f32(mid_k);
     int cm = 0;
 #pragma unroll
-    for (int t = 0; t < kMaxSlots; ++t) cm += (id[t] >= 0 && v[t] > mid) ? 1 : 0;
+    for (int t = 0; t < SLOTS; ++t) cm += (id[t] >= 0 && v[t] > mid) ? 1 : 0;
     cm = __reduce_add_sync(0xffffffffu, cm);
     if (cm >= KP) {
       lo_k = mid_k;
@@ -511,7 +514,7 @@ __global__ void __launch_bounds__(kFinalizeWarps * 32) topk_finalize_kernel(cons
   int base = 0;
   const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
-  for (int t = 0; t < kMaxSlots; ++t) {
+  for (int t = 0; t < SLOTS; ++t) {
     const bool sel = id[t] >= 0 && v[t] > keep_thr;
     const unsigned m = __ballot_sync(0xffffffffu, sel);
     const int pos = base + __popc(m & lt_mask);
@@ -523,7 +526,7 @@ __global__ void __launch_bounds__(kFinalizeWarps * 32) topk_finalize_kernel(cons
   }
   if (tie) {  // more than 32 equal scores at the threshold: any of them completes the list
 #pragma unroll
-    for (int t = 0; t < kMaxSlots; ++t) {
+    for (int t = 0; t < SLOTS; ++t) {
       const bool sel = id[t] >= 0 && !(v[t] > keep_thr) && v[t] > lo;
       const unsigned m = __ballot_sync(0xffffffffu, sel);
       const int pos = base + __popc(m & lt_mask);

@@ -243,6 +243,61 @@ def fused_eval(image_embeds, text_embeds, txt2img=None, img2txt=None, k=10, prec
     return ev, {'i2t': (r_i.val, r_i.idx), 't2i': (r_t.val, r_t.idx)}
 
 
+class FusedEvalPlan:
+    """Repeated fused evaluations of one shape (serving / per-epoch validation): static device buffers and
+    the whole step (cast -> tensor-core pass -> finalize -> Recall counts) captured once in a CUDA graph, so
+    a run is one H2D (if the inputs are on the host), one graph launch and one 32-byte D2H.
+
+        plan = FusedEvalPlan(n_img, n_txt, dim, txt2img, img2txt)
+        ev = plan.run(image_embeds, text_embeds)          # host (ideally pinned) or device fp32 tensors
+        ev, topk = plan.run(..., return_topk=True)        # topk tensors are overwritten by the next run
+    """
+
+    def __init__(self, n_img, n_txt, dim, txt2img=None, img2txt=None, k=10, precision="f16", gt=None,
+                 tiles_per_chunk=0):
+        self.dev = _device()
+        self.n_img, self.n_txt, self.k = n_img, n_txt, k
+        self.fmt = ops.fmt_of(precision)
+        self.tpc = tiles_per_chunk
+        self.gt = gt if gt is not None else prepare_gt(txt2img, img2txt, n_img, n_txt, self.dev)
+        self.img = torch.zeros((n_img, dim), dtype=torch.float32, device=self.dev)
+        self.txt = torch.zeros((n_txt, dim), dtype=torch.float32, device=self.dev)
+        self.img[:, 0] = 1.0  # harmless unit rows for the capture run
+        self.txt[:, 0] = 1.0
+        self.host = torch.empty(8, dtype=torch.float32).pin_memory()
+        self._step()  # warm-up outside capture: lazy module load, kernel attributes
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._step()
+
+    def _step(self):
+        I, T = ops.prep(self.img, self.fmt), ops.prep(self.txt, self.fmt)
+        r_i, r_t = ops.sim_topk([(I, T, self.gt[0]), (T, I, self.gt[1])], k=self.k, tiles_per_chunk=self.tpc)
+        self.out = torch.cat([r_i.recall_counts.float(), r_t.recall_counts.float(), I.stats[3:4], T.stats[3:4]])
+        self.topk = {'i2t': (r_i.val, r_i.idx), 't2i': (r_t.val, r_t.idx)}
+        self.ranks = (r_i.rank, r_t.rank)
+
+    def launch(self, image_embeds=None, text_embeds=None):
+        """Asynchronous part of a run: stage the inputs (if given) and replay the graph."""
+        if image_embeds is not None:
+            self.img.copy_(torch.as_tensor(image_embeds), non_blocking=True)
+        if text_embeds is not None:
+            self.txt.copy_(torch.as_tensor(text_embeds), non_blocking=True)
+        self.graph.replay()
+
+    @torch.no_grad()
+    def run(self, image_embeds=None, text_embeds=None, return_topk=False):
+        self.launch(image_embeds, text_embeds)
+        self.host.copy_(self.out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h = self.host.tolist()
+        if h[6] != 0.0 or h[7] != 0.0:
+            raise N.LeccrError("embeddings overflow the fp16 operand format; build the plan with precision='bf16'")
+        ev = metrics_from_counts([int(c) for c in h[0:3]], self.n_img, [int(c) for c in h[3:6]], self.n_txt)
+        return (ev, self.topk) if return_topk else ev
+
+
 # ----------------------------------------------------------------------------- multi-GPU (SURVEY.md section 8e)
 @torch.no_grad()
 def fused_eval_sharded(image_embeds, text_embeds, txt2img, img2txt, k=10, precision="f16", group=None):

@@ -246,3 +246,19 @@ def test_contrastive_local_rows_of_a_larger_gather():
                                                          dtype=torch.float64)
         assert (dA.cpu().double() - ra).norm() <= 2e-3 * ra.norm()
         assert (dB.cpu().double() - rb).norm() <= 2e-3 * rb.norm()
+
+
+def test_fused_eval_plan_matches_reference(golden):
+    """The CUDA-graph plan (repeated evaluation path) gives the reference's dict, run after run."""
+    g = golden("baseline_configs.npz")
+    rs = synth.cfg1_multi30k()
+    plan = leccr_b200.FusedEvalPlan(1000, 5000, 256, rs.txt2img, rs.img2txt)
+    for _ in range(2):
+        ev, topk = plan.run(rs.image, rs.text, return_topk=True)
+        assert_ev_equal(ev, ev_of(g, "cfg1_ev_"))
+    i2t, _ = oracle.score_matrices(rs.image, rs.text)
+    check_topk_against(i2t, *topk["i2t"], 10, F16_TOL)
+    other = synth.retrieval_set(1000, 5, 256, seed=77)          # same shape, different data, same plan
+    ev2 = plan.run(other.image.pin_memory(), other.text.pin_memory())
+    o_i2t, o_t2i = oracle.score_matrices(other.image, other.text)
+    assert_ev_equal(ev2, oracle.itm_eval_by_count(o_i2t, o_t2i, other.txt2img, other.img2txt))
