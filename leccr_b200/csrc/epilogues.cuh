@@ -168,6 +168,10 @@ struct EpiTopK {
     int debug_mode;     // measurement aid: 1 = threshold +inf (filter only), 2 = skip the tile entirely
     unsigned long long* debug_counters;  // measurement aid: [chunks, hit chunks, hit groups, shrink rounds, appends]
     int trig;           // a shrink round starts when some row of the warp holds more than this (<= TRIG)
+    int dense;          // While nearly every 8-column group holds a candidate for one of the warp's 32 rows
+                        // (threshold warm-up, short rows) the filter and its branches only cost: such tiles
+                        // append (predicated) all 32 columns of every chunk.  0 never, 1 always, 2 adaptive:
+                        // the first tiles of a work item, then again whenever >= 6 of a tile's 8 chunks hit.
   };
   static constexpr int kSmemBytes = 2 * kEpiThreads * LDSW * 4;
   static constexpr int kIdxOff = kEpiThreads * LDSW * 4;  // byte offset from a value slot to its index slot
@@ -176,6 +180,7 @@ struct EpiTopK {
     int cnt;
     uint32_t vb, ib;  // shared-window addresses of this thread's value / index list
     unsigned dc[5];   // debug counters (per thread; lane 0's are warp-level events)
+    int dense_tiles;  // warp-uniform: upcoming tiles to run without the filter (see Params::dense)
   };
 
   __device__ static void begin(State& st, const Params& P, const ItemCtx& c) {
@@ -183,6 +188,7 @@ struct EpiTopK {
     st.cnt = 0;
 #pragma unroll
     for (int i = 0; i < 5; ++i) st.dc[i] = 0;
+    st.dense_tiles = P.dense == 2 ? 4 : 0;
     st.vb = smem_u32(c.smem) + static_cast<uint32_t>(c.et) * LDSW * 4;
     st.ib = st.vb + kEpiThreads * LDSW * 4;
   }
@@ -312,11 +318,43 @@ struct EpiTopK {
       const unsigned k = *reinterpret_cast<volatile unsigned*>(shared_thr);
       if (k > f32_key(st.thr)) st.thr = key_f32(k);
     }
+    const bool dense = P.dense == 1 || st.dense_tiles > 0;  // warp-uniform
+    if (st.dense_tiles > 0) --st.dense_tiles;
+    if (dense && __any_sync(0xffffffffu, st.cnt > C - 32)) {  // the dense path appends up to 32 per chunk
+      if (st.cnt > JOIN) {
+        const unsigned long long r = quad_shrink(st.thr, st.cnt, st.vb, st.ib);
+        st.thr = __uint_as_float(static_cast<unsigned>(r >> 32));
+        st.cnt = static_cast<int>(r & 0xffffffffu);
+        if (shared_thr != nullptr) atomicMax(shared_thr, f32_key(st.thr));
+      }
+    }
+    int hit_chunks = 0;  // warp-uniform
     for_each_chunk(taddr, col0, n_cols, [&](float(&v)[32], int col) {
       if (col + 32 > n_cols) {  // ragged last columns (TMA zero-filled): exclude them
 #pragma unroll
         for (int e = 0; e < 32; ++e)
           if (col + e >= n_cols) v[e] = -CUDART_INF_F;
+      }
+      if (dense) {  // warp-uniform; requires cnt <= C - 32 on entry (rounds start above C - 32)
+        const float thr = st.thr;
+        int cnt = st.cnt;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          sts_pair_if_gt(v[e], thr, st.vb + cnt * 4, st.ib + cnt * 4, col + e);
+          cnt += (v[e] > thr) ? 1 : 0;
+        }
+        st.dc[4] += cnt - st.cnt;
+        st.cnt = cnt;
+        if (__any_sync(0xffffffffu, cnt > C - 32)) {
+          ++st.dc[3];
+          if (cnt > JOIN) {
+            const unsigned long long r = quad_shrink(st.thr, cnt, st.vb, st.ib);
+            st.thr = __uint_as_float(static_cast<unsigned>(r >> 32));
+            st.cnt = static_cast<int>(r & 0xffffffffu);
+            if (shared_thr != nullptr) atomicMax(shared_thr, f32_key(st.thr));
+          }
+        }
+        return;
       }
       float gm[4];
 #pragma unroll
@@ -331,6 +369,7 @@ struct EpiTopK {
       ++st.dc[0];
       if (hm == 0u) return;  // warp-uniform; on long rows almost every chunk ends here
       ++st.dc[1];
+      ++hit_chunks;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         if (hm & (1u << g)) {  // warp-uniform
@@ -357,6 +396,7 @@ struct EpiTopK {
         }
       }
     });
+    if (P.dense == 2 && hit_chunks >= 6) st.dense_tiles = 4;
   }
 
   // Dump the raw lists; rows of a warp are written one after another so stores coalesce.

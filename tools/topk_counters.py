@@ -13,6 +13,6 @@ for (n, m, dt, both) in [(5000, 25000, torch.float32, True), (12500, 1000000, to
     cnt.zero_(); ops.sim_topk(probs, k=10); torch.cuda.synchronize()
     c = cnt.tolist()
     rows = n + (m if both else 0)
-    print(f"n={n} m={m} both={both}: warp-chunks {c[0]}, hit chunks {c[1]} ({100*c[1]/c[0]:.1f}%), hit groups {c[2]} ({c[2]/max(1,c[1]):.2f}/hit chunk), "
+    print(f"n={n} m={m} both={both}: warp-chunks {c[0]}, hit chunks {c[1]} ({100*c[1]/max(1,c[0]):.1f}%), hit groups {c[2]} ({c[2]/max(1,c[1]):.2f}/hit chunk), "
           f"shrink rounds {c[3]} ({c[3]/(rows/32):.1f}/warp-rowset), appends {c[4]} ({c[4]/rows:.1f}/row)")
     del q, g, Q, G
