@@ -79,6 +79,17 @@ int leccr_profile_read(double* total_ms, int* launches);
 int leccr_prep(const float* src, int64_t n, int D, int64_t ld_src, int normalize, int fmt, int layout,
                void* dst16, int64_t ld_dst, float* rn_hi, float* rn_lo, float* stats,
                leccr_stream_t stream);
+/* The cast prologue fused with its all-gather (replaces AllGather.forward, models/xvlm.py:53-59, for the
+ * contrastive operands): casts this rank's n rows and stores them into EVERY rank's gathered operand
+ * buffer at [dst_row0 + i][dst_col0 ...] through peer pointers (NVLink).  dst_ptrs_dev: device array of
+ * `world` base pointers of symmetric buffers (own included), leading dimension ld_dst elements.
+ * The caller issues a cross-rank barrier before anyone reads the gathered buffers. */
+int leccr_prep_push(const float* src, int64_t n, int D, int64_t ld_src, int normalize, int fmt,
+                    void* const* dst_ptrs_dev, int world, int64_t dst_row0, int64_t dst_col0, int64_t ld_dst,
+                    leccr_stream_t stream);
+/* Same exchange for a block of 8-byte words (the idx labels, models/xvlm.py:285). */
+int leccr_push_words(const void* src, int64_t n_words, void* const* dst_ptrs_dev, int world, int64_t dst_word0,
+                     leccr_stream_t stream);
 int leccr_stats16(const void* src16, int fmt, int64_t n, int D, int64_t ld_src, float* rn_hi,
                   float* rn_lo, float* stats, leccr_stream_t stream);
 /* [n][D] -> [D][ld_dst] (ld_dst >= n, columns n..ld_dst zero-filled). */

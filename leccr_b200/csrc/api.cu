@@ -280,6 +280,38 @@ int leccr_prep(const float* src, int64_t n, int D, int64_t ld_src, int normalize
   return LECCR_OK;
 }
 
+int leccr_prep_push(const float* src, int64_t n, int D, int64_t ld_src, int normalize, int fmt,
+                    void* const* dst_ptrs_dev, int world, int64_t dst_row0, int64_t dst_col0, int64_t ld_dst,
+                    leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (src == nullptr || dst_ptrs_dev == nullptr || n <= 0 || D <= 0 || bad_fmt(fmt) || world < 1 || ld_src < D ||
+      dst_row0 < 0 || dst_col0 < 0 || ld_dst < dst_col0 + D)
+    return LECCR_ERR_ARG;
+  const int wpb = 8;
+  const unsigned grid = static_cast<unsigned>((n + wpb - 1) / wpb);
+  uint16_t* const* dsts = reinterpret_cast<uint16_t* const*>(dst_ptrs_dev);
+  if (fmt == LECCR_FMT_F16)
+    prep_push_kernel<0><<<grid, wpb * 32, 0, stream>>>(src, ld_src, (int)n, D, normalize, dsts, world, dst_row0,
+                                                      dst_col0, ld_dst);
+  else
+    prep_push_kernel<1><<<grid, wpb * 32, 0, stream>>>(src, ld_src, (int)n, D, normalize, dsts, world, dst_row0,
+                                                      dst_col0, ld_dst);
+  LAUNCH_CHECK("prep_push_kernel");
+  return LECCR_OK;
+}
+
+int leccr_push_words(const void* src, int64_t n_words, void* const* dst_ptrs_dev, int world, int64_t dst_word0,
+                     leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (src == nullptr || dst_ptrs_dev == nullptr || n_words <= 0 || world < 1 || dst_word0 < 0) return LECCR_ERR_ARG;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>((n_words + 255) / 256, 2LL * num_sms()));
+  push_words_kernel<<<grid, 256, 0, stream>>>(static_cast<const unsigned long long*>(src), n_words,
+                                             reinterpret_cast<unsigned long long* const*>(dst_ptrs_dev), world,
+                                             dst_word0);
+  LAUNCH_CHECK("push_words_kernel");
+  return LECCR_OK;
+}
+
 int leccr_stats16(const void* src16, int fmt, int64_t n, int D, int64_t ld_src, float* rn_hi, float* rn_lo,
                   float* stats, leccr_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

@@ -215,6 +215,56 @@ __global__ void prep_rows_vec_kernel(const float* __restrict__ src, long long ld
   publish_stats(stats, a, b, amax, anybad != 0);
 }
 
+// --------------------------------------------------------------------------------
+// prep_push: the cast prologue fused with its all-gather.  Every rank casts ITS rows of the fp32
+// features to the 16-bit operand format and stores them straight into EVERY rank's gathered operand
+// buffer (peer pointers over NVLink, own pointer included) at its row offset -- the exchange of
+// models/xvlm.py:53-59 happens inside the kernel that produces the data, no separate collective.
+// dsts: device array of `world` base pointers (symmetric buffers, one per rank).  One warp per row.
+// --------------------------------------------------------------------------------
+template <int FMT>
+__global__ void prep_push_kernel(const float* __restrict__ src, long long ld_src, int n, int D, int normalize,
+                                 uint16_t* const* __restrict__ dsts, int world, long long dst_row0,
+                                 long long dst_col0, long long ld_dst) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float* x = src + static_cast<long long>(row) * ld_src;
+  float inv = 1.f;
+  if (normalize) {
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) ss = fmaf(x[d], x[d], ss);
+    inv = 1.f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+  }
+  const long long off = (dst_row0 + row) * ld_dst + dst_col0;
+  const bool vec = (D & 3) == 0 && (ld_src & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+                   (ld_dst & 3) == 0 && (dst_col0 & 3) == 0;
+  if (vec) {
+    for (int d = 4 * lane; d < D; d += 128) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(x + d));
+      const uint16_t h0 = f32_to_16<FMT>(t.x * inv), h1 = f32_to_16<FMT>(t.y * inv);
+      const uint16_t h2 = f32_to_16<FMT>(t.z * inv), h3 = f32_to_16<FMT>(t.w * inv);
+      const uint2 hv = make_uint2(h0 | (static_cast<uint32_t>(h1) << 16), h2 | (static_cast<uint32_t>(h3) << 16));
+      for (int p = 0; p < world; ++p) *reinterpret_cast<uint2*>(dsts[p] + off + d) = hv;  // peer stores
+    }
+  } else {
+    for (int d = lane; d < D; d += 32) {
+      const uint16_t h = f32_to_16<FMT>(x[d] * inv);
+      for (int p = 0; p < world; ++p) dsts[p][off + d] = h;
+    }
+  }
+}
+
+// Push a contiguous block of 8-byte words (the idx column, models/xvlm.py:285) to every rank's buffer.
+__global__ void push_words_kernel(const unsigned long long* __restrict__ src, long long n_words,
+                                  unsigned long long* const* __restrict__ dsts, int world, long long dst_word0) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_words;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const unsigned long long w = src[i];
+    for (int p = 0; p < world; ++p) dsts[p][dst_word0 + i] = w;
+  }
+}
+
 // Row norms / maxima of an operand that is already 16-bit (e.g. a bf16-stored gallery).
 template <int FMT>
 __global__ void stats_rows16_kernel(const uint16_t* __restrict__ src, long long ld_src, int n, int D,
