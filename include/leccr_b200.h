@@ -193,6 +193,25 @@ int leccr_recall_counts(const int32_t* rank, int64_t n, int32_t* counts, leccr_s
 int leccr_double_sim_fuse(float* S, const float* Cn, int n_cap, int64_t numel, float* Cmax, uint32_t* mm,
                           float w1, float w2, int mode, leccr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Cross-rank exchange over peer memory (one node, NVLink / NVSwitch).  The pointer
+ * tables are device arrays of `world` device pointers into peer-mapped (symmetric) buffers, own rank
+ * included; the Python shim obtains them from torch.distributed._symmetric_memory.
+ *
+ * leccr_peer_barrier: stream-ordered barrier across the ranks.  flag_ptrs_dev[p] -> rank p's block of
+ *   `world` uint32 words (zero-initialised once); `epoch` must grow by one per barrier on every rank.
+ *   Orders all earlier peer stores of this stream before all later work of the peers' streams.
+ * leccr_topk_merge_peers: the exchange step of the row-partitioned gallery (replaces nothing in the
+ *   reference, which ranks on one CPU; north_star layout).  Rank p published its per-query local top-k
+ *   ([Q][k_in] fp32 descending / int32 local columns, ties by lower column) in its peer-visible buffer;
+ *   this call pulls the lists of queries [q_begin, q_begin + q_count) from all ranks and merges them in
+ *   ONE kernel: out [q_count][k_out], global column = local + col_offset_host[p].
+ * ------------------------------------------------------------------------------------------ */
+int leccr_peer_barrier(uint32_t* const* flag_ptrs_dev, int world, int rank, uint32_t epoch, leccr_stream_t stream);
+int leccr_topk_merge_peers(const float* const* val_ptrs_dev, const int32_t* const* idx_ptrs_dev, int world, int k_in,
+                           int64_t q_begin, int64_t q_count, const int64_t* col_offset_host, int k_out,
+                           float* out_val, int32_t* out_idx, leccr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,8 @@ _SIGNATURES = {
     "leccr_prep": (c_int, [vp, i64, c_int, i64, c_int, c_int, c_int, vp, i64, vp, vp, vp, vp]),
     "leccr_prep_push": (c_int, [vp, i64, c_int, i64, c_int, c_int, vp, c_int, i64, i64, i64, vp]),
     "leccr_push_words": (c_int, [vp, i64, vp, c_int, i64, vp]),
+    "leccr_peer_barrier": (c_int, [vp, c_int, c_int, ctypes.c_uint32, vp]),
+    "leccr_topk_merge_peers": (c_int, [vp, vp, c_int, c_int, i64, i64, ctypes.POINTER(i64), c_int, vp, vp, vp]),
     "leccr_stats16": (c_int, [vp, c_int, i64, c_int, i64, vp, vp, vp, vp]),
     "leccr_transpose16": (c_int, [vp, i64, c_int, i64, vp, i64, vp]),
     "leccr_sim_f32": (c_int, [vp, i64, vp, i64, i64, i64, c_int, c_int, vp, i64, c_float, vp, vp]),

@@ -5,8 +5,9 @@ Same signature and semantics: `get_contrastive_loss(self, image_feat, text_feat,
 the symmetric InfoNCE loss as a 0-d tensor wired into autograd: gradients reach the LOCAL rows of
 image_feat / text_feat (what AllGather.backward keeps) and `self.temp`.
 
-Mechanism: the local rows are cast to 16-bit tensor-core operands BEFORE the exchange (one NCCL
-all-gather of [image | text] halves instead of two fp32 ones), the N x N logits live only in TMEM, the
+Mechanism: the local rows are cast to 16-bit tensor-core operands BEFORE the exchange; on one NVLink node
+the cast kernel itself performs the exchange through peer pointers (leccr_prep_push; one barrier kernel
+instead of three collectives), elsewhere one all-gather of the [image | text] halves replaces two fp32 ones; the N x N logits live only in TMEM, the
 forward emits per-row log-sum-exp statistics and d loss / d temp, and the backward recomputes the logits
 of the local row strips only.
 """
@@ -15,6 +16,7 @@ import torch.distributed as dist
 
 from . import _native as N
 from . import ops
+from . import peer
 from .allgather import gather_into
 
 PRECISION = "f16"  # tensor-core operand format for fp32 inputs: "f16" (default) or "bf16"
@@ -35,14 +37,20 @@ class _SymmetricInfoNCE(torch.autograd.Function):
         n = B * world
         dev = image_feat.device
         dt16 = torch.float16 if fmt == N.FMT_F16 else torch.bfloat16
-        # local cast, then one exchange of the packed [image | text] 16-bit rows
-        local = torch.empty((B, 2 * D), dtype=dt16, device=dev)
-        ops.prep_into(image_feat.detach().float(), local[:, :D], fmt)
-        ops.prep_into(text_feat.detach().float(), local[:, D:], fmt)
-        both = gather_into(torch.empty((n, 2 * D), dtype=dt16, device=dev), local)
-        idx_all = None
-        if idx is not None:
-            idx_all = gather_into(torch.empty(n, dtype=torch.int64, device=dev), idx.detach().view(-1).long())
+        # One node, NCCL ranks: the cast kernel stores each rank's rows straight into every rank's gathered
+        # operand buffer through peer pointers (leccr_b200.peer).  Otherwise: local cast, then one
+        # all-gather of the packed [image | text] 16-bit rows (and one of idx).
+        pushed = peer.gather_contrastive(image_feat, text_feat, idx, fmt) if world > 1 else None
+        if pushed is not None:
+            both, idx_all = pushed
+        else:
+            local = torch.empty((B, 2 * D), dtype=dt16, device=dev)
+            ops.prep_into(image_feat.detach().float(), local[:, :D], fmt)
+            ops.prep_into(text_feat.detach().float(), local[:, D:], fmt)
+            both = gather_into(torch.empty((n, 2 * D), dtype=dt16, device=dev), local)
+            idx_all = None
+            if idx is not None:
+                idx_all = gather_into(torch.empty(n, dtype=torch.int64, device=dev), idx.detach().view(-1).long())
         a = ops.Operand(both[:, :D], fmt, N.LAYOUT_HI, n, D, None, None, None, both[:, :D])
         b = ops.Operand(both[:, D:], fmt, N.LAYOUT_HI, n, D, None, None, None, both[:, D:])
         temp_dev = temp.detach().reshape(()).float()

@@ -520,6 +520,7 @@ int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
   for (int p = 0; p < n_prob; ++p)
     if (plans[p].tiles_per_chunk > 32) EP.dense = 0;
   if (const char* dn = getenv("LECCR_TOPK_DENSE")) EP.dense = atoi(dn);  // measurement aid
+  if (two) EP.dense = 0;  // 32-entry lists cannot take 16 unfiltered columns between checks (DTRIG < JOIN)
   if (const char* tg = getenv("LECCR_TOPK_TRIG")) EP.trig = std::min(EP.trig, std::max(LECCR_TOPK_KP + 4, atoi(tg)));
   if (const char* dc = getenv("LECCR_TOPK_COUNTERS")) {  // measurement aid only: device address (hex) of 5 x u64
     EP.debug_counters = reinterpret_cast<unsigned long long*>(strtoull(dc, nullptr, 16));
@@ -838,6 +839,44 @@ int leccr_double_sim_fuse(float* S, const float* Cn, int n_cap, int64_t numel, f
   LAUNCH_CHECK("capmax_minmax_kernel");
   fuse_scores_kernel<<<g, 256, 0, stream>>>(S, Cmax, numel, mm, w1, w2, mode);
   LAUNCH_CHECK("fuse_scores_kernel");
+  return LECCR_OK;
+}
+
+int leccr_peer_barrier(uint32_t* const* flag_ptrs_dev, int world, int rank, uint32_t epoch, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (flag_ptrs_dev == nullptr || world < 1 || world > 32 || rank < 0 || rank >= world) return LECCR_ERR_ARG;
+  peer_barrier_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<unsigned* const*>(flag_ptrs_dev), world, rank, epoch);
+  LAUNCH_CHECK("peer_barrier_kernel");
+  return LECCR_OK;
+}
+
+int leccr_topk_merge_peers(const float* const* val_ptrs_dev, const int32_t* const* idx_ptrs_dev, int world, int k_in,
+                           int64_t q_begin, int64_t q_count, const int64_t* col_offset_host, int k_out,
+                           float* out_val, int32_t* out_idx, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (val_ptrs_dev == nullptr || idx_ptrs_dev == nullptr || world < 1 || world > kMergeMaxWorld || k_in < 1 ||
+      k_in > 64 || k_out < 1 || k_out > world * k_in || q_begin < 0 || q_count < 0 || out_val == nullptr ||
+      out_idx == nullptr)
+    return LECCR_ERR_ARG;
+  if (q_count == 0) return LECCR_OK;
+  MergeOffsets offs;
+  for (int p = 0; p < kMergeMaxWorld; ++p) {
+    const int64_t o = (col_offset_host != nullptr && p < world) ? col_offset_host[p] : 0;
+    if (o < 0 || o > 0x7fffffffLL) return LECCR_ERR_ARG;
+    offs.off[p] = static_cast<int>(o);
+  }
+  const int warps = 2;
+  const size_t smem = static_cast<size_t>(warps) * world * 32 * k_in * 8;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(topk_merge_peers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  if (smem > 200 * 1024) return LECCR_ERR_ARG;
+  const unsigned grid = static_cast<unsigned>((q_count + warps * 32 - 1) / (warps * 32));
+  topk_merge_peers_kernel<<<grid, warps * 32, smem, stream>>>(val_ptrs_dev, reinterpret_cast<const int* const*>(idx_ptrs_dev),
+                                                            world, k_in, q_begin, q_count, offs, k_out, out_val, out_idx);
+  LAUNCH_CHECK("topk_merge_peers_kernel");
   return LECCR_OK;
 }
 

@@ -64,6 +64,7 @@ struct EpiStore {
   struct State {};
   __device__ static void begin(State&, const Params&, const ItemCtx&) {}
   __device__ static void end(State&, const Params&, const ItemCtx&) {}
+  __device__ static void prefetch(State&, const Params&, const ItemCtx&) {}
   __device__ static void tile(State&, const Params& P, const ItemCtx& c, uint32_t taddr, int col0) {
     float scale = P.scale[c.p];
     if (P.scale_ptr[c.p] != nullptr) scale *= __ldg(P.scale_ptr[c.p]);
@@ -151,7 +152,8 @@ template <int KP, int C_, int WGS>
 struct EpiTopK {
   static constexpr int kWGs = WGS;
   static constexpr int C = C_;           // list capacity
-  static constexpr int LDSW = C + 1;     // row pitch in words: conflict-free for per-thread and per-row access
+  static constexpr int ES = 8;           // bytes per list entry: (score, column) interleaved so an append is ONE 64-bit store
+  static constexpr int LDSW = 2 * C + 2; // row pitch in words (even: 8-byte aligned entries; 64-bit per-thread accesses conflict-free)
   static constexpr int TRIG = C - 8;     // a group of 8 columns must always fit
   static constexpr int G = C / 16;       // strided group size of the cheap shrink (16 groups)
   static constexpr int KEEP = KP + 2;    // the bisection fallback stops once this few remain
@@ -173,15 +175,17 @@ struct EpiTopK {
                         // append (predicated) all 32 columns of every chunk.  0 never, 1 always, 2 adaptive:
                         // the first tiles of a work item, then again whenever >= 6 of a tile's 8 chunks hit.
   };
-  static constexpr int kSmemBytes = 2 * kEpiThreads * LDSW * 4;
-  static constexpr int kIdxOff = kEpiThreads * LDSW * 4;  // byte offset from a value slot to its index slot
+  static constexpr int kSmemBytes = kEpiThreads * LDSW * 4;
+  static constexpr int kIdxOff = 4;  // byte offset from a value slot to its index slot
   struct State {
     float thr;
     int cnt;
     uint32_t vb, ib;  // shared-window addresses of this thread's value / index list
     unsigned dc[5];   // debug counters (per thread; lane 0's are warp-level events)
     int dense_tiles;  // warp-uniform: upcoming tiles to run without the filter (see Params::dense)
+    unsigned pre_key; // shared threshold key fetched while waiting for the accumulator (see prefetch)
   };
+  static constexpr int DTRIG = C - 16;   // dense mode appends 16 columns between checks
 
   __device__ static void begin(State& st, const Params& P, const ItemCtx& c) {
     st.thr = P.debug_mode == 1 ? CUDART_INF_F : -CUDART_INF_F;
@@ -189,15 +193,16 @@ struct EpiTopK {
 #pragma unroll
     for (int i = 0; i < 5; ++i) st.dc[i] = 0;
     st.dense_tiles = P.dense == 2 ? 4 : 0;
+    st.pre_key = 0u;
     st.vb = smem_u32(c.smem) + static_cast<uint32_t>(c.et) * LDSW * 4;
-    st.ib = st.vb + kEpiThreads * LDSW * 4;
+    st.ib = st.vb + kIdxOff;
   }
 
   __device__ static int count_above(uint32_t vb, int n, float t) {
     int cgt = 0;
 #pragma unroll 8
     for (int s = 0; s < C; ++s) {
-      const float x = lds_f32(vb + s * 4);
+      const float x = lds_f32(vb + s * ES);
       cgt += (s < n && x > t) ? 1 : 0;
     }
     return cgt;
@@ -217,7 +222,7 @@ struct EpiTopK {
     float x[C];
 #pragma unroll
     for (int s = 0; s < C; ++s) {
-      x[s] = lds_f32(vb + s * 4);
+      x[s] = lds_f32(vb + s * ES);
       if (s >= n) x[s] = -CUDART_INF_F;
     }
     // exact 16th largest of the list: sort the C/16 groups of 16, merge keeping the top 16
@@ -238,11 +243,11 @@ struct EpiTopK {
     int j = 0;
 #pragma unroll 8
     for (int s = 0; s < C; ++s) {  // the network permuted x: re-read the list
-      const float xs = lds_f32(vb + s * 4);
-      const int id = lds_s32(ib + s * 4);
+      const float xs = lds_f32(vb + s * ES);
+      const int id = lds_s32(ib + s * ES);
       if (s < n && xs >= te) {
-        sts_f32(vb + j * 4, xs);
-        sts_s32(ib + j * 4, id);
+        sts_f32(vb + j * ES, xs);
+        sts_s32(ib + j * ES, id);
         ++j;
       }
     }
@@ -255,7 +260,7 @@ struct EpiTopK {
     float vmax = -CUDART_INF_F, vmin = CUDART_INF_F;
 #pragma unroll 8
     for (int s = 0; s < C; ++s) {
-      const float x = lds_f32(vb + s * 4);
+      const float x = lds_f32(vb + s * ES);
       if (s < n) {
         vmax = fmaxf(vmax, x);
         vmin = fminf(vmin, x);
@@ -292,20 +297,27 @@ struct EpiTopK {
     int j = 0;
 #pragma unroll 4
     for (int s = 0; s < C; ++s) {
-      const float x = lds_f32(vb + s * 4);
-      const int id = lds_s32(ib + s * 4);
+      const float x = lds_f32(vb + s * ES);
+      const int id = lds_s32(ib + s * ES);
       bool keep = s < n && x > keep_thr;
       if (!keep && s < n && quota > 0 && x > lo) {
         keep = true;
         --quota;
       }
       if (keep) {
-        sts_f32(vb + j * 4, x);
-        sts_s32(ib + j * 4, id);
+        sts_f32(vb + j * ES, x);
+        sts_s32(ib + j * ES, id);
         ++j;
       }
     }
     return pack_state(keep_thr, j);
+  }
+
+  // Called before the wait for the accumulator: the (L2) read of the row's shared threshold overlaps it.
+  // A threshold proven valid by ANY column chunk of this row is valid for every chunk; stale reads are fine.
+  __device__ static void prefetch(State& st, const Params& P, const ItemCtx& c) {
+    if (P.row_thr[c.p] != nullptr && c.row < c.n_rows)
+      st.pre_key = *reinterpret_cast<volatile unsigned*>(P.row_thr[c.p] + c.row);
   }
 
   __device__ static void tile(State& st, const Params& P, const ItemCtx& c, uint32_t taddr, int col0) {
@@ -314,13 +326,10 @@ struct EpiTopK {
     // A threshold proven valid by ANY column chunk of this row (>= 16 scores of the row are at least
     // that large) is valid for every chunk: adopt the best one published so far.  Stale reads are fine.
     unsigned* shared_thr = (P.row_thr[c.p] != nullptr && c.row < c.n_rows) ? P.row_thr[c.p] + c.row : nullptr;
-    if (shared_thr != nullptr) {
-      const unsigned k = *reinterpret_cast<volatile unsigned*>(shared_thr);
-      if (k > f32_key(st.thr)) st.thr = key_f32(k);
-    }
+    if (st.pre_key > f32_key(st.thr)) st.thr = key_f32(st.pre_key);  // fetched by prefetch() during the wait
     const bool dense = P.dense == 1 || st.dense_tiles > 0;  // warp-uniform
     if (st.dense_tiles > 0) --st.dense_tiles;
-    if (dense && __any_sync(0xffffffffu, st.cnt > C - 32)) {  // the dense path appends up to 32 per chunk
+    if (dense && __any_sync(0xffffffffu, st.cnt > DTRIG)) {  // the dense path appends up to 16 between checks
       if (st.cnt > JOIN) {
         const unsigned long long r = quad_shrink(st.thr, st.cnt, st.vb, st.ib);
         st.thr = __uint_as_float(static_cast<unsigned>(r >> 32));
@@ -335,23 +344,26 @@ struct EpiTopK {
         for (int e = 0; e < 32; ++e)
           if (col + e >= n_cols) v[e] = -CUDART_INF_F;
       }
-      if (dense) {  // warp-uniform; requires cnt <= C - 32 on entry (rounds start above C - 32)
-        const float thr = st.thr;
-        int cnt = st.cnt;
+      if (dense) {  // warp-uniform; invariant: cnt <= DTRIG = C - 16 before every 16 columns
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          sts_pair_if_gt(v[e], thr, st.vb + cnt * 4, st.ib + cnt * 4, col + e);
-          cnt += (v[e] > thr) ? 1 : 0;
-        }
-        st.dc[4] += cnt - st.cnt;
-        st.cnt = cnt;
-        if (__any_sync(0xffffffffu, cnt > C - 32)) {
-          ++st.dc[3];
-          if (cnt > JOIN) {
-            const unsigned long long r = quad_shrink(st.thr, cnt, st.vb, st.ib);
-            st.thr = __uint_as_float(static_cast<unsigned>(r >> 32));
-            st.cnt = static_cast<int>(r & 0xffffffffu);
-            if (shared_thr != nullptr) atomicMax(shared_thr, f32_key(st.thr));
+        for (int h = 0; h < 2; ++h) {
+          const float thr = st.thr;
+          uint32_t cur = st.vb + st.cnt * ES;  // list cursor as an address: one predicated add per element
+#pragma unroll
+          for (int e = 0; e < 16; e += 4)
+            cur = append4_if_gt(v[16 * h + e], v[16 * h + e + 1], v[16 * h + e + 2], v[16 * h + e + 3], thr, cur,
+                                col + 16 * h + e);
+          const int cnt = static_cast<int>(cur - st.vb) / ES;
+          st.dc[4] += cnt - st.cnt;
+          st.cnt = cnt;
+          if (__any_sync(0xffffffffu, cnt > DTRIG)) {
+            ++st.dc[3];
+            if (cnt > JOIN) {
+              const unsigned long long r = quad_shrink(st.thr, cnt, st.vb, st.ib);
+              st.thr = __uint_as_float(static_cast<unsigned>(r >> 32));
+              st.cnt = static_cast<int>(r & 0xffffffffu);
+              if (shared_thr != nullptr) atomicMax(shared_thr, f32_key(st.thr));
+            }
           }
         }
         return;
@@ -379,7 +391,7 @@ struct EpiTopK {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {  // predicated appends: straight-line code beats any branch here
             const float x = v[8 * g + e];
-            sts_pair_if_gt(x, thr, st.vb + cnt * 4, st.ib + cnt * 4, col + 8 * g + e);
+            sts_pair_if_gt(x, thr, st.vb + cnt * ES, st.ib + cnt * ES, col + 8 * g + e);
             cnt += (x > thr) ? 1 : 0;
           }
           st.dc[4] += cnt - st.cnt;
@@ -411,20 +423,20 @@ struct EpiTopK {
     }
     const int nch = P.n_sub[c.p];
     const uint32_t wbase = smem_u32(c.smem) + static_cast<uint32_t>(c.warp_q * 32) * LDSW * 4;
-#pragma unroll 1
+#pragma unroll 4
     for (int src = 0; src < 32; ++src) {
       const int row = c.rb * BM + c.warp_q * 32 + src;
       if (row >= c.n_rows) break;  // warp-uniform
       const int cnt_src = __shfl_sync(0xffffffffu, st.cnt, src);
       const long long o = (static_cast<long long>(row) * nch + c.sub) * C;
       const uint32_t vb = wbase + static_cast<uint32_t>(src) * LDSW * 4;
-      const uint32_t ib = vb + kEpiThreads * LDSW * 4;
+      const uint32_t ib = vb + kIdxOff;
 #pragma unroll
       for (int h = 0; h < C / 32; ++h) {
         const int s = c.lane + 32 * h;
         if (s < cnt_src) {
-          P.out_val[c.p][o + s] = lds_f32(vb + s * 4);
-          P.out_idx[c.p][o + s] = lds_s32(ib + s * 4);
+          P.out_val[c.p][o + s] = lds_f32(vb + s * ES);
+          P.out_idx[c.p][o + s] = lds_s32(ib + s * ES);
         }
       }
       if (c.lane == 0) P.out_cnt[c.p][static_cast<long long>(row) * nch + c.sub] = cnt_src;
@@ -466,6 +478,7 @@ struct EpiLse {
     const long long* ir = P.idx_rows[c.p];
     st.my_idx = (ir != nullptr && c.row < c.n_rows) ? __ldg(ir + c.row) : static_cast<long long>(c.row);
   }
+  __device__ static void prefetch(State&, const Params&, const ItemCtx&) {}
   __device__ static void tile(State& st, const Params& P, const ItemCtx& c, uint32_t taddr, int col0) {
     const long long* ic = P.idx_cols[c.p];
     const int n_cols = c.n_cols;
@@ -580,6 +593,7 @@ struct EpiGrad {
     st.my_idx = (ir != nullptr && ok) ? __ldg(ir + c.row) : static_cast<long long>(c.row);
   }
   __device__ static void end(State&, const Params&, const ItemCtx&) {}
+  __device__ static void prefetch(State&, const Params&, const ItemCtx&) {}
   __device__ static void tile(State& st, const Params& P, const ItemCtx& c, uint32_t taddr, int col0) {
     const long long* ic = P.idx_cols[c.p];
     const float* lc = P.lse_cols[c.p];

@@ -220,6 +220,7 @@ sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typ
         if (kWGs == 2 && (tile_n & 1u) != static_cast<uint32_t>(c.wg)) continue;
         const uint32_t buf = tile_n & 1u;
         const uint32_t use = tile_n >> 1;
+        Epi::prefetch(st, EP, c);  // loads whose latency should hide behind the wait
         mbar_wait(&tfull_bar[buf], use & 1u, 400 + buf, 32);
         tc_fence_after();
         const uint32_t taddr = tmem_base + buf * BN + (static_cast<uint32_t>(c.warp_q * 32) << 16);

@@ -893,4 +893,97 @@ __global__ void fuse_scores_kernel(float* __restrict__ S, const float* __restric
   }
 }
 
+// --------------------------------------------------------------------------------
+// Cross-rank exchange helpers over peer memory (one node, NVLink / NVSwitch).
+// --------------------------------------------------------------------------------
+// Barrier over peer-visible flag words.  flags[p] -> rank p's block of `world` uint32 (slot r is written by
+// rank r only).  Thread p publishes `epoch` into peer p's slot [rank] (release, system scope: everything
+// this stream did before -- including peer stores of earlier kernels -- is visible to whoever acquires it)
+// and waits until peer p's epoch has arrived in the own block.  Epochs only grow.  Bounded spin: a lost
+// peer traps instead of hanging the box.
+__global__ void peer_barrier_kernel(unsigned* const* __restrict__ flags, int world, int rank, unsigned epoch) {
+  const int p = threadIdx.x;
+  if (p >= world) return;
+  __threadfence_system();
+  unsigned* theirs = flags[p] + rank;
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
+  const unsigned* mine = flags[rank] + p;
+  unsigned seen = 0;
+  long long spins = 0;
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+    if (static_cast<int>(seen - epoch) >= 0) break;
+    if (++spins > (1LL << 26)) __trap();  // seconds
+    __nanosleep(64);
+  }
+}
+
+// Gather + merge in one kernel for the row-partitioned gallery: every rank keeps its per-query local top-k
+// lists (descending, ties by lower column) in a peer-visible buffer; after a barrier each rank PULLS the
+// lists of its query slice from all ranks (coalesced peer loads staged through shared memory, one warp per
+// 32 consecutive queries) and each thread W-way merges one query.  Global column = local + off[p].
+// Ties across ranks: lower global column first (the order a single pass over the whole gallery gives).
+constexpr int kMergeMaxWorld = 8;
+struct MergeOffsets {
+  int off[kMergeMaxWorld];
+};
+__global__ void topk_merge_peers_kernel(const float* const* __restrict__ vals, const int* const* __restrict__ idxs,
+                                        int world, int k_in, long long q_begin, long long q_count, MergeOffsets offs,
+                                        int k_out, float* __restrict__ out_val, int* __restrict__ out_idx) {
+  extern __shared__ float merge_smem[];
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long q0 = (static_cast<long long>(blockIdx.x) * warps + warp) * 32;  // first query of this warp (slice-relative)
+  if (q0 >= q_count) return;
+  const int nq = static_cast<int>(min(32LL, q_count - q0));
+  const int seg = 32 * k_in;  // words per (rank, warp) segment
+  float* sv = merge_smem + static_cast<size_t>(warp) * world * seg * 2;
+  int* si = reinterpret_cast<int*>(sv + static_cast<size_t>(world) * seg);
+  for (int p = 0; p < world; ++p) {
+    const float* gv = vals[p] + (q_begin + q0) * k_in;
+    const int* gi = idxs[p] + (q_begin + q0) * k_in;
+    for (int t = lane; t < nq * k_in; t += 32) {
+      sv[p * seg + t] = gv[t];
+      si[p * seg + t] = gi[t] + offs.off[p];
+    }
+  }
+  __syncwarp();
+  if (lane >= nq) return;
+  int pos[kMergeMaxWorld];
+  float hv[kMergeMaxWorld];
+  int hi[kMergeMaxWorld];
+#pragma unroll
+  for (int p = 0; p < kMergeMaxWorld; ++p) {
+    pos[p] = 0;
+    const bool ok = p < world;
+    hv[p] = ok ? sv[p * seg + lane * k_in] : -CUDART_INF_F;
+    hi[p] = ok ? si[p * seg + lane * k_in] : 0x7fffffff;
+  }
+  const long long o = (q0 + lane) * k_out;
+  for (int s = 0; s < k_out; ++s) {
+    int best = 0;
+    float bv = hv[0];
+    int bi = hi[0];
+#pragma unroll
+    for (int p = 1; p < kMergeMaxWorld; ++p) {
+      const bool better = hv[p] > bv || (hv[p] == bv && hi[p] < bi);
+      if (better) {
+        best = p;
+        bv = hv[p];
+        bi = hi[p];
+      }
+    }
+    out_val[o + s] = bv;
+    out_idx[o + s] = bi;
+#pragma unroll
+    for (int p = 0; p < kMergeMaxWorld; ++p) {
+      if (p == best) {
+        const int np = ++pos[p];
+        const bool ok = np < k_in && p < world;
+        hv[p] = ok ? sv[p * seg + lane * k_in + np] : -CUDART_INF_F;
+        hi[p] = ok ? si[p * seg + lane * k_in + np] : 0x7fffffff;
+      }
+    }
+  }
+}
+
 }  // namespace leccr

@@ -265,6 +265,65 @@ __device__ __forceinline__ void sts_pair_if_gt(float x, float thr, uint32_t addr
       : "memory");
 }
 
+// Append to a list of interleaved (score, column) entries whose cursor is a shared-window ADDRESS:
+// if (x > thr) *cursor = {x, idx} as ONE predicated 64-bit store; returns the cursor advance (8 or 0) so the
+// caller forms the next cursor in a fresh register (overwriting the address register of a store still in
+// flight stalls on its operand read).  Shared-store issue slots, not ALU work, bound the unfiltered loop.
+__device__ __forceinline__ uint32_t append_if_gt(float x, float thr, uint32_t cursor, int idx) {
+  uint32_t inc;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.gt.f32 p, %1, %2;\n"
+      "selp.u32 %0, 8, 0, p;\n"
+      "@p st.shared.v2.b32 [%3], {%4, %5};\n"
+      "}\n"
+      : "=r"(inc)
+      : "f"(x), "f"(thr), "r"(cursor), "r"(__float_as_uint(x)), "r"(idx)
+      : "memory");
+  return inc;
+}
+
+// Four appends at once: the cursor offsets of the four entries are a prefix sum of the four hit flags that
+// does not depend on the cursor, so the loop-carried chain is ONE add per four elements (the one-at-a-time
+// form above is bound by its add -> select chain, ~14 cycles per element with a single warp per scheduler).
+__device__ __forceinline__ uint32_t append4_if_gt(float x0, float x1, float x2, float x3, float thr, uint32_t cursor,
+                                                  int idx0) {
+  uint32_t next;
+  asm volatile(
+      "{\n"
+      ".reg .pred p0, p1, p2, p3;\n"
+      ".reg .u32 i0, i1, i2, i3, s01, s23, a1, a2, a3, j1, j2, j3;\n"
+      "setp.gt.f32 p0, %2, %6;\n"
+      "setp.gt.f32 p1, %3, %6;\n"
+      "setp.gt.f32 p2, %4, %6;\n"
+      "setp.gt.f32 p3, %5, %6;\n"
+      "selp.u32 i0, 8, 0, p0;\n"
+      "selp.u32 i1, 8, 0, p1;\n"
+      "selp.u32 i2, 8, 0, p2;\n"
+      "selp.u32 i3, 8, 0, p3;\n"
+      "add.u32 s01, i0, i1;\n"
+      "add.u32 s23, i2, i3;\n"
+      "add.u32 a1, %1, i0;\n"
+      "add.u32 a2, %1, s01;\n"
+      "add.u32 a3, a2, i2;\n"
+      "add.u32 j1, %11, 1;\n"
+      "add.u32 j2, %11, 2;\n"
+      "add.u32 j3, %11, 3;\n"
+      "@p0 st.shared.v2.b32 [%1], {%7, %11};\n"
+      "@p1 st.shared.v2.b32 [a1], {%8, j1};\n"
+      "@p2 st.shared.v2.b32 [a2], {%9, j2};\n"
+      "@p3 st.shared.v2.b32 [a3], {%10, j3};\n"
+      "add.u32 s01, s01, s23;\n"
+      "add.u32 %0, %1, s01;\n"
+      "}\n"
+      : "=r"(next)
+      : "r"(cursor), "f"(x0), "f"(x1), "f"(x2), "f"(x3), "f"(thr), "r"(__float_as_uint(x0)),
+        "r"(__float_as_uint(x1)), "r"(__float_as_uint(x2)), "r"(__float_as_uint(x3)), "r"(idx0)
+      : "memory");
+  return next;
+}
+
 // Order-preserving float <-> uint32 key (any sign, +-inf included).
 __device__ __forceinline__ uint32_t f32_key(float f) {
   const uint32_t b = __float_as_uint(f);

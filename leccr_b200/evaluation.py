@@ -339,8 +339,10 @@ def fused_eval_sharded(image_embeds, text_embeds, txt2img, img2txt, k=10, precis
 @torch.no_grad()
 def topk_gallery_sharded(queries, gallery_shard, shard_offset: int, k=10, precision="bf16", group=None):
     """Row-partitioned gallery: every rank holds all queries and ITS gallery rows [shard_offset, ...).
-    Local fused similarity + top-k, global column = local + shard_offset, then one all-gather of the
-    (Q, k) lists and a merge (leccr_b200.sharding).  Returns the same (val, idx int64) on every rank."""
+    Local fused similarity + top-k, global column = local + shard_offset, then the exchange: on one NVLink
+    node every rank pulls the other ranks' (Q, k) lists through peer pointers inside the merge kernel
+    (leccr_topk_merge_peers); otherwise one all-gather and a merge (leccr_b200.sharding).
+    Returns the same (val, idx int64) on every rank."""
     from . import sharding
 
     dev = _device()
@@ -349,4 +351,10 @@ def topk_gallery_sharded(queries, gallery_shard, shard_offset: int, k=10, precis
     fmt = ops.fmt_of(precision)
     Q, G = ops.prep(q, fmt, want_stats=False), ops.prep(g, fmt, want_stats=False)
     res, = ops.sim_topk([(Q, G, None)], k=k)
+    if group is None:
+        from . import peer
+
+        merged = peer.merge_topk_peers(res.val, res.idx, shard_offset, k)  # pull + merge in one kernel
+        if merged is not None:
+            return merged[0], merged[1].long()
     return sharding.allgather_topk(res.val, res.idx.long() + shard_offset, k, group)

@@ -1,0 +1,191 @@
+"""Peer-memory exchange inside one NVLink / NVSwitch node.
+
+The reference exchanges embeddings with `dist.all_gather` + `torch.cat` (models/xvlm.py:53-59) and has no
+top-k exchange at all (it ranks on rank 0's CPU).  Here the exchange is done by OUR kernels through peer
+pointers: the kernel that casts a rank's rows stores them straight into every rank's gathered operand
+buffer (`leccr_prep_push`), and the gallery-partition merge pulls the per-query lists of all ranks while it
+merges them (`leccr_topk_merge_peers`).  torch supplies only the plumbing: peer-mapped allocations
+(`torch.distributed._symmetric_memory`) and the process group used for their rendezvous.
+
+Every buffer is double-buffered (two slots used alternately) and every exchange ends with ONE cross-rank
+barrier (`leccr_peer_barrier`, flag words in the same peer-mapped allocation).  That is enough: a peer can
+start writing slot s again only after passing the barrier of the exchange in between, which every rank
+enters (stream-ordered) after it has finished reading slot s.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+from . import _native as N
+
+_DISABLED = os.environ.get("LECCR_PEER", "1") == "0"
+_cache = {}
+_warned = False
+
+
+def available(device) -> bool:
+    """Peer exchange is used for NCCL process groups of CUDA ranks on one node."""
+    if _DISABLED or not (dist.is_available() and dist.is_initialized()):
+        return False
+    if dist.get_world_size() < 2 or dist.get_world_size() > 8 or device.type != "cuda":
+        return False
+    try:
+        return "nccl" in str(dist.get_backend()).lower()
+    except Exception:  # pragma: no cover
+        return False
+
+
+class PeerBuffer:
+    """A peer-mapped allocation of `nbytes` payload bytes x 2 slots + a block of barrier flags, identical
+    on every rank of the default group.  Collective: every rank must construct it at the same time."""
+
+    FLAG_BYTES = 256
+
+    def __init__(self, nbytes: int, device):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.slot_bytes = (nbytes + 255) // 256 * 256
+        total = self.FLAG_BYTES + 2 * self.slot_bytes
+        group = dist.group.WORLD
+        try:
+            symm_mem.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass  # newer torch enables it implicitly
+        self.buf = symm_mem.empty(total, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        assert self.ptrs[self.rank] == self.buf.data_ptr()
+        self.flag_table = torch.tensor(self.ptrs, dtype=torch.int64, device=device)
+        self._tables = {}
+        self.device = device
+        self.epoch = 0
+        self.calls = 0
+        # everybody's flags are zero before anybody's first barrier
+        torch.cuda.current_stream().synchronize()
+        dist.barrier()
+
+    def next_slot(self) -> int:
+        s = self.calls & 1
+        self.calls += 1
+        return s
+
+    def slot_offset(self, slot: int) -> int:
+        return self.FLAG_BYTES + slot * self.slot_bytes
+
+    def table(self, byte_offset: int) -> torch.Tensor:
+        """Device array of `world` pointers: every rank's buffer base + byte_offset."""
+        t = self._tables.get(byte_offset)
+        if t is None:
+            t = torch.tensor([p + byte_offset for p in self.ptrs], dtype=torch.int64, device=self.device)
+            self._tables[byte_offset] = t
+        return t
+
+    def local(self, byte_offset: int, shape, dtype) -> torch.Tensor:
+        """View of this rank's own buffer."""
+        n = 1
+        for s in shape:
+            n *= s
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        return self.buf[byte_offset: byte_offset + nbytes].view(dtype).view(shape)
+
+    def barrier(self):
+        self.epoch += 1
+        N.check(N.load().leccr_peer_barrier(N.ptr(self.flag_table), self.world, self.rank, self.epoch,
+                                            N.stream_ptr()), "leccr_peer_barrier")
+
+
+def get_buffer(key, nbytes: int, device):
+    """Cached PeerBuffer per use (key); None when peer memory cannot be set up (NCCL is used instead)."""
+    global _warned
+    if key in _cache:
+        return _cache[key]
+    try:
+        pb = PeerBuffer(nbytes, device)
+    except Exception as e:  # allocation / rendezvous unsupported on this system
+        if not _warned:
+            import warnings
+
+            warnings.warn(f"leccr_b200: peer-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL")
+            _warned = True
+        pb = None
+    _cache[key] = pb
+    return pb
+
+
+def gather_contrastive(image_feat, text_feat, idx, fmt):
+    """Cast + exchange of the contrastive operands in one step (replaces the three AllGather calls of
+    models/xvlm.py:271-272,285).  Returns (both [n, 2D] 16-bit private copy, idx_all [n] int64 or None),
+    or None when peer exchange is not available."""
+    dev = image_feat.device
+    if not available(dev):
+        return None
+    B, D = image_feat.shape
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n = B * world
+    row_bytes = 2 * D * 2
+    pb = get_buffer(("itc", B, D, fmt), n * row_bytes + n * 8, dev)
+    if pb is None:
+        return None
+    lib = N.load()
+    slot = pb.next_slot()
+    off = pb.slot_offset(slot)
+    rows_tab = pb.table(off)
+    img = image_feat.detach().float()
+    txt = text_feat.detach().float()
+    if img.stride(1) != 1:
+        img = img.contiguous()
+    if txt.stride(1) != 1:
+        txt = txt.contiguous()
+    st = N.stream_ptr()
+    N.check(lib.leccr_prep_push(N.ptr(img), B, D, img.stride(0), 0, fmt, N.ptr(rows_tab), world, rank * B, 0, 2 * D,
+                                st), "leccr_prep_push")
+    N.check(lib.leccr_prep_push(N.ptr(txt), B, D, txt.stride(0), 0, fmt, N.ptr(rows_tab), world, rank * B, D, 2 * D,
+                                st), "leccr_prep_push")
+    if idx is not None:
+        ix = idx.detach().view(-1).long().contiguous()
+        idx_tab = pb.table(off + n * row_bytes)
+        N.check(lib.leccr_push_words(N.ptr(ix), B, N.ptr(idx_tab), world, rank * B, st), "leccr_push_words")
+    pb.barrier()
+    dt16 = torch.float16 if fmt == N.FMT_F16 else torch.bfloat16
+    both = pb.local(off, (n, 2 * D), dt16).clone()
+    idx_all = pb.local(off + n * row_bytes, (n,), torch.int64).clone() if idx is not None else None
+    return both, idx_all
+
+
+def merge_topk_peers(val, idx, shard_offset: int, k: int, all_queries: bool = True):
+    """Row-partitioned gallery exchange: publish this rank's [Q, k_in] local lists, barrier, then pull + merge.
+    Returns (val [Q', k], idx int32 [Q', k] global columns, (q_begin, q_end)) where Q' is all queries
+    (all_queries) or this rank's balanced slice.  None when peer exchange is not available."""
+    from .sharding import shard_range
+
+    dev = val.device
+    if not available(dev):
+        return None
+    Q, k_in = val.shape
+    world, rank = dist.get_world_size(), dist.get_rank()
+    pb = get_buffer(("topk", Q, k_in), Q * k_in * 8, dev)
+    if pb is None:
+        return None
+    lib = N.load()
+    slot = pb.next_slot()
+    off = pb.slot_offset(slot)
+    pb.local(off, (Q, k_in), torch.float32).copy_(val)
+    pb.local(off + Q * k_in * 4, (Q, k_in), torch.int32).copy_(idx)
+    offs = torch.tensor([shard_offset], dtype=torch.int64, device=dev)
+    all_offs = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_offs, offs)  # 8 bytes per rank, once per call (host needs them)
+    host_offs = all_offs.cpu().tolist()
+    pb.barrier()
+    qb, qe = (0, Q) if all_queries else shard_range(Q, rank, world)
+    out_v = torch.empty((qe - qb, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((qe - qb, k), dtype=torch.int32, device=dev)
+    import ctypes
+
+    arr = (ctypes.c_int64 * world)(*host_offs)
+    N.check(lib.leccr_topk_merge_peers(N.ptr(pb.table(off)), N.ptr(pb.table(off + Q * k_in * 4)), world, k_in, qb,
+                                       qe - qb, arr, k, N.ptr(out_v), N.ptr(out_i), N.stream_ptr()),
+            "leccr_topk_merge_peers")
+    return out_v, out_i, (qb, qe)

@@ -262,3 +262,67 @@ def test_fused_eval_plan_matches_reference(golden):
     ev2 = plan.run(other.image.pin_memory(), other.text.pin_memory())
     o_i2t, o_t2i = oracle.score_matrices(other.image, other.text)
     assert_ev_equal(ev2, oracle.itm_eval_by_count(o_i2t, o_t2i, other.txt2img, other.img2txt))
+
+
+# ----------------------------------------------------------------------------- peer-memory exchange kernels
+# (one GPU: the "peers" are separate local buffers; tools/dist_check.py runs the same entry points over
+# real peer mappings on two ranks)
+def test_prep_push_writes_every_peer_buffer():
+    lib = N.load()
+    g = torch.Generator().manual_seed(11)
+    B, D, world, rank = 96, 256, 3, 1
+    x = torch.randn(B, D, generator=g).cuda()
+    bufs = [torch.zeros((world * B, 2 * D), dtype=torch.float16, device="cuda") for _ in range(world)]
+    table = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device="cuda")
+    N.check(lib.leccr_prep_push(N.ptr(x), B, D, x.stride(0), 1, N.FMT_F16, N.ptr(table), world, rank * B, D, 2 * D,
+                                N.stream_ptr()), "leccr_prep_push")
+    want = ops.prep(x, N.FMT_F16, normalize=True, want_stats=False).t16
+    for b in bufs:
+        assert torch.equal(b[rank * B:(rank + 1) * B, D:], want)
+        assert not b[rank * B:(rank + 1) * B, :D].any() and not b[:rank * B].any() and not b[(rank + 1) * B:].any()
+    idx = torch.randint(0, 1 << 40, (B,), generator=g).cuda()
+    ibufs = [torch.zeros(world * B, dtype=torch.int64, device="cuda") for _ in range(world)]
+    itab = torch.tensor([b.data_ptr() for b in ibufs], dtype=torch.int64, device="cuda")
+    N.check(lib.leccr_push_words(N.ptr(idx), B, N.ptr(itab), world, rank * B, N.stream_ptr()), "leccr_push_words")
+    for b in ibufs:
+        assert torch.equal(b[rank * B:(rank + 1) * B], idx) and int((b != 0).sum()) == int((idx != 0).sum())
+
+
+def test_peer_barrier_single_rank_and_merge_peers_against_sort():
+    lib = N.load()
+    flags = torch.zeros(64, dtype=torch.int32, device="cuda")
+    ftab = torch.tensor([flags.data_ptr()], dtype=torch.int64, device="cuda")
+    for epoch in (1, 2, 3):
+        N.check(lib.leccr_peer_barrier(N.ptr(ftab), 1, 0, epoch, N.stream_ptr()), "leccr_peer_barrier")
+    torch.cuda.synchronize()
+    assert int(flags[0]) == 3
+    import ctypes
+
+    from leccr_b200 import sharding
+
+    g = torch.Generator().manual_seed(5)
+    for world, Q, k_in, k in [(3, 1000, 10, 10), (8, 77, 16, 10), (2, 33, 4, 7), (1, 5, 10, 10)]:
+        # quantised scores force cross-rank ties; columns are distinct within and across ranks
+        vals = (torch.randint(0, 50, (world, Q, k_in), generator=g).float() / 50).sort(dim=2, descending=True).values
+        idx = torch.stack([torch.stack([torch.randperm(1000, generator=g)[:k_in] for _ in range(Q)])
+                           for _ in range(world)]).int()
+        # ties inside a rank's list must come lower column first (what topk_finalize emits)
+        order = torch.argsort(idx, dim=2, stable=True)
+        idx_s, vals_s = torch.gather(idx, 2, order), torch.gather(vals, 2, order)
+        order = torch.argsort(vals_s, dim=2, descending=True, stable=True)
+        idx_s, vals_s = torch.gather(idx_s, 2, order).contiguous(), torch.gather(vals_s, 2, order).contiguous()
+        offs = [1000 * p for p in range(world)]
+        dv = [vals_s[p].cuda() for p in range(world)]
+        di = [idx_s[p].cuda() for p in range(world)]
+        vt = torch.tensor([t.data_ptr() for t in dv], dtype=torch.int64, device="cuda")
+        it = torch.tensor([t.data_ptr() for t in di], dtype=torch.int64, device="cuda")
+        qb, qn = (0, Q) if world != 3 else (100, 555)
+        out_v = torch.empty((qn, k), dtype=torch.float32, device="cuda")
+        out_i = torch.empty((qn, k), dtype=torch.int32, device="cuda")
+        arr = (ctypes.c_int64 * world)(*offs)
+        N.check(lib.leccr_topk_merge_peers(N.ptr(vt), N.ptr(it), world, k_in, qb, qn, arr, k, N.ptr(out_v),
+                                           N.ptr(out_i), N.stream_ptr()), "leccr_topk_merge_peers")
+        gidx = idx_s.long() + torch.tensor(offs).view(-1, 1, 1)
+        wv, wi = sharding.merge_topk(vals_s, gidx, k)
+        assert torch.equal(out_v.cpu(), wv[qb:qb + qn]), (world, Q, k_in, k)
+        assert torch.equal(out_i.cpu().long(), wi[qb:qb + qn]), (world, Q, k_in, k)

@@ -47,7 +47,11 @@ mv, mi = leccr_b200.topk_gallery_sharded(qry, gal[b0:e0], b0, k=10)
 full, = _ops.sim_topk([(_ops.prep(qry), _ops.prep(gal), None)], k=10)
 merge_ok = bool(torch.equal(mi, full.idx.long())) and bool(torch.equal(mv, full.val))
 ok &= merge_ok
-print(f"rank {rank}: sharded eval == golden {ev_ok}; gallery-partition merge == single pass {merge_ok}", flush=True)
+from leccr_b200 import peer as _peer
+paths = {str(k_[0]): (v_ is not None) for k_, v_ in _peer._cache.items()}
+print(f"rank {rank}: sharded eval == golden {ev_ok}; gallery-partition merge == single pass {merge_ok}; peer-memory paths used: {paths}", flush=True)
+if os.environ.get("LECCR_PEER", "1") != "0":
+    ok &= paths.get("itc", False) and paths.get("topk", False)  # on a B200 NVLink box the peer kernels must be what ran
 # timing of the training step (fwd + bwd) on this rank, max over ranks
 def step():
     me.temp.grad = None

@@ -21,8 +21,11 @@ def unit(n, d, dtype):
 
 modes = sys.argv[1].split(",") if len(sys.argv) > 1 else ["0"]
 print("LECCR_TOPK_WGS", os.environ.get("LECCR_TOPK_WGS"))
-for (n, m, dt, both) in [(5000, 25000, torch.float32, True), (20000, 250000, torch.float32, False),
-                         (12500, 1000000, torch.bfloat16, False), (100000, 125000, torch.bfloat16, False)]:
+SHAPES = [(5000, 25000, torch.float32, True), (20000, 250000, torch.float32, False),
+          (12500, 1000000, torch.bfloat16, False), (100000, 125000, torch.bfloat16, False)]
+if len(sys.argv) > 2:  # optional: comma-separated shape indices
+    SHAPES = [SHAPES[int(i)] for i in sys.argv[2].split(",")]
+for (n, m, dt, both) in SHAPES:
     q, g = unit(n, 256, dt), unit(m, 256, dt)
     Q, G = ops.prep(q), ops.prep(g)
     for mode in modes:
