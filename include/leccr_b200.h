@@ -141,6 +141,28 @@ int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
                    int tiles_per_chunk /* 0 = auto */, void* workspace, size_t workspace_bytes,
                    leccr_stream_t stream);
 
+/* Streamed evaluation: the columns of a problem arrive in windows (e.g. while the rest of the gallery is
+ * still crossing PCIe).  Each call may run the tensor-core phase over ONE window (cols16 / n_cols describe
+ * the window, col_begin its global position; the candidates go to list slots [sub_begin, sub_begin +
+ * sub_count) of the problem's persistent workspace) and / or the finalize phase over everything collected
+ * (then cols_x must address ALL columns and n_cols_total gives their number).  Per-row thresholds carry over
+ * from window to window.  A problem whose rows are complete in one call uses all three phases at once;
+ * the problems of one call share one tensor-core launch.  sub_total <= 8. */
+#define LECCR_TOPK_INIT 1     /* first call of a problem: reset its workspace */
+#define LECCR_TOPK_GEMM 2     /* similarity + candidate lists for the columns given */
+#define LECCR_TOPK_FINALIZE 4 /* merge all slots: top-k, exact ranks, Recall counts */
+typedef struct leccr_topk_stream {
+  int32_t phases;
+  int32_t sub_begin, sub_count, sub_total;
+  int64_t col_begin;
+  int64_t n_cols_total; /* finalize without a tensor-core phase: total number of columns (else 0) */
+  void* workspace;      /* leccr_sim_topk_stream_workspace(n_rows, sub_total) bytes, kept from INIT to FINALIZE */
+  size_t workspace_bytes;
+} leccr_topk_stream;
+size_t leccr_sim_topk_stream_workspace(int64_t n_rows, int sub_total);
+int leccr_sim_topk_stream(const leccr_topk_problem* probs, const leccr_topk_stream* streams, int n_prob, int D,
+                          int fmt, int k, leccr_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * leccr_infonce_fwd / leccr_infonce_bwd: symmetric InfoNCE over all-gathered embeddings.
  * Replaces: XVLMBase.get_contrastive_loss  models/xvlm.py:260-292 (forward: :273-292; backward:
@@ -211,6 +233,34 @@ int leccr_peer_barrier(uint32_t* const* flag_ptrs_dev, int world, int rank, uint
 int leccr_topk_merge_peers(const float* const* val_ptrs_dev, const int32_t* const* idx_ptrs_dev, int world, int k_in,
                            int64_t q_begin, int64_t q_count, const int64_t* col_offset_host, int k_out,
                            float* out_val, int32_t* out_idx, leccr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * leccr_itc_forward / leccr_itc_backward: the whole get_contrastive_loss step in two calls
+ * (models/xvlm.py:260-292 forward incl. its three AllGather calls :271-272,285; backward = autograd of the
+ * same lines + AllGather.backward :62-67).  They issue exactly the launches of leccr_prep(_push),
+ * leccr_peer_barrier, leccr_infonce_fwd / leccr_transpose16, leccr_infonce_bwd from C++ so the host cost of a
+ * training step is two library calls.
+ *   image_feat, text_feat : this rank's [B][D] fp32 rows;  idx: [B] int64 or NULL
+ *   world == 1 : rows_ptrs_dev .. local_idx are ignored
+ *   world  > 1 : rows_ptrs_dev[p] -> rank p's peer-mapped [n][2D] 16-bit slot, idx_ptrs_dev[p] -> its [n]
+ *                int64 slot, flag_ptrs_dev / epoch as in leccr_peer_barrier, local_rows / local_idx = this
+ *                rank's own slot (rows_ptrs_dev[rank], idx_ptrs_dev[rank]).  The caller alternates two slots.
+ *   both16 : out, private [n][2D] 16-bit gathered operands [image | text] (saved for the backward)
+ *   idx_all: out, [n] int64 (when idx != NULL);  out/lse2/rcnt as in leccr_infonce_fwd
+ *   backward: dA, dB [row_count][D] fp32, dtemp scalar = grad_out * out[1] (may be NULL)
+ * ------------------------------------------------------------------------------------------ */
+size_t leccr_itc_fwd_workspace(int64_t n, int tiles_per_chunk);
+int leccr_itc_forward(const float* image_feat, int64_t ld_img, const float* text_feat, int64_t ld_txt,
+                      const int64_t* idx, int64_t B, int D, int fmt, int rank, int world,
+                      void* const* rows_ptrs_dev, void* const* idx_ptrs_dev, uint32_t* const* flag_ptrs_dev,
+                      uint32_t epoch, const void* local_rows, const int64_t* local_idx, void* both16,
+                      int64_t* idx_all, const float* temp, float* out, float* lse2, float* rcnt,
+                      void* workspace, size_t workspace_bytes, leccr_stream_t stream);
+size_t leccr_itc_bwd_workspace(int64_t n, int64_t row_count, int D);
+int leccr_itc_backward(const void* both16, const int64_t* idx_all, int64_t n, int D, int fmt, const float* temp,
+                       const float* lse2, const float* rcnt, const float* out, int64_t row_begin, int64_t row_count,
+                       const float* grad_out, float* dA, float* dB, float* dtemp, void* workspace,
+                       size_t workspace_bytes, leccr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -40,6 +40,18 @@ class TopkProblem(ctypes.Structure):
     ]
 
 
+class TopkStream(ctypes.Structure):
+    """Mirror of struct leccr_topk_stream."""
+
+    _fields_ = [
+        ("phases", ctypes.c_int32), ("sub_begin", ctypes.c_int32), ("sub_count", ctypes.c_int32),
+        ("sub_total", ctypes.c_int32), ("col_begin", i64), ("n_cols_total", i64),
+        ("workspace", vp), ("workspace_bytes", sz),
+    ]
+
+
+TOPK_INIT, TOPK_GEMM, TOPK_FINALIZE = 1, 2, 4
+
 _SIGNATURES = {
     "leccr_strerror": (ctypes.c_char_p, [c_int]),
     "leccr_last_cuda_error": (ctypes.c_char_p, []),
@@ -50,6 +62,14 @@ _SIGNATURES = {
     "leccr_prep": (c_int, [vp, i64, c_int, i64, c_int, c_int, c_int, vp, i64, vp, vp, vp, vp]),
     "leccr_prep_push": (c_int, [vp, i64, c_int, i64, c_int, c_int, vp, c_int, i64, i64, i64, vp]),
     "leccr_push_words": (c_int, [vp, i64, vp, c_int, i64, vp]),
+    "leccr_sim_topk_stream_workspace": (sz, [i64, c_int]),
+    "leccr_sim_topk_stream": (c_int, [ctypes.POINTER(TopkProblem), ctypes.POINTER(TopkStream), c_int, c_int, c_int,
+                                      c_int, vp]),
+    "leccr_itc_fwd_workspace": (sz, [i64, c_int]),
+    "leccr_itc_forward": (c_int, [vp, i64, vp, i64, vp, i64, c_int, c_int, c_int, c_int, vp, vp, vp, ctypes.c_uint32,
+                                  vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "leccr_itc_bwd_workspace": (sz, [i64, i64, c_int]),
+    "leccr_itc_backward": (c_int, [vp, vp, i64, c_int, c_int, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, sz, vp]),
     "leccr_peer_barrier": (c_int, [vp, c_int, c_int, ctypes.c_uint32, vp]),
     "leccr_topk_merge_peers": (c_int, [vp, vp, c_int, c_int, i64, i64, ctypes.POINTER(i64), c_int, vp, vp, vp]),
     "leccr_stats16": (c_int, [vp, c_int, i64, c_int, i64, vp, vp, vp, vp]),

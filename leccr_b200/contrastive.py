@@ -28,50 +28,104 @@ def _world():
     return 0, 1
 
 
+_ws_cache = {}
+
+
+def _workspace(kind, nbytes, dev):
+    """Scratch reused by every call of one shape (stream-ordered, nothing in it outlives the call)."""
+    key = (kind, nbytes, dev)
+    t = _ws_cache.get(key)
+    if t is None:
+        t = torch.empty(max(1, nbytes), dtype=torch.uint8, device=dev)
+        _ws_cache[key] = t
+    return t
+
+
+def _a256(x):
+    return (x + 255) // 256 * 256
+
+
 class _SymmetricInfoNCE(torch.autograd.Function):
+    """forward = leccr_itc_forward, backward = leccr_itc_backward: two library calls per training step."""
+
     @staticmethod
     def forward(ctx, image_feat, text_feat, temp, idx, rank, world, fmt):
         if not image_feat.is_cuda:
             raise N.LeccrError("leccr_b200 has no CPU path: get_contrastive_loss needs CUDA tensors")
+        lib = N.load()
         B, D = image_feat.shape
         n = B * world
         dev = image_feat.device
-        dt16 = torch.float16 if fmt == N.FMT_F16 else torch.bfloat16
-        # One node, NCCL ranks: the cast kernel stores each rank's rows straight into every rank's gathered
-        # operand buffer through peer pointers (leccr_b200.peer).  Otherwise: local cast, then one
-        # all-gather of the packed [image | text] 16-bit rows (and one of idx).
-        pushed = peer.gather_contrastive(image_feat, text_feat, idx, fmt) if world > 1 else None
-        if pushed is not None:
-            both, idx_all = pushed
-        else:
+        img = image_feat.detach()
+        txt = text_feat.detach()
+        if img.dtype != torch.float32 or img.stride(1) != 1:
+            img = img.float().contiguous()
+        if txt.dtype != torch.float32 or txt.stride(1) != 1:
+            txt = txt.float().contiguous()
+        ix = None
+        if idx is not None:
+            ix = idx.detach().view(-1)
+            if ix.dtype != torch.int64 or not ix.is_contiguous():
+                ix = ix.long().contiguous()
+        temp_dev = temp.detach().reshape(())
+        if temp_dev.dtype != torch.float32:
+            temp_dev = temp_dev.float()
+        # everything the backward needs lives in ONE allocation: [both16 | idx_all | out(4) | lse2 | rcnt]
+        o_idx = _a256(n * 2 * D * 2)
+        o_out = o_idx + _a256(n * 8)
+        o_lse = o_out + 256
+        o_rc = o_lse + _a256(2 * n * 4)
+        saved = torch.empty(o_rc + _a256(2 * n * 4), dtype=torch.uint8, device=dev)
+        base = saved.data_ptr()
+        slot = peer.itc_slot(B, D, fmt, dev) if world > 1 else None
+        if world > 1 and slot is None:  # no peer memory (e.g. gloo, several nodes): NCCL all-gather of the cast rows
+            dt16 = torch.float16 if fmt == N.FMT_F16 else torch.bfloat16
             local = torch.empty((B, 2 * D), dtype=dt16, device=dev)
-            ops.prep_into(image_feat.detach().float(), local[:, :D], fmt)
-            ops.prep_into(text_feat.detach().float(), local[:, D:], fmt)
-            both = gather_into(torch.empty((n, 2 * D), dtype=dt16, device=dev), local)
+            ops.prep_into(img, local[:, :D], fmt)
+            ops.prep_into(txt, local[:, D:], fmt)
+            both = gather_into(saved[:n * 2 * D * 2].view(dt16).view(n, 2 * D), local)
             idx_all = None
-            if idx is not None:
-                idx_all = gather_into(torch.empty(n, dtype=torch.int64, device=dev), idx.detach().view(-1).long())
-        a = ops.Operand(both[:, :D], fmt, N.LAYOUT_HI, n, D, None, None, None, both[:, :D])
-        b = ops.Operand(both[:, D:], fmt, N.LAYOUT_HI, n, D, None, None, None, both[:, D:])
-        temp_dev = temp.detach().reshape(()).float()
-        out, lse2, rcnt = ops.infonce_forward(a, b, idx_all, temp_dev)
-        ctx.save_for_backward(both, idx_all if idx_all is not None else torch.empty(0, device=dev), temp_dev,
-                              lse2, rcnt, out)
-        ctx.meta = (rank, B, D, n, fmt, idx is not None)
-        return out[0].clone()
+            if ix is not None:
+                idx_all = gather_into(saved[o_idx:o_idx + n * 8].view(torch.int64), ix)
+            ws = _workspace("fwd", lib.leccr_infonce_fwd_workspace(n, 0), dev)
+            N.check(lib.leccr_infonce_fwd(base, base + 2 * D, 2 * D, N.ptr(idx_all), n, D, fmt, N.ptr(temp_dev),
+                                          base + o_out, base + o_lse, base + o_rc, 0, N.ptr(ws), ws.numel(),
+                                          N.stream_ptr()), "leccr_infonce_fwd")
+        else:
+            ws = _workspace("fwd", lib.leccr_itc_fwd_workspace(n, 0), dev)
+            rows_tab = idx_tab = flag_tab = None
+            epoch, l_rows, l_idx = 0, None, None
+            if slot is not None:
+                rows_tab, idx_tab, flag_tab, epoch, l_rows, l_idx = slot
+            N.check(lib.leccr_itc_forward(N.ptr(img), img.stride(0), N.ptr(txt), txt.stride(0), N.ptr(ix), B, D, fmt,
+                                          rank, world, N.ptr(rows_tab), N.ptr(idx_tab), N.ptr(flag_tab), epoch,
+                                          l_rows, l_idx, base, base + o_idx, N.ptr(temp_dev), base + o_out,
+                                          base + o_lse, base + o_rc, N.ptr(ws), ws.numel(), N.stream_ptr()),
+                    "leccr_itc_forward")
+        ctx.save_for_backward(saved, temp_dev)
+        ctx.meta = (rank, B, D, n, fmt, idx is not None, (o_idx, o_out, o_lse, o_rc))
+        return saved[o_out:o_out + 4].view(torch.float32)[0].clone()
 
     @staticmethod
     def backward(ctx, grad_out):
-        both, idx_all, temp_dev, lse2, rcnt, out = ctx.saved_tensors
-        rank, B, D, n, fmt, has_idx = ctx.meta
-        a = ops.Operand(both[:, :D], fmt, N.LAYOUT_HI, n, D, None, None, None, both[:, :D])
-        b = ops.Operand(both[:, D:], fmt, N.LAYOUT_HI, n, D, None, None, None, both[:, D:])
-        aT, bT = ops.transpose16(a), ops.transpose16(b)
-        go = grad_out.detach().reshape(()).float().contiguous()
-        dA, dB = ops.infonce_backward(a, b, aT, bT, idx_all if has_idx else None, temp_dev, lse2, rcnt,
-                                      rank * B, B, go)
-        dtemp = (go * out[1]).reshape(())
-        return dA, dB, dtemp, None, None, None, None
+        saved, temp_dev = ctx.saved_tensors
+        rank, B, D, n, fmt, has_idx, (o_idx, o_out, o_lse, o_rc) = ctx.meta
+        lib = N.load()
+        dev = saved.device
+        base = saved.data_ptr()
+        go = grad_out.detach().reshape(())
+        if go.dtype != torch.float32:
+            go = go.float()
+        grads = torch.empty(2 * B * D + 1, dtype=torch.float32, device=dev)
+        g = grads.data_ptr()
+        ws = _workspace("bwd", lib.leccr_itc_bwd_workspace(n, B, D), dev)
+        N.check(lib.leccr_itc_backward(base, base + o_idx if has_idx else None, n, D, fmt, N.ptr(temp_dev),
+                                       base + o_lse, base + o_rc, base + o_out, rank * B, B, N.ptr(go), g,
+                                       g + B * D * 4, g + 2 * B * D * 4, N.ptr(ws), ws.numel(), N.stream_ptr()),
+                "leccr_itc_backward")
+        dA = grads[:B * D].view(B, D)
+        dB = grads[B * D:2 * B * D].view(B, D)
+        return dA, dB, grads[2 * B * D].reshape(()), None, None, None, None
 
 
 def contrastive_loss(image_feat, text_feat, temp, idx=None, precision=None):

@@ -463,45 +463,35 @@ static int topk_plan(const leccr_topk_problem* probs, int n_prob, int tiles_per_
 
 static size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
+// Per-problem workspace: candidate lists [n_rows][subs][64] (score, column), counts [n_rows][subs],
+// undecided-row list, shared per-row thresholds.
+static size_t topk_ws_bytes(int64_t n_rows, int subs) {
+  const size_t lists = static_cast<size_t>(n_rows) * subs * 2;  // either epilogue shape: subs * 64 entries per row
+  return align256(lists * 32 * 4) * 2 + align256(lists * 4) + align256(static_cast<size_t>(n_rows) * 4 + 16) +
+         align256(static_cast<size_t>(n_rows) * 4);
+}
+
 size_t leccr_sim_topk_workspace(const leccr_topk_problem* probs, int n_prob, int tiles_per_chunk) {
   if (probs == nullptr || n_prob < 1 || n_prob > 2) return 0;
   Plan plans[2];
   if (topk_plan(probs, n_prob, tiles_per_chunk, plans) != LECCR_OK) return 0;
   size_t bytes = 0;
-  for (int p = 0; p < n_prob; ++p) {
-    // either shape: n_chunks * kWGs lists of C entries = n_chunks * 64 entries per row
-    const size_t lists = static_cast<size_t>(probs[p].n_rows) * plans[p].n_chunks * 2;
-    bytes += align256(lists * 32 * 4) * 2 + align256(lists * 4) +
-             align256(static_cast<size_t>(probs[p].n_rows) * 4 + 16) + align256(static_cast<size_t>(probs[p].n_rows) * 4);
-  }
+  for (int p = 0; p < n_prob; ++p) bytes += topk_ws_bytes(probs[p].n_rows, plans[p].n_chunks);
   return bytes;
 }
 
-int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, int k, int tiles_per_chunk,
-                   void* workspace, size_t workspace_bytes, leccr_stream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (probs == nullptr || n_prob < 1 || n_prob > 2 || D <= 0 || bad_fmt(fmt) || k < 1 || k > LECCR_TOPK_KP)
-    return LECCR_ERR_ARG;
-  for (int p = 0; p < n_prob; ++p) {
-    const leccr_topk_problem& q = probs[p];
-    if (q.rows16 == nullptr || q.cols16 == nullptr || q.n_rows <= 0 || q.n_cols <= 0 || q.topk_val == nullptr ||
-        q.topk_idx == nullptr)
-      return LECCR_ERR_ARG;
-    if (q.gt_off != nullptr &&
-        (q.gt_ids == nullptr || q.rows_x == nullptr || q.cols_x == nullptr || q.rn_hi == nullptr ||
-         q.rn_lo == nullptr || q.col_stats == nullptr || q.rank == nullptr || q.x_dtype < 0 || q.x_dtype > 2))
-      return LECCR_ERR_ARG;
-  }
-  int rc = leccr_check_device();
-  if (rc != LECCR_OK) return rc;
-  Plan plans[2];
-  rc = topk_plan(probs, n_prob, tiles_per_chunk, plans);
-  if (rc != LECCR_OK) return rc;  // tiles_per_chunk too small: more than 16 column chunks per row
-  if (workspace == nullptr || workspace_bytes < leccr_sim_topk_workspace(probs, n_prob, tiles_per_chunk))
-    return LECCR_ERR_WORKSPACE;
+size_t leccr_sim_topk_stream_workspace(int64_t n_rows, int sub_total) {
+  if (n_rows <= 0 || sub_total < 1 || sub_total > kMaxTopkChunks) return 0;
+  return topk_ws_bytes(n_rows, sub_total);
+}
+
+// The engine behind leccr_sim_topk and leccr_sim_topk_stream: per problem an optional tensor-core phase over
+// the columns given (writing candidate-list slots [sub_begin, sub_begin + chunks) of the problem's
+// persistent workspace) and an optional finalize phase over all sub_total slots.
+static int topk_core(const leccr_topk_problem* probs, const leccr_topk_stream* so, const Plan* plans, int n_prob, int D,
+                     int fmt, int k, cudaStream_t stream) {
   SimLaunch L;
   memset(&L, 0, sizeof(L));
-  L.n_prob = n_prob;
   L.fmt = fmt;
   L.k_chunks = (D + BK - 1) / BK;
   const bool two = topk_two_wgs();
@@ -518,26 +508,25 @@ int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
   // 342 -> 304 us; long chunks are better off filtering: 12,500 x 1M 1202 vs 832 TFLOP/s)
   EP.dense = 1;
   for (int p = 0; p < n_prob; ++p)
-    if (plans[p].tiles_per_chunk > 32) EP.dense = 0;
+    if ((so[p].phases & LECCR_TOPK_GEMM) && plans[p].tiles_per_chunk > 32) EP.dense = 0;
   if (const char* dn = getenv("LECCR_TOPK_DENSE")) EP.dense = atoi(dn);  // measurement aid
   if (two) EP.dense = 0;  // 32-entry lists cannot take 16 unfiltered columns between checks (DTRIG < JOIN)
   if (const char* tg = getenv("LECCR_TOPK_TRIG")) EP.trig = std::min(EP.trig, std::max(LECCR_TOPK_KP + 4, atoi(tg)));
   if (const char* dc = getenv("LECCR_TOPK_COUNTERS")) {  // measurement aid only: device address (hex) of 5 x u64
     EP.debug_counters = reinterpret_cast<unsigned long long*>(strtoull(dc, nullptr, 16));
   }
-  uint8_t* ws = static_cast<uint8_t*>(workspace);
   float* cand_val[2];
   int* cand_idx[2];
   int* cand_cnt[2];
   int* flag[2];
   int item_base = 0;
+  int n_launch = 0;  // problems taking part in the tensor-core launch
   for (int p = 0; p < n_prob; ++p) {
     const leccr_topk_problem& q = probs[p];
-    rc = fill_problem(L.prob[p], q.rows16, q.ld_rows16, q.cols16, q.ld_cols16, q.n_rows, q.n_cols, D, fmt,
-                      plans[p], item_base);
-    if (rc != LECCR_OK) return rc;
-    item_base += plans[p].row_blocks * plans[p].n_chunks;
-    const size_t lists = static_cast<size_t>(q.n_rows) * plans[p].n_chunks * 2;
+    const leccr_topk_stream& o = so[p];
+    if (o.workspace == nullptr || o.workspace_bytes < topk_ws_bytes(q.n_rows, o.sub_total)) return LECCR_ERR_WORKSPACE;
+    uint8_t* ws = static_cast<uint8_t*>(o.workspace);
+    const size_t lists = static_cast<size_t>(q.n_rows) * o.sub_total * 2;
     cand_val[p] = reinterpret_cast<float*>(ws);
     ws += align256(lists * 32 * 4);
     cand_idx[p] = reinterpret_cast<int*>(ws);
@@ -546,30 +535,49 @@ int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
     ws += align256(lists * 4);
     flag[p] = reinterpret_cast<int*>(ws);  // [0] count, [4..] list of undecided rows
     ws += align256(static_cast<size_t>(q.n_rows) * 4 + 16);
-    if (q.gt_off != nullptr) CUDA_TRY(cudaMemsetAsync(flag[p], 0, 16, stream));
-    if (plans[p].n_chunks > 1 || two) {  // every owner of a row cooperates through a shared threshold
-      EP.row_thr[p] = reinterpret_cast<unsigned*>(ws);
-      CUDA_TRY(cudaMemsetAsync(ws, 0, static_cast<size_t>(q.n_rows) * 4, stream));
+    unsigned* row_thr = reinterpret_cast<unsigned*>(ws);
+    // does this one call fill every slot?  (fewer column chunks than slots leave empty lists behind)
+    const bool whole = (o.phases & LECCR_TOPK_GEMM) && o.sub_begin == 0 && plans[p].n_chunks == o.sub_total;
+    if (o.phases & LECCR_TOPK_INIT) {
+      CUDA_TRY(cudaMemsetAsync(flag[p], 0, 16, stream));
+      CUDA_TRY(cudaMemsetAsync(row_thr, 0, static_cast<size_t>(q.n_rows) * 4, stream));
+      if (!whole) CUDA_TRY(cudaMemsetAsync(cand_cnt[p], 0, lists * 4, stream));
     }
-    ws += align256(static_cast<size_t>(q.n_rows) * 4);
-    EP.out_val[p] = cand_val[p];
-    EP.out_idx[p] = cand_idx[p];
-    EP.out_cnt[p] = cand_cnt[p];
-    EP.n_sub[p] = plans[p].n_chunks * wgs;
+    if (o.phases & LECCR_TOPK_GEMM) {
+      const int g = n_launch++;
+      int rc = fill_problem(L.prob[g], q.rows16, q.ld_rows16, q.cols16, q.ld_cols16, q.n_rows, q.n_cols, D, fmt,
+                            plans[p], item_base);
+      if (rc != LECCR_OK) return rc;
+      item_base += plans[p].row_blocks * plans[p].n_chunks;
+      // every owner of a row (column chunks of this call, earlier calls, the other warpgroup) cooperates
+      // through a shared per-row threshold
+      if (o.sub_total > 1 || two) EP.row_thr[g] = row_thr;
+      EP.out_val[g] = cand_val[p];
+      EP.out_idx[g] = cand_idx[p];
+      EP.out_cnt[g] = cand_cnt[p];
+      EP.n_sub[g] = o.sub_total * wgs;
+      EP.sub_base[g] = o.sub_begin * wgs;
+      EP.col_base[g] = static_cast<int>(o.col_begin);
+    }
   }
+  L.n_prob = n_launch;
   L.n_items = item_base;
-  prof_mark("topk:begin", stream);
-  if (two) {
-    TopK2::Params EP2;
-    memcpy(&EP2, &EP, sizeof(EP2));
-    rc = launch_gemm<TopK2>(L, EP2, stream);
-  } else {
-    rc = launch_gemm<TopK1>(L, EP, stream);
+  int rc = LECCR_OK;
+  if (n_launch > 0) {
+    prof_mark("topk:begin", stream);
+    if (two) {
+      TopK2::Params EP2;
+      memcpy(&EP2, &EP, sizeof(EP2));
+      rc = launch_gemm<TopK2>(L, EP2, stream);
+    } else {
+      rc = launch_gemm<TopK1>(L, EP, stream);
+    }
+    if (rc != LECCR_OK) return rc;
+    prof_mark("topk:gemm", stream);
   }
-  if (rc != LECCR_OK) return rc;
-  prof_mark("topk:gemm", stream);
 
   for (int p = 0; p < n_prob; ++p) {
+    if (!(so[p].phases & LECCR_TOPK_FINALIZE)) continue;
     const leccr_topk_problem& q = probs[p];
     TopkFinalizeParams F;
     memset(&F, 0, sizeof(F));
@@ -577,8 +585,8 @@ int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
     F.cand_idx = cand_idx[p];
     F.cand_cnt = cand_cnt[p];
     F.n_rows = static_cast<int>(q.n_rows);
-    F.n_cols = static_cast<int>(q.n_cols);
-    F.n_chunks = plans[p].n_chunks * wgs;
+    F.n_cols = static_cast<int>(so[p].n_cols_total > 0 ? so[p].n_cols_total : q.n_cols);
+    F.n_chunks = so[p].sub_total * wgs;
     F.list_cap = cap;
     F.KP = LECCR_TOPK_KP;
     F.k = k;
@@ -623,6 +631,67 @@ int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
     }
   }
   return LECCR_OK;
+}
+
+static int topk_check_problem(const leccr_topk_problem& q, bool need_finalize) {
+  if (q.rows16 == nullptr || q.cols16 == nullptr || q.n_rows <= 0 || q.n_cols <= 0) return LECCR_ERR_ARG;
+  if (need_finalize && (q.topk_val == nullptr || q.topk_idx == nullptr)) return LECCR_ERR_ARG;
+  if (need_finalize && q.gt_off != nullptr &&
+      (q.gt_ids == nullptr || q.rows_x == nullptr || q.cols_x == nullptr || q.rn_hi == nullptr ||
+       q.rn_lo == nullptr || q.col_stats == nullptr || q.rank == nullptr || q.x_dtype < 0 || q.x_dtype > 2))
+    return LECCR_ERR_ARG;
+  return LECCR_OK;
+}
+
+int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, int k, int tiles_per_chunk,
+                   void* workspace, size_t workspace_bytes, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (probs == nullptr || n_prob < 1 || n_prob > 2 || D <= 0 || bad_fmt(fmt) || k < 1 || k > LECCR_TOPK_KP)
+    return LECCR_ERR_ARG;
+  for (int p = 0; p < n_prob; ++p)
+    if (topk_check_problem(probs[p], true) != LECCR_OK) return LECCR_ERR_ARG;
+  int rc = leccr_check_device();
+  if (rc != LECCR_OK) return rc;
+  Plan plans[2];
+  rc = topk_plan(probs, n_prob, tiles_per_chunk, plans);
+  if (rc != LECCR_OK) return rc;  // tiles_per_chunk too small: more than kMaxTopkChunks column chunks per row
+  if (workspace == nullptr || workspace_bytes < leccr_sim_topk_workspace(probs, n_prob, tiles_per_chunk))
+    return LECCR_ERR_WORKSPACE;
+  leccr_topk_stream so[2];
+  memset(so, 0, sizeof(so));
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  for (int p = 0; p < n_prob; ++p) {
+    so[p].phases = LECCR_TOPK_INIT | LECCR_TOPK_GEMM | LECCR_TOPK_FINALIZE;
+    so[p].sub_begin = 0;
+    so[p].sub_count = so[p].sub_total = plans[p].n_chunks;
+    so[p].workspace = ws;
+    so[p].workspace_bytes = topk_ws_bytes(probs[p].n_rows, plans[p].n_chunks);
+    ws += so[p].workspace_bytes;
+  }
+  return topk_core(probs, so, plans, n_prob, D, fmt, k, stream);
+}
+
+int leccr_sim_topk_stream(const leccr_topk_problem* probs, const leccr_topk_stream* streams, int n_prob, int D,
+                          int fmt, int k, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (probs == nullptr || streams == nullptr || n_prob < 1 || n_prob > 2 || D <= 0 || bad_fmt(fmt) || k < 1 ||
+      k > LECCR_TOPK_KP)
+    return LECCR_ERR_ARG;
+  Plan plans[2];
+  for (int p = 0; p < n_prob; ++p) {
+    const leccr_topk_stream& o = streams[p];
+    if ((o.phases & ~(LECCR_TOPK_INIT | LECCR_TOPK_GEMM | LECCR_TOPK_FINALIZE)) != 0 || o.phases == 0 ||
+        o.sub_total < 1 || o.sub_total > kMaxTopkChunks || o.sub_begin < 0 || o.sub_count < 1 ||
+        o.sub_begin + o.sub_count > o.sub_total || o.col_begin < 0 || o.col_begin > 0x7fffffffLL)
+      return LECCR_ERR_ARG;
+    if (topk_check_problem(probs[p], (o.phases & LECCR_TOPK_FINALIZE) != 0) != LECCR_OK) return LECCR_ERR_ARG;
+    const int64_t col_tiles = (probs[p].n_cols + BN - 1) / BN;
+    const int tpc = static_cast<int>((col_tiles + o.sub_count - 1) / o.sub_count);
+    plans[p] = plan_problem(probs[p].n_cols, 0, probs[p].n_rows, tpc);
+  }
+  int rc = leccr_check_device();
+  if (rc != LECCR_OK) return rc;
+  return topk_core(probs, streams, plans, n_prob, D, fmt, k, stream);
 }
 
 // ------------------------------------------------------------------------------------ InfoNCE
@@ -877,6 +946,88 @@ int leccr_topk_merge_peers(const float* const* val_ptrs_dev, const int32_t* cons
   topk_merge_peers_kernel<<<grid, warps * 32, smem, stream>>>(val_ptrs_dev, reinterpret_cast<const int* const*>(idx_ptrs_dev),
                                                             world, k_in, q_begin, q_count, offs, k_out, out_val, out_idx);
   LAUNCH_CHECK("topk_merge_peers_kernel");
+  return LECCR_OK;
+}
+
+// ------------------------------------------------------------------------------------ one-call contrastive step
+// The Python shim's per-launch overhead (tens of microseconds per torch / ctypes call) dominated the
+// training step; these two entries issue the whole forward / backward launch sequence from C++.
+size_t leccr_itc_fwd_workspace(int64_t n, int tiles_per_chunk) { return leccr_infonce_fwd_workspace(n, tiles_per_chunk); }
+
+int leccr_itc_forward(const float* image_feat, int64_t ld_img, const float* text_feat, int64_t ld_txt,
+                      const int64_t* idx, int64_t B, int D, int fmt, int rank, int world,
+                      void* const* rows_ptrs_dev, void* const* idx_ptrs_dev, uint32_t* const* flag_ptrs_dev,
+                      uint32_t epoch, const void* local_rows, const int64_t* local_idx, void* both16,
+                      int64_t* idx_all, const float* temp, float* out, float* lse2, float* rcnt,
+                      void* workspace, size_t workspace_bytes, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (image_feat == nullptr || text_feat == nullptr || both16 == nullptr || B <= 0 || D <= 0 || (D & 7) != 0 ||
+      bad_fmt(fmt) || world < 1 || rank < 0 || rank >= world || (idx != nullptr && idx_all == nullptr))
+    return LECCR_ERR_ARG;
+  const int64_t n = B * world;
+  uint16_t* both = static_cast<uint16_t*>(both16);
+  int rc;
+  if (world == 1) {
+    rc = leccr_prep(image_feat, B, D, ld_img, 0, fmt, LECCR_LAYOUT_HI, both, 2 * D, nullptr, nullptr, nullptr, stream_);
+    if (rc != LECCR_OK) return rc;
+    rc = leccr_prep(text_feat, B, D, ld_txt, 0, fmt, LECCR_LAYOUT_HI, both + D, 2 * D, nullptr, nullptr, nullptr, stream_);
+    if (rc != LECCR_OK) return rc;
+    if (idx != nullptr) CUDA_TRY(cudaMemcpyAsync(idx_all, idx, static_cast<size_t>(B) * 8, cudaMemcpyDeviceToDevice, stream));
+  } else {
+    if (rows_ptrs_dev == nullptr || flag_ptrs_dev == nullptr || local_rows == nullptr ||
+        (idx != nullptr && (idx_ptrs_dev == nullptr || local_idx == nullptr)))
+      return LECCR_ERR_ARG;
+    // cast + exchange: every rank's rows land in every rank's peer-mapped buffer (NVLink stores)
+    rc = leccr_prep_push(image_feat, B, D, ld_img, 0, fmt, rows_ptrs_dev, world, rank * B, 0, 2 * D, stream_);
+    if (rc != LECCR_OK) return rc;
+    rc = leccr_prep_push(text_feat, B, D, ld_txt, 0, fmt, rows_ptrs_dev, world, rank * B, D, 2 * D, stream_);
+    if (rc != LECCR_OK) return rc;
+    if (idx != nullptr) {
+      rc = leccr_push_words(idx, B, idx_ptrs_dev, world, rank * B, stream_);
+      if (rc != LECCR_OK) return rc;
+    }
+    rc = leccr_peer_barrier(flag_ptrs_dev, world, rank, epoch, stream_);
+    if (rc != LECCR_OK) return rc;
+    // private copy: the peer-mapped slot is reused two calls later, the backward runs after that
+    CUDA_TRY(cudaMemcpyAsync(both, local_rows, static_cast<size_t>(n) * 2 * D * 2, cudaMemcpyDeviceToDevice, stream));
+    if (idx != nullptr)
+      CUDA_TRY(cudaMemcpyAsync(idx_all, local_idx, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToDevice, stream));
+  }
+  return leccr_infonce_fwd(both, both + D, 2 * D, idx != nullptr ? idx_all : nullptr, n, D, fmt, temp, out, lse2, rcnt,
+                           0, workspace, workspace_bytes, stream_);
+}
+
+size_t leccr_itc_bwd_workspace(int64_t n, int64_t row_count, int D) {
+  if (n <= 0 || row_count <= 0 || D <= 0) return 0;
+  const size_t tr = align256(static_cast<size_t>(D) * round_up8(n) * 2);
+  return 2 * tr + leccr_infonce_bwd_workspace(n, row_count, D);
+}
+
+int leccr_itc_backward(const void* both16, const int64_t* idx_all, int64_t n, int D, int fmt, const float* temp,
+                       const float* lse2, const float* rcnt, const float* out, int64_t row_begin, int64_t row_count,
+                       const float* grad_out, float* dA, float* dB, float* dtemp, void* workspace,
+                       size_t workspace_bytes, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (both16 == nullptr || workspace == nullptr || n <= 0 || D <= 0 || out == nullptr || grad_out == nullptr)
+    return LECCR_ERR_ARG;
+  if (workspace_bytes < leccr_itc_bwd_workspace(n, row_count, D)) return LECCR_ERR_WORKSPACE;
+  const uint16_t* both = static_cast<const uint16_t*>(both16);
+  const int64_t ldT = round_up8(n);
+  const size_t tr = align256(static_cast<size_t>(D) * ldT * 2);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  void* aT = ws;
+  void* bT = ws + tr;
+  int rc = leccr_transpose16(both, n, D, 2 * D, aT, ldT, stream_);
+  if (rc != LECCR_OK) return rc;
+  rc = leccr_transpose16(both + D, n, D, 2 * D, bT, ldT, stream_);
+  if (rc != LECCR_OK) return rc;
+  rc = leccr_infonce_bwd(both, both + D, 2 * D, aT, bT, ldT, idx_all, n, D, fmt, temp, lse2, rcnt, row_begin, row_count,
+                         grad_out, dA, dB, ws + 2 * tr, workspace_bytes - 2 * tr, stream_);
+  if (rc != LECCR_OK) return rc;
+  if (dtemp != nullptr) {  // dL/dtemp = grad_out * (d loss / d temp from the forward)
+    scalar_product_kernel<<<1, 32, 0, stream>>>(grad_out, out + 1, dtemp);
+    LAUNCH_CHECK("scalar_product_kernel");
+  }
   return LECCR_OK;
 }
 

@@ -165,7 +165,9 @@ struct EpiTopK {
     float* out_val[2];  // [n_rows][n_sub][C]
     int* out_idx[2];
     int* out_cnt[2];    // [n_rows][n_sub]
-    int n_sub[2];       // partial lists per row: n_chunks * kWGs
+    int n_sub[2];       // partial lists per row: n_chunks * kWGs (over all calls of a streamed evaluation)
+    int sub_base[2];    // first list slot this launch writes (streamed evaluation: one column window per call)
+    int col_base[2];    // global index of the launch's first column (added to the stored column indices)
     unsigned* row_thr[2];  // [n_rows] shared per-row threshold keys (zeroed per launch), or null
     int debug_mode;     // measurement aid: 1 = threshold +inf (filter only), 2 = skip the tile entirely
     unsigned long long* debug_counters;  // measurement aid: [chunks, hit chunks, hit groups, shrink rounds, appends]
@@ -338,12 +340,14 @@ struct EpiTopK {
       }
     }
     int hit_chunks = 0;  // warp-uniform
-    for_each_chunk(taddr, col0, n_cols, [&](float(&v)[32], int col) {
-      if (col + 32 > n_cols) {  // ragged last columns (TMA zero-filled): exclude them
+    const int cb = P.col_base[c.p];
+    for_each_chunk(taddr, col0, n_cols, [&](float(&v)[32], int lcol) {
+      if (lcol + 32 > n_cols) {  // ragged last columns (TMA zero-filled): exclude them
 #pragma unroll
         for (int e = 0; e < 32; ++e)
-          if (col + e >= n_cols) v[e] = -CUDART_INF_F;
+          if (lcol + e >= n_cols) v[e] = -CUDART_INF_F;
       }
+      const int col = lcol + cb;  // stored indices are global
       if (dense) {  // warp-uniform; invariant: cnt <= DTRIG = C - 16 before every 16 columns
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -428,7 +432,7 @@ struct EpiTopK {
       const int row = c.rb * BM + c.warp_q * 32 + src;
       if (row >= c.n_rows) break;  // warp-uniform
       const int cnt_src = __shfl_sync(0xffffffffu, st.cnt, src);
-      const long long o = (static_cast<long long>(row) * nch + c.sub) * C;
+      const long long o = (static_cast<long long>(row) * nch + P.sub_base[c.p] + c.sub) * C;
       const uint32_t vb = wbase + static_cast<uint32_t>(src) * LDSW * 4;
       const uint32_t ib = vb + kIdxOff;
 #pragma unroll
@@ -439,7 +443,7 @@ struct EpiTopK {
           P.out_idx[c.p][o + s] = lds_s32(ib + s * ES);
         }
       }
-      if (c.lane == 0) P.out_cnt[c.p][static_cast<long long>(row) * nch + c.sub] = cnt_src;
+      if (c.lane == 0) P.out_cnt[c.p][static_cast<long long>(row) * nch + P.sub_base[c.p] + c.sub] = cnt_src;
     }
     __syncwarp();
   }

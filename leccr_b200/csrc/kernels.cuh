@@ -986,4 +986,8 @@ __global__ void topk_merge_peers_kernel(const float* const* __restrict__ vals, c
   }
 }
 
+__global__ void scalar_product_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o) {
+  if (threadIdx.x == 0) *o = *a * *b;
+}
+
 }  // namespace leccr

@@ -298,6 +298,206 @@ class FusedEvalPlan:
         return (ev, self.topk) if return_topk else ev
 
 
+class StreamedEvalPlan:
+    """Fused evaluation of HOST-resident embeddings with the PCIe transfer overlapped: the text set crosses
+    in `windows` pieces on a copy stream while the tensor cores already rank what has arrived
+    (leccr_sim_topk_stream).  Per window one launch carries two problems: image rows x the window's text
+    columns (candidates accumulate in the image problem's list slots, finalised after the last window) and
+    the window's text rows x all images (complete rows, finalised at once).  Same results as fused_eval.
+
+        plan = StreamedEvalPlan(n_img, n_txt, dim, txt2img, img2txt)
+        ev = plan.run(image_embeds_host, text_embeds_host)      # pinned fp32 host tensors (or numpy)
+    """
+
+    def __init__(self, n_img, n_txt, dim, txt2img=None, img2txt=None, k=10, precision="f16", gt=None,
+                 windows=3, img_subs=2, txt_subs=3):
+        import ctypes
+
+        self.dev = _device()
+        lib = N.load()
+        self.lib = lib
+        self.n_img, self.n_txt, self.dim, self.k = n_img, n_txt, dim, k
+        self.fmt = ops.fmt_of(precision)
+        if dim % 8 != 0:
+            raise N.LeccrError("embedding dimension must be a multiple of 8 (TMA 16-byte rows)")
+        if isinstance(windows, int):
+            fracs = [1.0 / max(1, windows)] * max(1, windows)
+        else:
+            fracs = [float(f) / sum(windows) for f in windows]  # shrinking windows shorten the un-overlapped tail
+        fracs = fracs[:max(1, 8 // img_subs)]
+        self.gt = gt if gt is not None else prepare_gt(txt2img, img2txt, n_img, n_txt, self.dev)
+        dev = self.dev
+        dt16 = torch.float16 if self.fmt == N.FMT_F16 else torch.bfloat16
+        f32 = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.img = torch.empty((n_img, dim), **f32)
+        self.txt = torch.empty((n_txt, dim), **f32)
+        self.img16 = torch.empty((n_img, dim), dtype=dt16, device=dev)
+        self.txt16 = torch.empty((n_txt, dim), dtype=dt16, device=dev)
+        self.rn = torch.empty((4, max(n_img, n_txt)), **f32)       # rn_hi / rn_lo of images, of texts
+        self.small = torch.zeros(16, **f32)                          # [0:4] image stats, [4:8] text stats
+        self.counts = torch.zeros(8, **i32)                          # [0:3] i2t, [4:7] t2i Recall counts
+        self.out = torch.empty(8, **f32)
+        self.host = torch.empty(8, dtype=torch.float32).pin_memory()
+        self.topk = {'i2t': (torch.empty((n_img, k), **f32), torch.empty((n_img, k), **i32)),
+                     't2i': (torch.empty((n_txt, k), **f32), torch.empty((n_txt, k), **i32))}
+        self.ranks = (torch.empty(n_img, **i32), torch.empty(n_txt, **i32))
+        self.gts = (torch.empty(max(1, self.gt[0][1].numel()), **f32), torch.empty(max(1, self.gt[1][1].numel()), **f32))
+        # window boundaries: equal pieces, multiples of 256 columns except the last
+        self.bounds = []
+        b, acc = 0, 0.0
+        for i, f in enumerate(fracs):
+            acc += f
+            e = n_txt if i == len(fracs) - 1 else min(n_txt, (int(round(acc * n_txt)) + 255) // 256 * 256)
+            if e > b:
+                self.bounds.append((b, e))
+            b = max(b, e)
+        if b < n_txt:
+            self.bounds[-1] = (self.bounds[-1][0], n_txt)
+        per = max(e - b for b, e in self.bounds)
+        W = len(self.bounds)
+        self.sub_total = W * img_subs
+        self.ws_img = torch.empty(lib.leccr_sim_topk_stream_workspace(n_img, self.sub_total), dtype=torch.uint8, device=dev)
+        self.ws_txt = torch.empty(lib.leccr_sim_topk_stream_workspace(per, txt_subs), dtype=torch.uint8, device=dev)
+        esz = 2
+        gi_off, gi_ids = self.gt[0]
+        gt_off, gt_ids = self.gt[1]
+        # ground-truth CSR of a text window: offsets rebased on the host once (one GT image per text in the
+        # reference's datasets, but any CSR works)
+        off_host = gt_off.cpu()
+        self._keep = []
+        self.calls = []
+        for w, (b, e) in enumerate(self.bounds):
+            pr = (N.TopkProblem * 2)()
+            so = (N.TopkStream * 2)()
+            # problem 0: image rows x this window's text columns (tensor-core phase only)
+            p = pr[0]
+            p.rows16, p.cols16 = self.img16.data_ptr(), self.txt16.data_ptr() + b * dim * esz
+            p.ld_rows16 = p.ld_cols16 = dim
+            p.n_rows, p.n_cols = n_img, e - b
+            o = so[0]
+            o.phases = N.TOPK_GEMM | (N.TOPK_INIT if w == 0 else 0)
+            o.sub_begin, o.sub_count, o.sub_total = w * img_subs, img_subs, self.sub_total
+            o.col_begin = b
+            o.workspace, o.workspace_bytes = self.ws_img.data_ptr(), self.ws_img.numel()
+            # problem 1: this window's text rows x all images, complete
+            woff = (off_host[b:e + 1] - off_host[b]).to(torch.int32).to(dev)
+            wids = gt_ids[int(off_host[b]):int(off_host[e])]
+            self._keep += [woff, wids]
+            p = pr[1]
+            p.rows16, p.cols16 = self.txt16.data_ptr() + b * dim * esz, self.img16.data_ptr()
+            p.ld_rows16 = p.ld_cols16 = dim
+            p.n_rows, p.n_cols = e - b, n_img
+            p.topk_val = self.topk['t2i'][0].data_ptr() + b * k * 4
+            p.topk_idx = self.topk['t2i'][1].data_ptr() + b * k * 4
+            p.gt_off, p.gt_ids = woff.data_ptr(), wids.data_ptr()
+            p.rows_x, p.cols_x = self.txt.data_ptr() + b * dim * 4, self.img.data_ptr()
+            p.ld_rows_x = p.ld_cols_x = dim
+            p.x_dtype = N.F32
+            p.rn_hi, p.rn_lo = self.rn[2].data_ptr() + b * 4, self.rn[3].data_ptr() + b * 4
+            p.col_stats = self.small.data_ptr()
+            p.rank = self.ranks[1].data_ptr() + b * 4
+            p.recall_counts = self.counts.data_ptr() + 16
+            p.gt_score = self.gts[1].data_ptr() + int(off_host[b]) * 4
+            o = so[1]
+            o.phases = N.TOPK_INIT | N.TOPK_GEMM | N.TOPK_FINALIZE
+            o.sub_begin, o.sub_count, o.sub_total = 0, txt_subs, txt_subs
+            o.workspace, o.workspace_bytes = self.ws_txt.data_ptr(), self.ws_txt.numel()
+            self.calls.append((pr, so, 2))
+        # final call: merge the image problem's slots
+        pr = (N.TopkProblem * 1)()
+        so = (N.TopkStream * 1)()
+        p = pr[0]
+        p.rows16, p.cols16 = self.img16.data_ptr(), self.txt16.data_ptr()
+        p.ld_rows16 = p.ld_cols16 = dim
+        p.n_rows, p.n_cols = n_img, n_txt
+        p.topk_val, p.topk_idx = self.topk['i2t'][0].data_ptr(), self.topk['i2t'][1].data_ptr()
+        p.gt_off, p.gt_ids = gi_off.data_ptr(), gi_ids.data_ptr()
+        p.rows_x, p.cols_x = self.img.data_ptr(), self.txt.data_ptr()
+        p.ld_rows_x = p.ld_cols_x = dim
+        p.x_dtype = N.F32
+        p.rn_hi, p.rn_lo = self.rn[0].data_ptr(), self.rn[1].data_ptr()
+        p.col_stats = self.small.data_ptr() + 16
+        p.rank = self.ranks[0].data_ptr()
+        p.recall_counts = self.counts.data_ptr()
+        p.gt_score = self.gts[0].data_ptr()
+        o = so[0]
+        o.phases = N.TOPK_FINALIZE
+        o.sub_begin, o.sub_count, o.sub_total = 0, self.sub_total, self.sub_total
+        o.n_cols_total = n_txt
+        o.workspace, o.workspace_bytes = self.ws_img.data_ptr(), self.ws_img.numel()
+        self.calls.append((pr, so, 1))
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ev_img = torch.cuda.Event()
+        self.ev_win = [torch.cuda.Event() for _ in self.bounds]
+
+    def _prep(self, src, dst16, row0, row1, rn_hi, rn_lo, stats_ptr, st):
+        d = self.dim
+        N.check(self.lib.leccr_prep(src.data_ptr() + row0 * d * 4, row1 - row0, d, d, 0, self.fmt, N.LAYOUT_HI,
+                                    dst16.data_ptr() + row0 * d * 2, d, rn_hi.data_ptr() + row0 * 4,
+                                    rn_lo.data_ptr() + row0 * 4, stats_ptr, st), "leccr_prep")
+
+    def _issue(self, img_h, txt_h):
+        """Everything of one evaluation, asynchronously: windowed H2D on the copy stream, casts, tensor-core
+        passes and finalizes on the current stream, D2H of the counts into self.host."""
+        cur = torch.cuda.current_stream()
+        cs = self.copy_stream
+        cs.wait_stream(cur)  # the previous run has consumed the staging buffers
+        with torch.cuda.stream(cs):
+            self.img.copy_(img_h, non_blocking=True)
+            self.ev_img.record(cs)
+            for w, (b, e) in enumerate(self.bounds):
+                self.txt[b:e].copy_(txt_h[b:e], non_blocking=True)
+                self.ev_win[w].record(cs)
+        st = cur.cuda_stream
+        self.small.zero_()
+        self.counts.zero_()
+        cur.wait_event(self.ev_img)
+        self._prep(self.img, self.img16, 0, self.n_img, self.rn[0], self.rn[1], self.small.data_ptr(), st)
+        for w, (b, e) in enumerate(self.bounds):
+            cur.wait_event(self.ev_win[w])
+            self._prep(self.txt, self.txt16, b, e, self.rn[2], self.rn[3], self.small.data_ptr() + 16, st)
+            pr, so, n = self.calls[w]
+            N.check(self.lib.leccr_sim_topk_stream(pr, so, n, self.dim, self.fmt, self.k, st), "leccr_sim_topk_stream")
+        pr, so, n = self.calls[-1]
+        N.check(self.lib.leccr_sim_topk_stream(pr, so, n, self.dim, self.fmt, self.k, st), "leccr_sim_topk_stream")
+        cur.wait_stream(cs)
+        torch.cat([self.counts[0:3].float(), self.counts[4:7].float(), self.small[3:4], self.small[7:8]], out=self.out)
+        self.host.copy_(self.out, non_blocking=True)
+
+    @torch.no_grad()
+    def run(self, image_embeds, text_embeds, return_topk=False, graph=True):
+        """One evaluation.  With pinned host tensors the whole sequence (H2D windows included) is captured in
+        a CUDA graph on first use and replayed whenever the SAME pinned buffers are passed again (serving:
+        refill the buffers in place); other inputs take the eager path."""
+        img_h = torch.as_tensor(image_embeds)
+        txt_h = torch.as_tensor(text_embeds)
+        if img_h.shape != self.img.shape or txt_h.shape != self.txt.shape or img_h.dtype != torch.float32 \
+                or txt_h.dtype != torch.float32:
+            raise N.LeccrError("StreamedEvalPlan.run needs fp32 [n_img, D] and [n_txt, D] inputs of the planned shape")
+        pinned = (not img_h.is_cuda) and (not txt_h.is_cuda) and img_h.is_pinned() and txt_h.is_pinned() \
+            and img_h.is_contiguous() and txt_h.is_contiguous()
+        key = (img_h.data_ptr(), txt_h.data_ptr())
+        if graph and pinned and getattr(self, "_graph_key", None) == key:
+            self._graph.replay()
+        elif graph and pinned:
+            self._issue(img_h, txt_h)  # eager once: lazy initialisation must not happen under capture
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._issue(img_h, txt_h)
+            self._graph, self._graph_key, self._graph_src = g, key, (img_h, txt_h)
+            g.replay()
+        else:
+            self._issue(img_h, txt_h)
+        torch.cuda.current_stream().synchronize()
+        h = self.host.tolist()
+        if h[6] != 0.0 or h[7] != 0.0:
+            raise N.LeccrError("embeddings overflow the fp16 operand format; build the plan with precision='bf16'")
+        ev = metrics_from_counts([int(c) for c in h[0:3]], self.n_img, [int(c) for c in h[3:6]], self.n_txt)
+        return (ev, self.topk) if return_topk else ev
+
+
 # ----------------------------------------------------------------------------- multi-GPU (SURVEY.md section 8e)
 @torch.no_grad()
 def fused_eval_sharded(image_embeds, text_embeds, txt2img, img2txt, k=10, precision="f16", group=None):

@@ -115,44 +115,23 @@ def get_buffer(key, nbytes: int, device):
     return pb
 
 
-def gather_contrastive(image_feat, text_feat, idx, fmt):
-    """Cast + exchange of the contrastive operands in one step (replaces the three AllGather calls of
-    models/xvlm.py:271-272,285).  Returns (both [n, 2D] 16-bit private copy, idx_all [n] int64 or None),
-    or None when peer exchange is not available."""
-    dev = image_feat.device
-    if not available(dev):
+def itc_slot(B: int, D: int, fmt: int, device):
+    """Peer-mapped slot for one contrastive exchange (leccr_itc_forward): returns
+    (rows_table, idx_table, flag_table, epoch, local_rows_ptr, local_idx_ptr) or None when peer exchange
+    is not available.  Collective on first use per shape; alternates two slots."""
+    if not available(device):
         return None
-    B, D = image_feat.shape
-    world, rank = dist.get_world_size(), dist.get_rank()
+    world = dist.get_world_size()
     n = B * world
     row_bytes = 2 * D * 2
-    pb = get_buffer(("itc", B, D, fmt), n * row_bytes + n * 8, dev)
+    pb = get_buffer(("itc", B, D, fmt), n * row_bytes + n * 8, device)
     if pb is None:
         return None
-    lib = N.load()
-    slot = pb.next_slot()
-    off = pb.slot_offset(slot)
-    rows_tab = pb.table(off)
-    img = image_feat.detach().float()
-    txt = text_feat.detach().float()
-    if img.stride(1) != 1:
-        img = img.contiguous()
-    if txt.stride(1) != 1:
-        txt = txt.contiguous()
-    st = N.stream_ptr()
-    N.check(lib.leccr_prep_push(N.ptr(img), B, D, img.stride(0), 0, fmt, N.ptr(rows_tab), world, rank * B, 0, 2 * D,
-                                st), "leccr_prep_push")
-    N.check(lib.leccr_prep_push(N.ptr(txt), B, D, txt.stride(0), 0, fmt, N.ptr(rows_tab), world, rank * B, D, 2 * D,
-                                st), "leccr_prep_push")
-    if idx is not None:
-        ix = idx.detach().view(-1).long().contiguous()
-        idx_tab = pb.table(off + n * row_bytes)
-        N.check(lib.leccr_push_words(N.ptr(ix), B, N.ptr(idx_tab), world, rank * B, st), "leccr_push_words")
-    pb.barrier()
-    dt16 = torch.float16 if fmt == N.FMT_F16 else torch.bfloat16
-    both = pb.local(off, (n, 2 * D), dt16).clone()
-    idx_all = pb.local(off + n * row_bytes, (n,), torch.int64).clone() if idx is not None else None
-    return both, idx_all
+    off = pb.slot_offset(pb.next_slot())
+    pb.epoch += 1
+    base = pb.buf.data_ptr()
+    return (pb.table(off), pb.table(off + n * row_bytes), pb.flag_table, pb.epoch, base + off,
+            base + off + n * row_bytes)
 
 
 def merge_topk_peers(val, idx, shard_offset: int, k: int, all_queries: bool = True):

@@ -326,3 +326,26 @@ def test_peer_barrier_single_rank_and_merge_peers_against_sort():
         wv, wi = sharding.merge_topk(vals_s, gidx, k)
         assert torch.equal(out_v.cpu(), wv[qb:qb + qn]), (world, Q, k_in, k)
         assert torch.equal(out_i.cpu().long(), wi[qb:qb + qn]), (world, Q, k_in, k)
+
+
+# ----------------------------------------------------------------------------- streamed evaluation
+@pytest.mark.parametrize("cfg,windows", [("cfg1", 4), ("cfg1", 1), ("cfg2", (0.4, 0.3, 0.2, 0.1)), ("ragged", 3)])
+def test_streamed_eval_plan_equals_reference_and_fused_eval(golden, cfg, windows):
+    """Host embeddings crossing PCIe in windows (leccr_sim_topk_stream) give the same dict and the same
+    top-k lists as the one-launch fused_eval; cfg1 / cfg2 dicts are the reference's own."""
+    if cfg == "ragged":
+        rs = synth.retrieval_set(333, 3, d=64, seed=9)   # 999 texts: ragged windows and tiles
+    else:
+        rs = synth.cfg1_multi30k() if cfg == "cfg1" else synth.cfg2_mscoco5k()
+    n, m, d = rs.image.shape[0], rs.text.shape[0], rs.image.shape[1]
+    plan = leccr_b200.StreamedEvalPlan(n, m, d, rs.txt2img, rs.img2txt, windows=windows)
+    img_h, txt_h = rs.image.contiguous().pin_memory(), rs.text.contiguous().pin_memory()
+    want_ev, want_topk = leccr_b200.fused_eval(rs.image, rs.text, rs.txt2img, rs.img2txt, k=10)
+    for _ in range(2):  # second run reuses every static buffer
+        ev, topk = plan.run(img_h, txt_h, return_topk=True)
+        assert_ev_equal(ev, want_ev)
+        if cfg in ("cfg1", "cfg2"):
+            assert_ev_equal(ev, ev_of(golden("baseline_configs.npz"), f"{cfg}_ev_"))
+        for d_ in ("i2t", "t2i"):
+            assert torch.equal(topk[d_][0], want_topk[d_][0]), d_
+            assert torch.equal(topk[d_][1], want_topk[d_][1]), d_
