@@ -242,9 +242,12 @@ int leccr_topk_merge_peers(const float* const* val_ptrs_dev, const int32_t* cons
  * training step is two library calls.
  *   image_feat, text_feat : this rank's [B][D] fp32 rows;  idx: [B] int64 or NULL
  *   world == 1 : rows_ptrs_dev .. local_idx are ignored
- *   world  > 1 : rows_ptrs_dev[p] -> rank p's peer-mapped [n][2D] 16-bit slot, idx_ptrs_dev[p] -> its [n]
- *                int64 slot, flag_ptrs_dev / epoch as in leccr_peer_barrier, local_rows / local_idx = this
- *                rank's own slot (rows_ptrs_dev[rank], idx_ptrs_dev[rank]).  The caller alternates two slots.
+ *   world == 1 : rows_ptrs_dev .. local_slot_bytes are ignored; 3 launches: cast, tensor-core pass, finalize
+ *   world  > 1 : rows_ptrs_dev[p] -> rank p's peer-mapped slot: [n][2D] 16-bit rows followed (at idx_all -
+ *                both16 bytes) by [n] int64 labels -- the private buffer's own layout; idx_ptrs_dev[p] -> the
+ *                labels part; flag_ptrs_dev / epoch as in leccr_peer_barrier; local_slot = this rank's slot,
+ *                local_slot_bytes the bytes to copy into both16 (rows, + labels when idx != NULL).
+ *                The caller alternates two slots.  5 launches: push, barrier, copy, tensor-core pass, finalize.
  *   both16 : out, private [n][2D] 16-bit gathered operands [image | text] (saved for the backward)
  *   idx_all: out, [n] int64 (when idx != NULL);  out/lse2/rcnt as in leccr_infonce_fwd
  *   backward: dA, dB [row_count][D] fp32, dtemp scalar = grad_out * out[1] (may be NULL)
@@ -253,7 +256,7 @@ size_t leccr_itc_fwd_workspace(int64_t n, int tiles_per_chunk);
 int leccr_itc_forward(const float* image_feat, int64_t ld_img, const float* text_feat, int64_t ld_txt,
                       const int64_t* idx, int64_t B, int D, int fmt, int rank, int world,
                       void* const* rows_ptrs_dev, void* const* idx_ptrs_dev, uint32_t* const* flag_ptrs_dev,
-                      uint32_t epoch, const void* local_rows, const int64_t* local_idx, void* both16,
+                      uint32_t epoch, const void* local_slot, size_t local_slot_bytes, void* both16,
                       int64_t* idx_all, const float* temp, float* out, float* lse2, float* rcnt,
                       void* workspace, size_t workspace_bytes, leccr_stream_t stream);
 size_t leccr_itc_bwd_workspace(int64_t n, int64_t row_count, int D);

@@ -67,7 +67,7 @@ _SIGNATURES = {
                                       c_int, vp]),
     "leccr_itc_fwd_workspace": (sz, [i64, c_int]),
     "leccr_itc_forward": (c_int, [vp, i64, vp, i64, vp, i64, c_int, c_int, c_int, c_int, vp, vp, vp, ctypes.c_uint32,
-                                  vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+                                  vp, sz, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "leccr_itc_bwd_workspace": (sz, [i64, i64, c_int]),
     "leccr_itc_backward": (c_int, [vp, vp, i64, c_int, c_int, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, sz, vp]),
     "leccr_peer_barrier": (c_int, [vp, c_int, c_int, ctypes.c_uint32, vp]),

@@ -94,12 +94,13 @@ class _SymmetricInfoNCE(torch.autograd.Function):
         else:
             ws = _workspace("fwd", lib.leccr_itc_fwd_workspace(n, 0), dev)
             rows_tab = idx_tab = flag_tab = None
-            epoch, l_rows, l_idx = 0, None, None
+            epoch, l_slot = 0, None
             if slot is not None:
-                rows_tab, idx_tab, flag_tab, epoch, l_rows, l_idx = slot
+                rows_tab, idx_tab, flag_tab, epoch, l_slot = slot
+            l_bytes = (o_idx + n * 8) if ix is not None else n * 2 * D * 2
             N.check(lib.leccr_itc_forward(N.ptr(img), img.stride(0), N.ptr(txt), txt.stride(0), N.ptr(ix), B, D, fmt,
                                           rank, world, N.ptr(rows_tab), N.ptr(idx_tab), N.ptr(flag_tab), epoch,
-                                          l_rows, l_idx, base, base + o_idx, N.ptr(temp_dev), base + o_out,
+                                          l_slot, l_bytes, base, base + o_idx, N.ptr(temp_dev), base + o_out,
                                           base + o_lse, base + o_rc, N.ptr(ws), ws.numel(), N.stream_ptr()),
                     "leccr_itc_forward")
         ctx.save_for_backward(saved, temp_dev)
@@ -116,16 +117,16 @@ class _SymmetricInfoNCE(torch.autograd.Function):
         go = grad_out.detach().reshape(())
         if go.dtype != torch.float32:
             go = go.float()
-        grads = torch.empty(2 * B * D + 1, dtype=torch.float32, device=dev)
-        g = grads.data_ptr()
+        # separate allocations: autograd can adopt them as .grad without a copy
+        dA = torch.empty((B, D), dtype=torch.float32, device=dev)
+        dB = torch.empty((B, D), dtype=torch.float32, device=dev)
+        dtemp = torch.empty((), dtype=torch.float32, device=dev)
         ws = _workspace("bwd", lib.leccr_itc_bwd_workspace(n, B, D), dev)
         N.check(lib.leccr_itc_backward(base, base + o_idx if has_idx else None, n, D, fmt, N.ptr(temp_dev),
-                                       base + o_lse, base + o_rc, base + o_out, rank * B, B, N.ptr(go), g,
-                                       g + B * D * 4, g + 2 * B * D * 4, N.ptr(ws), ws.numel(), N.stream_ptr()),
+                                       base + o_lse, base + o_rc, base + o_out, rank * B, B, N.ptr(go), N.ptr(dA),
+                                       N.ptr(dB), N.ptr(dtemp), N.ptr(ws), ws.numel(), N.stream_ptr()),
                 "leccr_itc_backward")
-        dA = grads[:B * D].view(B, D)
-        dB = grads[B * D:2 * B * D].view(B, D)
-        return dA, dB, grads[2 * B * D].reshape(()), None, None, None, None
+        return dA, dB, dtemp, None, None, None, None
 
 
 def contrastive_loss(image_feat, text_feat, temp, idx=None, precision=None):

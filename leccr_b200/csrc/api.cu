@@ -352,7 +352,8 @@ struct StoreProblem {
 };
 
 static int launch_store(const StoreProblem* sp, int n_prob, int K, int fmt, float scale, const float* scale_dev,
-                        const float* div_dev, int k_splits, cudaStream_t stream) {
+                        const float* div_dev, int k_splits, cudaStream_t stream, const float* prod_a = nullptr,
+                        const float* prod_b = nullptr, float* prod_out = nullptr) {
   SimLaunch L;
   memset(&L, 0, sizeof(L));
   L.n_prob = n_prob;
@@ -397,13 +398,27 @@ static int launch_store(const StoreProblem* sp, int n_prob, int K, int fmt, floa
   L.n_items = item_base;
   int rc = launch_gemm<EpiStore>(L, EP, stream);
   if (rc != LECCR_OK) return rc;
+  bool prod_done = false;
   if (split) {
-    for (int p = 0; p < n_prob; ++p) {
-      const long long plane = sp[p].n_rows * sp[p].ld_out;
-      const unsigned g = static_cast<unsigned>(std::min<long long>((plane + 255) / 256, 4LL * num_sms()));
-      splitk_reduce_kernel<<<g, 256, 0, stream>>>(sp[p].parts, n_planes, plane, sp[p].out);
-      LAUNCH_CHECK("splitk_reduce_kernel");
+    const long long plane0 = sp[0].n_rows * sp[0].ld_out;
+    if (n_prob == 2 && sp[1].n_rows * sp[1].ld_out == plane0) {  // one launch for both (and the scalar product)
+      dim3 g(static_cast<unsigned>(std::min<long long>((plane0 + 255) / 256, 2LL * num_sms())), 2);
+      splitk_reduce2_kernel<<<g, 256, 0, stream>>>(sp[0].parts, sp[1].parts, n_planes, plane0, sp[0].out, sp[1].out,
+                                                  prod_a, prod_b, prod_out);
+      LAUNCH_CHECK("splitk_reduce2_kernel");
+      prod_done = true;
+    } else {
+      for (int p = 0; p < n_prob; ++p) {
+        const long long plane = sp[p].n_rows * sp[p].ld_out;
+        const unsigned g = static_cast<unsigned>(std::min<long long>((plane + 255) / 256, 4LL * num_sms()));
+        splitk_reduce_kernel<<<g, 256, 0, stream>>>(sp[p].parts, n_planes, plane, sp[p].out);
+        LAUNCH_CHECK("splitk_reduce_kernel");
+      }
     }
+  }
+  if (prod_out != nullptr && !prod_done) {
+    scalar_product_kernel<<<1, 32, 0, stream>>>(prod_a, prod_b, prod_out);
+    LAUNCH_CHECK("scalar_product_kernel");
   }
   return LECCR_OK;
 }
@@ -707,9 +722,27 @@ size_t leccr_infonce_fwd_workspace(int64_t n, int tiles_per_chunk) {
   return 2 * align256(static_cast<size_t>(n) * pl.n_chunks * EpiLse::kWGs * 5 * 4) + 256;
 }
 
+// scratch (8 doubles of block sums + ticket) sits behind the two partial planes of the workspace
+static double* infonce_fwd_scratch(int64_t n, int tiles_per_chunk, void* workspace) {
+  const Plan pl = infonce_plan(n, tiles_per_chunk);
+  const size_t part_bytes = align256(static_cast<size_t>(n) * pl.n_chunks * EpiLse::kWGs * 5 * 4);
+  return reinterpret_cast<double*>(static_cast<uint8_t*>(workspace) + 2 * part_bytes);
+}
+
+static int infonce_fwd_impl(const void* a16, const void* b16, int64_t ld16, const int64_t* idx, int64_t n, int D,
+                            int fmt, const float* temp, float* out, float* lse2, float* rcnt, int tiles_per_chunk,
+                            void* workspace, size_t workspace_bytes, bool scratch_is_zero, leccr_stream_t stream_);
+
 int leccr_infonce_fwd(const void* a16, const void* b16, int64_t ld16, const int64_t* idx, int64_t n, int D,
                       int fmt, const float* temp, float* out, float* lse2, float* rcnt, int tiles_per_chunk,
                       void* workspace, size_t workspace_bytes, leccr_stream_t stream_) {
+  return infonce_fwd_impl(a16, b16, ld16, idx, n, D, fmt, temp, out, lse2, rcnt, tiles_per_chunk, workspace,
+                          workspace_bytes, false, stream_);
+}
+
+static int infonce_fwd_impl(const void* a16, const void* b16, int64_t ld16, const int64_t* idx, int64_t n, int D,
+                            int fmt, const float* temp, float* out, float* lse2, float* rcnt, int tiles_per_chunk,
+                            void* workspace, size_t workspace_bytes, bool scratch_is_zero, leccr_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (a16 == nullptr || b16 == nullptr || temp == nullptr || out == nullptr || lse2 == nullptr || rcnt == nullptr ||
       n <= 0 || D <= 0 || bad_fmt(fmt))
@@ -735,7 +768,7 @@ int leccr_infonce_fwd(const void* a16, const void* b16, int64_t ld16, const int6
   float* part0 = static_cast<float*>(workspace);
   float* part1 = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + part_bytes);
   double* scratch = reinterpret_cast<double*>(static_cast<uint8_t*>(workspace) + 2 * part_bytes);
-  CUDA_TRY(cudaMemsetAsync(scratch, 0, 64, stream));
+  if (!scratch_is_zero) CUDA_TRY(cudaMemsetAsync(scratch, 0, 64, stream));
   EpiLse::Params EP;
   memset(&EP, 0, sizeof(EP));
   EP.temp = temp;
@@ -782,11 +815,27 @@ size_t leccr_infonce_bwd_workspace(int64_t n, int64_t row_count, int D) {
   return 2 * align256(static_cast<size_t>(row_count) * round_up8(n) * 2) + align256(parts);
 }
 
+static int infonce_bwd_impl(const void* a16, const void* b16, int64_t ld16, const void* aT16, const void* bT16,
+                            int64_t ldT, const int64_t* idx, int64_t n, int D, int fmt, const float* temp,
+                            const float* lse2, const float* rcnt, int64_t row_begin, int64_t row_count,
+                            const float* grad_out, float* dA, float* dB, void* workspace, size_t workspace_bytes,
+                            const float* prod_b, float* prod_out, leccr_stream_t stream_);
+
 int leccr_infonce_bwd(const void* a16, const void* b16, int64_t ld16, const void* aT16, const void* bT16,
                       int64_t ldT, const int64_t* idx, int64_t n, int D, int fmt, const float* temp,
                       const float* lse2, const float* rcnt, int64_t row_begin, int64_t row_count,
                       const float* grad_out, float* dA, float* dB, void* workspace, size_t workspace_bytes,
                       leccr_stream_t stream_) {
+  return infonce_bwd_impl(a16, b16, ld16, aT16, bT16, ldT, idx, n, D, fmt, temp, lse2, rcnt, row_begin, row_count,
+                          grad_out, dA, dB, workspace, workspace_bytes, nullptr, nullptr, stream_);
+}
+
+// prod_out (optional) = grad_out * *prod_b, computed by the last launch
+static int infonce_bwd_impl(const void* a16, const void* b16, int64_t ld16, const void* aT16, const void* bT16,
+                            int64_t ldT, const int64_t* idx, int64_t n, int D, int fmt, const float* temp,
+                            const float* lse2, const float* rcnt, int64_t row_begin, int64_t row_count,
+                            const float* grad_out, float* dA, float* dB, void* workspace, size_t workspace_bytes,
+                            const float* prod_b, float* prod_out, leccr_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (a16 == nullptr || b16 == nullptr || aT16 == nullptr || bT16 == nullptr || temp == nullptr ||
       lse2 == nullptr || rcnt == nullptr || dA == nullptr || dB == nullptr || n <= 0 || D <= 0 || bad_fmt(fmt) ||
@@ -848,7 +897,7 @@ int leccr_infonce_bwd(const void* a16, const void* b16, int64_t ld16, const void
         {strip1, aT16, ldS, ldT, row_count, D, dB, D, parts1},
     };
     rc = launch_store(sp, 2, static_cast<int>(n), fmt, 1.0f / (2.0f * static_cast<float>(n)), grad_out, temp,
-                      splits, stream);
+                      splits, stream, grad_out, prod_b, prod_out);
     if (rc != LECCR_OK) return rc;
   }
   return LECCR_OK;
@@ -957,44 +1006,58 @@ size_t leccr_itc_fwd_workspace(int64_t n, int tiles_per_chunk) { return leccr_in
 int leccr_itc_forward(const float* image_feat, int64_t ld_img, const float* text_feat, int64_t ld_txt,
                       const int64_t* idx, int64_t B, int D, int fmt, int rank, int world,
                       void* const* rows_ptrs_dev, void* const* idx_ptrs_dev, uint32_t* const* flag_ptrs_dev,
-                      uint32_t epoch, const void* local_rows, const int64_t* local_idx, void* both16,
+                      uint32_t epoch, const void* local_slot, size_t local_slot_bytes, void* both16,
                       int64_t* idx_all, const float* temp, float* out, float* lse2, float* rcnt,
                       void* workspace, size_t workspace_bytes, leccr_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (image_feat == nullptr || text_feat == nullptr || both16 == nullptr || B <= 0 || D <= 0 || (D & 7) != 0 ||
-      bad_fmt(fmt) || world < 1 || rank < 0 || rank >= world || (idx != nullptr && idx_all == nullptr))
+      bad_fmt(fmt) || world < 1 || rank < 0 || rank >= world || (idx != nullptr && idx_all == nullptr) ||
+      ld_img < D || ld_txt < D)
     return LECCR_ERR_ARG;
   const int64_t n = B * world;
+  if (workspace == nullptr || workspace_bytes < leccr_infonce_fwd_workspace(n, 0)) return LECCR_ERR_WORKSPACE;
+  double* scratch = infonce_fwd_scratch(n, 0, workspace);
   uint16_t* both = static_cast<uint16_t*>(both16);
-  int rc;
+  // ONE launch casts both operands (and pushes idx): into every rank's peer-mapped slot (world > 1, NVLink
+  // stores) or straight into the private buffers (world == 1, a "world" of this rank's own two pointers)
+  const int wpb = 8;
+  dim3 grid(static_cast<unsigned>((B + wpb - 1) / wpb), idx != nullptr ? 3 : 2);
+  const unsigned long long* idx_u = reinterpret_cast<const unsigned long long*>(idx);
   if (world == 1) {
-    rc = leccr_prep(image_feat, B, D, ld_img, 0, fmt, LECCR_LAYOUT_HI, both, 2 * D, nullptr, nullptr, nullptr, stream_);
-    if (rc != LECCR_OK) return rc;
-    rc = leccr_prep(text_feat, B, D, ld_txt, 0, fmt, LECCR_LAYOUT_HI, both + D, 2 * D, nullptr, nullptr, nullptr, stream_);
-    if (rc != LECCR_OK) return rc;
-    if (idx != nullptr) CUDA_TRY(cudaMemcpyAsync(idx_all, idx, static_cast<size_t>(B) * 8, cudaMemcpyDeviceToDevice, stream));
-  } else {
-    if (rows_ptrs_dev == nullptr || flag_ptrs_dev == nullptr || local_rows == nullptr ||
-        (idx != nullptr && (idx_ptrs_dev == nullptr || local_idx == nullptr)))
-      return LECCR_ERR_ARG;
-    // cast + exchange: every rank's rows land in every rank's peer-mapped buffer (NVLink stores)
-    rc = leccr_prep_push(image_feat, B, D, ld_img, 0, fmt, rows_ptrs_dev, world, rank * B, 0, 2 * D, stream_);
-    if (rc != LECCR_OK) return rc;
-    rc = leccr_prep_push(text_feat, B, D, ld_txt, 0, fmt, rows_ptrs_dev, world, rank * B, D, 2 * D, stream_);
-    if (rc != LECCR_OK) return rc;
-    if (idx != nullptr) {
-      rc = leccr_push_words(idx, B, idx_ptrs_dev, world, rank * B, stream_);
-      if (rc != LECCR_OK) return rc;
-    }
-    rc = leccr_peer_barrier(flag_ptrs_dev, world, rank, epoch, stream_);
-    if (rc != LECCR_OK) return rc;
-    // private copy: the peer-mapped slot is reused two calls later, the backward runs after that
-    CUDA_TRY(cudaMemcpyAsync(both, local_rows, static_cast<size_t>(n) * 2 * D * 2, cudaMemcpyDeviceToDevice, stream));
-    if (idx != nullptr)
-      CUDA_TRY(cudaMemcpyAsync(idx_all, local_idx, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToDevice, stream));
+    unsigned long long* own_idx = reinterpret_cast<unsigned long long*>(idx_all);
+    if (fmt == LECCR_FMT_F16)
+      itc_push_kernel<0><<<grid, wpb * 32, 0, stream>>>(image_feat, ld_img, text_feat, ld_txt, idx_u, (int)B, D, nullptr,
+                                                       nullptr, both, own_idx, 1, 0, scratch, 8);
+    else
+      itc_push_kernel<1><<<grid, wpb * 32, 0, stream>>>(image_feat, ld_img, text_feat, ld_txt, idx_u, (int)B, D, nullptr,
+                                                       nullptr, both, own_idx, 1, 0, scratch, 8);
+    LAUNCH_CHECK("itc_push_kernel");
+    return infonce_fwd_impl(both, both + D, 2 * D, idx != nullptr ? idx_all : nullptr, n, D, fmt, temp, out, lse2, rcnt,
+                            0, workspace, workspace_bytes, true, stream_);
   }
-  return leccr_infonce_fwd(both, both + D, 2 * D, idx != nullptr ? idx_all : nullptr, n, D, fmt, temp, out, lse2, rcnt,
-                           0, workspace, workspace_bytes, stream_);
+  if (rows_ptrs_dev == nullptr || flag_ptrs_dev == nullptr || local_slot == nullptr ||
+      (idx != nullptr && idx_ptrs_dev == nullptr))
+    return LECCR_ERR_ARG;
+  {
+    uint16_t* const* dsts = reinterpret_cast<uint16_t* const*>(rows_ptrs_dev);
+    unsigned long long* const* idsts = reinterpret_cast<unsigned long long* const*>(idx_ptrs_dev);
+    if (fmt == LECCR_FMT_F16)
+      itc_push_kernel<0><<<grid, wpb * 32, 0, stream>>>(image_feat, ld_img, text_feat, ld_txt, idx_u, (int)B, D, dsts,
+                                                       idsts, nullptr, nullptr, world,
+                                                       static_cast<long long>(rank) * B, scratch, 8);
+    else
+      itc_push_kernel<1><<<grid, wpb * 32, 0, stream>>>(image_feat, ld_img, text_feat, ld_txt, idx_u, (int)B, D, dsts,
+                                                       idsts, nullptr, nullptr, world,
+                                                       static_cast<long long>(rank) * B, scratch, 8);
+    LAUNCH_CHECK("itc_push_kernel");
+  }
+  int rc = leccr_peer_barrier(flag_ptrs_dev, world, rank, epoch, stream_);
+  if (rc != LECCR_OK) return rc;
+  // private copy (one memcpy: the slot and the private buffer share the layout [rows | idx]): the peer-mapped
+  // slot is reused two calls later, the backward runs after that
+  CUDA_TRY(cudaMemcpyAsync(both, local_slot, local_slot_bytes, cudaMemcpyDeviceToDevice, stream));
+  return infonce_fwd_impl(both, both + D, 2 * D, idx != nullptr ? idx_all : nullptr, n, D, fmt, temp, out, lse2, rcnt,
+                          0, workspace, workspace_bytes, true, stream_);
 }
 
 size_t leccr_itc_bwd_workspace(int64_t n, int64_t row_count, int D) {
@@ -1017,18 +1080,17 @@ int leccr_itc_backward(const void* both16, const int64_t* idx_all, int64_t n, in
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   void* aT = ws;
   void* bT = ws + tr;
-  int rc = leccr_transpose16(both, n, D, 2 * D, aT, ldT, stream_);
-  if (rc != LECCR_OK) return rc;
-  rc = leccr_transpose16(both + D, n, D, 2 * D, bT, ldT, stream_);
-  if (rc != LECCR_OK) return rc;
-  rc = leccr_infonce_bwd(both, both + D, 2 * D, aT, bT, ldT, idx_all, n, D, fmt, temp, lse2, rcnt, row_begin, row_count,
-                         grad_out, dA, dB, ws + 2 * tr, workspace_bytes - 2 * tr, stream_);
-  if (rc != LECCR_OK) return rc;
-  if (dtemp != nullptr) {  // dL/dtemp = grad_out * (d loss / d temp from the forward)
-    scalar_product_kernel<<<1, 32, 0, stream>>>(grad_out, out + 1, dtemp);
-    LAUNCH_CHECK("scalar_product_kernel");
+  {
+    dim3 grid(static_cast<unsigned>((ldT + 31) / 32), static_cast<unsigned>((D + 31) / 32), 2);
+    dim3 block(32, 8);
+    transpose16_pair_kernel<<<grid, block, 0, stream>>>(both, both + D, 2 * D, (int)n, D, static_cast<uint16_t*>(aT),
+                                                       static_cast<uint16_t*>(bT), ldT);
+    LAUNCH_CHECK("transpose16_pair_kernel");
   }
-  return LECCR_OK;
+  // dL/dtemp = grad_out * (d loss / d temp from the forward), written by the backward's last launch
+  return infonce_bwd_impl(both, both + D, 2 * D, aT, bT, ldT, idx_all, n, D, fmt, temp, lse2, rcnt, row_begin,
+                          row_count, grad_out, dA, dB, ws + 2 * tr, workspace_bytes - 2 * tr,
+                          dtemp != nullptr ? out + 1 : nullptr, dtemp, stream_);
 }
 
 }  // extern "C"

@@ -255,6 +255,56 @@ __global__ void prep_push_kernel(const float* __restrict__ src, long long ld_src
   }
 }
 
+// The whole contrastive exchange of one rank in ONE launch: blockIdx.y = 0 casts + pushes the image rows to
+// column 0 of every rank's [n][2D] buffer, 1 the text rows to column D, 2 pushes the idx words (optional);
+// block (0, 0) also clears `zero_words` doubles at `zero` (scratch of the forward that follows).
+template <int FMT>
+__global__ void itc_push_kernel(const float* __restrict__ img, long long ld_img, const float* __restrict__ txt,
+                                long long ld_txt, const unsigned long long* __restrict__ idx, int B, int D,
+                                uint16_t* const* __restrict__ dsts, unsigned long long* const* __restrict__ idx_dsts,
+                                uint16_t* __restrict__ own_rows, unsigned long long* __restrict__ own_idx,
+                                int world, long long row0, double* __restrict__ zero, int zero_words) {
+  // world == 1 (dsts == nullptr): the only destination is this rank's private buffer
+  if (blockIdx.x == 0 && blockIdx.y == 0 && zero != nullptr && threadIdx.x < zero_words) zero[threadIdx.x] = 0.0;
+  if (blockIdx.y == 2) {
+    if (idx == nullptr) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
+      const unsigned long long w = idx[i];
+      if (idx_dsts == nullptr) own_idx[row0 + i] = w;
+      else
+        for (int p = 0; p < world; ++p) idx_dsts[p][row0 + i] = w;
+    }
+    return;
+  }
+  const float* src = blockIdx.y == 0 ? img : txt;
+  const long long ld_src = blockIdx.y == 0 ? ld_img : ld_txt;
+  const long long col0 = blockIdx.y == 0 ? 0 : D;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const float* x = src + static_cast<long long>(row) * ld_src;
+  const long long off = (row0 + row) * (2LL * D) + col0;
+  const bool vec = (D & 3) == 0 && (ld_src & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  if (vec) {
+    for (int d = 4 * lane; d < D; d += 128) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(x + d));
+      const uint16_t h0 = f32_to_16<FMT>(t.x), h1 = f32_to_16<FMT>(t.y);
+      const uint16_t h2 = f32_to_16<FMT>(t.z), h3 = f32_to_16<FMT>(t.w);
+      const uint2 hv = make_uint2(h0 | (static_cast<uint32_t>(h1) << 16), h2 | (static_cast<uint32_t>(h3) << 16));
+      if (dsts == nullptr) *reinterpret_cast<uint2*>(own_rows + off + d) = hv;
+      else
+        for (int p = 0; p < world; ++p) *reinterpret_cast<uint2*>(dsts[p] + off + d) = hv;  // peer stores
+    }
+  } else {
+    for (int d = lane; d < D; d += 32) {
+      const uint16_t h = f32_to_16<FMT>(x[d]);
+      if (dsts == nullptr) own_rows[off + d] = h;
+      else
+        for (int p = 0; p < world; ++p) dsts[p][off + d] = h;
+    }
+  }
+}
+
 // Push a contiguous block of 8-byte words (the idx column, models/xvlm.py:285) to every rank's buffer.
 __global__ void push_words_kernel(const unsigned long long* __restrict__ src, long long n_words,
                                   unsigned long long* const* __restrict__ dsts, int world, long long dst_word0) {
@@ -320,6 +370,41 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ parts, int n_spli
     float acc = 0.f;
     for (int sp = 0; sp < n_splits; ++sp) acc += parts[static_cast<long long>(sp) * plane + i];
     out[i] = acc;
+  }
+}
+
+// Two equally shaped problems in one launch (blockIdx.y selects), plus an optional scalar product
+// o = a * b (dL/dtemp of the contrastive backward) so the backward needs no launch of its own for it.
+__global__ void splitk_reduce2_kernel(const float* __restrict__ parts0, const float* __restrict__ parts1, int n_splits,
+                                      long long plane, float* __restrict__ out0, float* __restrict__ out1,
+                                      const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o) {
+  const float* parts = blockIdx.y == 0 ? parts0 : parts1;
+  float* out = blockIdx.y == 0 ? out0 : out1;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < plane;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float acc = 0.f;
+    for (int sp = 0; sp < n_splits; ++sp) acc += parts[static_cast<long long>(sp) * plane + i];
+    out[i] = acc;
+  }
+  if (o != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *o = *a * *b;
+}
+
+// Both transposes of the contrastive backward in one launch (blockIdx.z selects the operand).
+__global__ void transpose16_pair_kernel(const uint16_t* __restrict__ src0, const uint16_t* __restrict__ src1,
+                                        long long ld_src, int n, int D, uint16_t* __restrict__ dst0,
+                                        uint16_t* __restrict__ dst1, long long ld_dst) {
+  __shared__ uint16_t t[32][34];
+  const uint16_t* src = blockIdx.z == 0 ? src0 : src1;
+  uint16_t* dst = blockIdx.z == 0 ? dst0 : dst1;
+  const int r0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, d = d0 + threadIdx.x;
+    t[i][threadIdx.x] = (r < n && d < D) ? src[static_cast<long long>(r) * ld_src + d] : 0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int d = d0 + i, r = r0 + threadIdx.x;
+    if (d < D && r < ld_dst) dst[static_cast<long long>(d) * ld_dst + r] = (r < n) ? t[threadIdx.x][i] : 0;
   }
 }
 

@@ -117,21 +117,20 @@ def get_buffer(key, nbytes: int, device):
 
 def itc_slot(B: int, D: int, fmt: int, device):
     """Peer-mapped slot for one contrastive exchange (leccr_itc_forward): returns
-    (rows_table, idx_table, flag_table, epoch, local_rows_ptr, local_idx_ptr) or None when peer exchange
-    is not available.  Collective on first use per shape; alternates two slots."""
+    (rows_table, idx_table, flag_table, epoch, local_slot_ptr) or None when peer exchange is not available.
+    Slot layout = the private buffer's: [n][2D] 16-bit rows (padded to 256 bytes) then [n] int64 labels.
+    Collective on first use per shape; alternates two slots."""
     if not available(device):
         return None
     world = dist.get_world_size()
     n = B * world
-    row_bytes = 2 * D * 2
-    pb = get_buffer(("itc", B, D, fmt), n * row_bytes + n * 8, device)
+    rows_bytes = (n * 2 * D * 2 + 255) // 256 * 256
+    pb = get_buffer(("itc", B, D, fmt), rows_bytes + n * 8, device)
     if pb is None:
         return None
     off = pb.slot_offset(pb.next_slot())
     pb.epoch += 1
-    base = pb.buf.data_ptr()
-    return (pb.table(off), pb.table(off + n * row_bytes), pb.flag_table, pb.epoch, base + off,
-            base + off + n * row_bytes)
+    return pb.table(off), pb.table(off + rows_bytes), pb.flag_table, pb.epoch, pb.buf.data_ptr() + off
 
 
 def merge_topk_peers(val, idx, shard_offset: int, k: int, all_queries: bool = True):
