@@ -443,6 +443,7 @@ int leccr_sim_f32(const void* rows16, int64_t ld_rows, const void* cols16, int64
 // Two epilogue shapes (see EpiTopK): one warpgroup with 64-entry lists, or two with 32-entry lists.
 using TopK1 = EpiTopK<LECCR_TOPK_KP, 64, 1>;
 using TopK2 = EpiTopK<LECCR_TOPK_KP, 32, 2>;
+using TopK1D = EpiTopK<LECCR_TOPK_KP, 64, 1, 1>;  // dense-only build of TopK1 (short column chunks)
 constexpr int kMaxTopkChunks = 8;  // topk_finalize holds n_chunks * kWGs * (C / 32) <= 16 slots per lane
 
 static bool topk_two_wgs() {
@@ -584,6 +585,11 @@ static int topk_core(const leccr_topk_problem* probs, const leccr_topk_stream* s
       TopK2::Params EP2;
       memcpy(&EP2, &EP, sizeof(EP2));
       rc = launch_gemm<TopK2>(L, EP2, stream);
+    } else if (EP.dense == 1 && EP.debug_mode == 0 && EP.debug_counters == nullptr) {
+      TopK1D::Params EPD;
+      static_assert(sizeof(TopK1D::Params) == sizeof(TopK1::Params), "parameter layouts must agree");
+      memcpy(&EPD, &EP, sizeof(EPD));
+      rc = launch_gemm<TopK1D>(L, EPD, stream);
     } else {
       rc = launch_gemm<TopK1>(L, EP, stream);
     }

@@ -148,7 +148,10 @@ __device__ __forceinline__ void top16_of_two(float* a, const float* b, bool reso
 // Two shapes: <16, 64, 1> one warpgroup with 64-entry lists, <16, 32, 2> two warpgroups (alternate
 // tiles) with 32-entry lists; in both the lists take 66 KB of shared memory.  The two threads that own
 // the same row (and the CTAs that own other column chunks of it) cooperate through row_thr.
-template <int KP, int C_, int WGS>
+// MODE 0: the filter / dense choice is a run-time parameter (Params::dense); MODE 1: always dense, the
+// filter code is not even compiled in (half the instruction footprint: the single epilogue warp per
+// scheduler cannot hide instruction-cache misses or branch resolution).
+template <int KP, int C_, int WGS, int MODE = 0>
 struct EpiTopK {
   static constexpr int kWGs = WGS;
   static constexpr int C = C_;           // list capacity
@@ -194,7 +197,7 @@ struct EpiTopK {
     st.cnt = 0;
 #pragma unroll
     for (int i = 0; i < 5; ++i) st.dc[i] = 0;
-    st.dense_tiles = P.dense == 2 ? 4 : 0;
+    st.dense_tiles = (MODE == 0 && P.dense == 2) ? 4 : 0;
     st.pre_key = 0u;
     st.vb = smem_u32(c.smem) + static_cast<uint32_t>(c.et) * LDSW * 4;
     st.ib = st.vb + kIdxOff;
@@ -329,7 +332,7 @@ struct EpiTopK {
     // that large) is valid for every chunk: adopt the best one published so far.  Stale reads are fine.
     unsigned* shared_thr = (P.row_thr[c.p] != nullptr && c.row < c.n_rows) ? P.row_thr[c.p] + c.row : nullptr;
     if (st.pre_key > f32_key(st.thr)) st.thr = key_f32(st.pre_key);  // fetched by prefetch() during the wait
-    const bool dense = P.dense == 1 || st.dense_tiles > 0;  // warp-uniform
+    const bool dense = MODE == 1 || P.dense == 1 || st.dense_tiles > 0;  // warp-uniform
     if (st.dense_tiles > 0) --st.dense_tiles;
     if (dense && __any_sync(0xffffffffu, st.cnt > DTRIG)) {  // the dense path appends up to 16 between checks
       if (st.cnt > JOIN) {
@@ -372,6 +375,7 @@ struct EpiTopK {
         }
         return;
       }
+      if (MODE == 1) return;  // compile-time: nothing below exists in the dense-only kernel
       float gm[4];
 #pragma unroll
       for (int g = 0; g < 4; ++g)
@@ -412,7 +416,7 @@ struct EpiTopK {
         }
       }
     });
-    if (P.dense == 2 && hit_chunks >= 6) st.dense_tiles = 4;
+    if (MODE == 0 && P.dense == 2 && hit_chunks >= 6) st.dense_tiles = 4;
   }
 
   // Dump the raw lists; rows of a warp are written one after another so stores coalesce.
