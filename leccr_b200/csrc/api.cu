@@ -64,18 +64,18 @@ int num_sms() {
 }
 
 // 2-D K-major 16-bit operand [n][K] (ld elements) with a {BK, box_rows} box and 128-byte swizzle.
-int make_tmap(CUtensorMap* tm, const void* base, int64_t n, int64_t K, int64_t ld, int fmt, int box_rows) {
+int make_tmap(CUtensorMap* tm, const void* base, int64_t n, int64_t K, int64_t ld, int fmt, int box_rows, int bk = BK) {
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld & 7) != 0) return LECCR_ERR_ALIGN;
   if (n <= 0 || K <= 0 || ld < K) return LECCR_ERR_ARG;
   EncodeTiledFn enc = get_encode_fn();
   if (enc == nullptr) return LECCR_ERR_DRIVER;
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(n)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, fmt == LECCR_FMT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                    2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_cuda_err, sizeof(g_cuda_err), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -107,10 +107,10 @@ int auto_tiles_per_chunk(int64_t total_tiles, int min_tpc) {
 }
 
 int fill_problem(SimProblem& P, const void* rows16, int64_t ld_rows, const void* cols16, int64_t ld_cols,
-                 int64_t n_rows, int64_t n_cols, int K, int fmt, const Plan& pl, int item_base) {
-  int rc = make_tmap(&P.tm_rows, rows16, n_rows, K, ld_rows, fmt, BM);
+                 int64_t n_rows, int64_t n_cols, int K, int fmt, const Plan& pl, int item_base, int bk = BK) {
+  int rc = make_tmap(&P.tm_rows, rows16, n_rows, K, ld_rows, fmt, BM, bk);
   if (rc != LECCR_OK) return rc;
-  rc = make_tmap(&P.tm_cols, cols16, n_cols, K, ld_cols, fmt, BN);
+  rc = make_tmap(&P.tm_cols, cols16, n_cols, K, ld_cols, fmt, BN, bk);
   if (rc != LECCR_OK) return rc;
   P.n_rows = static_cast<int>(n_rows);
   P.n_cols = static_cast<int>(n_cols);
@@ -166,16 +166,16 @@ void prof_dump() {
 }
 
 // As many pipeline stages as fit beside the epilogue's own shared memory (227 KB per CTA).
-template <class Epi>
+template <class Epi, int kBK = BK>
 constexpr int stages_for() {
-  return sim_gemm_smem_bytes<Epi, 4>() <= 232448 ? 4 : 3;
+  return sim_gemm_smem_bytes<Epi, 4, kBK>() <= 232448 ? 4 : 3;
 }
 
-template <class Epi>
+template <class Epi, int kBK = BK>
 int launch_gemm(const SimLaunch& L, const typename Epi::Params& EP, cudaStream_t stream) {
-  constexpr int kStages = stages_for<Epi>();
-  auto kern = sim_gemm_kernel<Epi, kStages>;
-  constexpr size_t smem = sim_gemm_smem_bytes<Epi, kStages>();
+  constexpr int kStages = stages_for<Epi, kBK>();
+  auto kern = sim_gemm_kernel<Epi, kStages, kBK>;
+  constexpr size_t smem = sim_gemm_smem_bytes<Epi, kStages, kBK>();
   static_assert(smem <= 232448, "exceeds the 227 KB shared memory limit of sm_100");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -442,17 +442,28 @@ int leccr_sim_f32(const void* rows16, int64_t ld_rows, const void* cols16, int64
 // share of ~4 work items per SM proportional to its tile count.
 // Two epilogue shapes (see EpiTopK): one warpgroup with 64-entry lists, or two with 32-entry lists.
 using TopK1 = EpiTopK<LECCR_TOPK_KP, 64, 1>;
-using TopK2 = EpiTopK<LECCR_TOPK_KP, 32, 2>;
 using TopK1D = EpiTopK<LECCR_TOPK_KP, 64, 1, 1>;  // dense-only build of TopK1 (short column chunks)
+// Short column chunks are bound by the issue latency of the single epilogue warp per scheduler (ncu: issue
+// slots 36 % busy).  TopK2D runs TWO epilogue warpgroups (alternate tiles, each with its own 64-entry lists);
+// their 130 KB of lists fit beside the pipeline because its stages are half as deep (K = 32, 64-byte swizzle).
+using TopK2D = EpiTopK<LECCR_TOPK_KP, 64, 2, 1>;
+constexpr int kBK2 = 32;
 constexpr int kMaxTopkChunks = 8;  // topk_finalize holds n_chunks * kWGs * (C / 32) <= 16 slots per lane
 
-static bool topk_two_wgs() {
+static bool topk_two_wgs_allowed() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("LECCR_TOPK_WGS");  // measurement aid: 2 selects the two-warpgroup shape
-    v = (e != nullptr && atoi(e) == 2) ? 1 : 0;
+    const char* e = getenv("LECCR_TOPK_WGS");  // measurement aid: 1 keeps the single-warpgroup shapes
+    v = (e != nullptr && atoi(e) == 1) ? 0 : 1;
   }
   return v == 1;
+}
+// Dense mode (and with it the two-warpgroup shape) is chosen when every tensor-core problem of the launch has
+// short column chunks; decided from the plans alone so that workspace sizing and launch agree.
+static bool topk_dense(const Plan* plans, int n_prob, const int* gemm_mask) {
+  for (int p = 0; p < n_prob; ++p)
+    if ((gemm_mask == nullptr || gemm_mask[p]) && plans[p].tiles_per_chunk > 32) return false;
+  return true;
 }
 
 static int topk_plan(const leccr_topk_problem* probs, int n_prob, int tiles_per_chunk, Plan* plans) {
@@ -481,10 +492,11 @@ static size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255);
 
 // Per-problem workspace: candidate lists [n_rows][subs][64] (score, column), counts [n_rows][subs],
 // undecided-row list, shared per-row thresholds.
-static size_t topk_ws_bytes(int64_t n_rows, int subs) {
-  const size_t lists = static_cast<size_t>(n_rows) * subs * 2;  // either epilogue shape: subs * 64 entries per row
+static size_t topk_ws_bytes(int64_t n_rows, int subs, bool two = true) {
+  // lists of 32 entries: one warpgroup keeps 64 entries per (row, column chunk), two keep 128
+  const size_t lists = static_cast<size_t>(n_rows) * subs * (two ? 4 : 2);
   return align256(lists * 32 * 4) * 2 + align256(lists * 4) + align256(static_cast<size_t>(n_rows) * 4 + 16) +
-         align256(static_cast<size_t>(n_rows) * 4);
+         align256(static_cast<size_t>(n_rows) * 12);  // row_thr [n_rows] + row_h8 [n_rows][2]
 }
 
 size_t leccr_sim_topk_workspace(const leccr_topk_problem* probs, int n_prob, int tiles_per_chunk) {
@@ -492,41 +504,45 @@ size_t leccr_sim_topk_workspace(const leccr_topk_problem* probs, int n_prob, int
   Plan plans[2];
   if (topk_plan(probs, n_prob, tiles_per_chunk, plans) != LECCR_OK) return 0;
   size_t bytes = 0;
-  for (int p = 0; p < n_prob; ++p) bytes += topk_ws_bytes(probs[p].n_rows, plans[p].n_chunks);
+  const bool two = topk_two_wgs_allowed() && topk_dense(plans, n_prob, nullptr);
+  for (int p = 0; p < n_prob; ++p) bytes += topk_ws_bytes(probs[p].n_rows, plans[p].n_chunks, two);
   return bytes;
 }
 
 size_t leccr_sim_topk_stream_workspace(int64_t n_rows, int sub_total) {
   if (n_rows <= 0 || sub_total < 1 || sub_total > kMaxTopkChunks) return 0;
-  return topk_ws_bytes(n_rows, sub_total);
+  return topk_ws_bytes(n_rows, sub_total, true);
 }
 
 // The engine behind leccr_sim_topk and leccr_sim_topk_stream: per problem an optional tensor-core phase over
 // the columns given (writing candidate-list slots [sub_begin, sub_begin + chunks) of the problem's
 // persistent workspace) and an optional finalize phase over all sub_total slots.
 static int topk_core(const leccr_topk_problem* probs, const leccr_topk_stream* so, const Plan* plans, int n_prob, int D,
-                     int fmt, int k, cudaStream_t stream) {
+                     int fmt, int k, int two_hint, cudaStream_t stream) {
   SimLaunch L;
   memset(&L, 0, sizeof(L));
   L.fmt = fmt;
-  L.k_chunks = (D + BK - 1) / BK;
-  const bool two = topk_two_wgs();
+  int gemm_mask[2] = {0, 0};
+  for (int p = 0; p < n_prob; ++p) gemm_mask[p] = (so[p].phases & LECCR_TOPK_GEMM) ? 1 : 0;
+  const bool dense_launch = topk_dense(plans, n_prob, gemm_mask);
+  // a problem's lists must have ONE shape over all its calls: streamed problems (two_hint) say so themselves
+  const bool two = two_hint >= 0 ? (two_hint == 1) : (topk_two_wgs_allowed() && dense_launch);
   const int wgs = two ? 2 : 1;
-  const int cap = two ? TopK2::C : TopK1::C;
-  TopK1::Params EP;  // both shapes share the parameter layout
-  static_assert(sizeof(TopK1::Params) == sizeof(TopK2::Params), "parameter layouts must agree");
+  const int cap = TopK1::C;
+  const int bk = two ? kBK2 : BK;
+  L.k_chunks = (D + bk - 1) / bk;
+  TopK1::Params EP;  // all shapes share the parameter layout
+  static_assert(sizeof(TopK1::Params) == sizeof(TopK2D::Params), "parameter layouts must agree");
   memset(&EP, 0, sizeof(EP));
   if (const char* dbg = getenv("LECCR_TOPK_DEBUG")) EP.debug_mode = atoi(dbg);  // measurement aid only
   // shrink rounds start when a list holds more than `trig`; long chunks prefer fresher thresholds
   // (fewer candidates pass), short ones fewer rounds (measured optimum is flat between 36 and 56)
-  EP.trig = two ? TopK2::TRIG : (plans[0].tiles_per_chunk >= 64 ? 40 : TopK1::TRIG);
+  EP.trig = plans[0].tiles_per_chunk >= 64 ? 40 : TopK1::TRIG;
   // short column chunks never leave the warm-up regime: run them without the filter (measured: cfg2
   // 342 -> 304 us; long chunks are better off filtering: 12,500 x 1M 1202 vs 832 TFLOP/s)
-  EP.dense = 1;
-  for (int p = 0; p < n_prob; ++p)
-    if ((so[p].phases & LECCR_TOPK_GEMM) && plans[p].tiles_per_chunk > 32) EP.dense = 0;
+  EP.dense = dense_launch ? 1 : 0;
   if (const char* dn = getenv("LECCR_TOPK_DENSE")) EP.dense = atoi(dn);  // measurement aid
-  if (two) EP.dense = 0;  // 32-entry lists cannot take 16 unfiltered columns between checks (DTRIG < JOIN)
+  if (two) EP.dense = 1;  // the two-warpgroup shape exists as a dense-only build
   if (const char* tg = getenv("LECCR_TOPK_TRIG")) EP.trig = std::min(EP.trig, std::max(LECCR_TOPK_KP + 4, atoi(tg)));
   if (const char* dc = getenv("LECCR_TOPK_COUNTERS")) {  // measurement aid only: device address (hex) of 5 x u64
     EP.debug_counters = reinterpret_cast<unsigned long long*>(strtoull(dc, nullptr, 16));
@@ -540,9 +556,9 @@ static int topk_core(const leccr_topk_problem* probs, const leccr_topk_stream* s
   for (int p = 0; p < n_prob; ++p) {
     const leccr_topk_problem& q = probs[p];
     const leccr_topk_stream& o = so[p];
-    if (o.workspace == nullptr || o.workspace_bytes < topk_ws_bytes(q.n_rows, o.sub_total)) return LECCR_ERR_WORKSPACE;
+    if (o.workspace == nullptr || o.workspace_bytes < topk_ws_bytes(q.n_rows, o.sub_total, two)) return LECCR_ERR_WORKSPACE;
     uint8_t* ws = static_cast<uint8_t*>(o.workspace);
-    const size_t lists = static_cast<size_t>(q.n_rows) * o.sub_total * 2;
+    const size_t lists = static_cast<size_t>(q.n_rows) * o.sub_total * (two ? 4 : 2);
     cand_val[p] = reinterpret_cast<float*>(ws);
     ws += align256(lists * 32 * 4);
     cand_idx[p] = reinterpret_cast<int*>(ws);
@@ -556,18 +572,19 @@ static int topk_core(const leccr_topk_problem* probs, const leccr_topk_stream* s
     const bool whole = (o.phases & LECCR_TOPK_GEMM) && o.sub_begin == 0 && plans[p].n_chunks == o.sub_total;
     if (o.phases & LECCR_TOPK_INIT) {
       CUDA_TRY(cudaMemsetAsync(flag[p], 0, 16, stream));
-      CUDA_TRY(cudaMemsetAsync(row_thr, 0, static_cast<size_t>(q.n_rows) * 4, stream));
+      CUDA_TRY(cudaMemsetAsync(row_thr, 0, static_cast<size_t>(q.n_rows) * 12, stream));
       if (!whole) CUDA_TRY(cudaMemsetAsync(cand_cnt[p], 0, lists * 4, stream));
     }
     if (o.phases & LECCR_TOPK_GEMM) {
       const int g = n_launch++;
       int rc = fill_problem(L.prob[g], q.rows16, q.ld_rows16, q.cols16, q.ld_cols16, q.n_rows, q.n_cols, D, fmt,
-                            plans[p], item_base);
+                            plans[p], item_base, bk);
       if (rc != LECCR_OK) return rc;
       item_base += plans[p].row_blocks * plans[p].n_chunks;
       // every owner of a row (column chunks of this call, earlier calls, the other warpgroup) cooperates
       // through a shared per-row threshold
       if (o.sub_total > 1 || two) EP.row_thr[g] = row_thr;
+      if (two) EP.row_h8[g] = row_thr + q.n_rows;
       EP.out_val[g] = cand_val[p];
       EP.out_idx[g] = cand_idx[p];
       EP.out_cnt[g] = cand_cnt[p];
@@ -582,9 +599,9 @@ static int topk_core(const leccr_topk_problem* probs, const leccr_topk_stream* s
   if (n_launch > 0) {
     prof_mark("topk:begin", stream);
     if (two) {
-      TopK2::Params EP2;
+      TopK2D::Params EP2;
       memcpy(&EP2, &EP, sizeof(EP2));
-      rc = launch_gemm<TopK2>(L, EP2, stream);
+      rc = launch_gemm<TopK2D, kBK2>(L, EP2, stream);
     } else if (EP.dense == 1 && EP.debug_mode == 0 && EP.debug_counters == nullptr) {
       TopK1D::Params EPD;
       static_assert(sizeof(TopK1D::Params) == sizeof(TopK1::Params), "parameter layouts must agree");
@@ -635,6 +652,7 @@ static int topk_core(const leccr_topk_problem* probs, const leccr_topk_stream* s
     if (slots <= 2) topk_finalize_kernel<2><<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
     else if (slots <= 4) topk_finalize_kernel<4><<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
     else if (slots <= 8) topk_finalize_kernel<8><<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
+    else if (slots <= 16) topk_finalize_kernel<16><<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
     else topk_finalize_kernel<kMaxSlots><<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
     LAUNCH_CHECK("topk_finalize_kernel");
     prof_mark("topk:finalize", stream);
@@ -680,16 +698,17 @@ int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
     return LECCR_ERR_WORKSPACE;
   leccr_topk_stream so[2];
   memset(so, 0, sizeof(so));
+  const bool two = topk_two_wgs_allowed() && topk_dense(plans, n_prob, nullptr);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   for (int p = 0; p < n_prob; ++p) {
     so[p].phases = LECCR_TOPK_INIT | LECCR_TOPK_GEMM | LECCR_TOPK_FINALIZE;
     so[p].sub_begin = 0;
     so[p].sub_count = so[p].sub_total = plans[p].n_chunks;
     so[p].workspace = ws;
-    so[p].workspace_bytes = topk_ws_bytes(probs[p].n_rows, plans[p].n_chunks);
+    so[p].workspace_bytes = topk_ws_bytes(probs[p].n_rows, plans[p].n_chunks, two);
     ws += so[p].workspace_bytes;
   }
-  return topk_core(probs, so, plans, n_prob, D, fmt, k, stream);
+  return topk_core(probs, so, plans, n_prob, D, fmt, k, two ? 1 : 0, stream);
 }
 
 int leccr_sim_topk_stream(const leccr_topk_problem* probs, const leccr_topk_stream* streams, int n_prob, int D,
@@ -712,7 +731,14 @@ int leccr_sim_topk_stream(const leccr_topk_problem* probs, const leccr_topk_stre
   }
   int rc = leccr_check_device();
   if (rc != LECCR_OK) return rc;
-  return topk_core(probs, streams, plans, n_prob, D, fmt, k, stream);
+  // A streamed problem's lists keep one shape from INIT to FINALIZE: the two-warpgroup dense shape, which
+  // requires every window's column chunks to be short (<= 32 tiles): choose sub_count accordingly.
+  const bool two = topk_two_wgs_allowed();
+  if (two) {
+    for (int p = 0; p < n_prob; ++p)
+      if ((streams[p].phases & LECCR_TOPK_GEMM) && plans[p].tiles_per_chunk > 32) return LECCR_ERR_ARG;
+  }
+  return topk_core(probs, streams, plans, n_prob, D, fmt, k, two ? 1 : 0, stream);
 }
 
 // ------------------------------------------------------------------------------------ InfoNCE

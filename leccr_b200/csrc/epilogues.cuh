@@ -20,8 +20,8 @@ constexpr float kLn2 = 0.6931471805599453f;
 // the next chunk in flight while the current one is processed.  f(v, col, n_valid) must be
 // warp-uniform in its use of collectives.  n_limit: first column index that does not exist.
 template <class F>
-__device__ __forceinline__ void for_each_chunk(uint32_t taddr, int col0, int n_limit, F&& f) {
-  const int nch = min(BN / 32, (n_limit - col0 + 31) / 32);  // warp-uniform
+__device__ __forceinline__ void for_each_chunk(uint32_t taddr, int col0, int n_limit, F&& f, int max_chunks = BN / 32) {
+  const int nch = min(max_chunks, (n_limit - col0 + 31) / 32);  // warp-uniform
   if (nch <= 0) return;
   float va[32], vb[32];
   tmem_ld_32x32(taddr, va);
@@ -59,6 +59,7 @@ struct EpiStore {
     long long split_stride[2];  // elements between split-K partial planes (0 when not split)
   };
   static constexpr int kWGs = 2;
+  static constexpr bool kSplitCols = false;
   static constexpr int kTileLd = 33;
   static constexpr int kSmemBytes = 4 * 32 * kTileLd * 4;
   struct State {};
@@ -145,8 +146,8 @@ __device__ __forceinline__ void top16_of_two(float* a, const float* b, bool reso
   if (resort) bitonic_merge_desc<16>(a);
 }
 
-// Two shapes: <16, 64, 1> one warpgroup with 64-entry lists, <16, 32, 2> two warpgroups (alternate
-// tiles) with 32-entry lists; in both the lists take 66 KB of shared memory.  The two threads that own
+// Shapes: <16, 64, 1> one warpgroup with 64-entry lists (66 KB), <16, 64, 2> two warpgroups (alternate tiles),
+// each with its own 64-entry lists (133 KB, beside a pipeline of half-depth stages).  The two threads that own
 // the same row (and the CTAs that own other column chunks of it) cooperate through row_thr.
 // MODE 0: the filter / dense choice is a run-time parameter (Params::dense); MODE 1: always dense, the
 // filter code is not even compiled in (half the instruction footprint: the single epilogue warp per
@@ -154,6 +155,7 @@ __device__ __forceinline__ void top16_of_two(float* a, const float* b, bool reso
 template <int KP, int C_, int WGS, int MODE = 0>
 struct EpiTopK {
   static constexpr int kWGs = WGS;
+  static constexpr bool kSplitCols = WGS > 1;  // two warpgroups: each takes half the columns of every tile
   static constexpr int C = C_;           // list capacity
   static constexpr int ES = 8;           // bytes per list entry: (score, column) interleaved so an append is ONE 64-bit store
   static constexpr int LDSW = 2 * C + 2; // row pitch in words (even: 8-byte aligned entries; 64-bit per-thread accesses conflict-free)
@@ -172,6 +174,11 @@ struct EpiTopK {
     int sub_base[2];    // first list slot this launch writes (streamed evaluation: one column window per call)
     int col_base[2];    // global index of the launch's first column (added to the stored column indices)
     unsigned* row_thr[2];  // [n_rows] shared per-row threshold keys (zeroed per launch), or null
+    unsigned* row_h8[2];   // [n_rows][2] (two warpgroups only) key of the 8th best score seen by ANY list of
+                           // warpgroup 0 / 1 for the row.  Lists of different warpgroups hold disjoint columns,
+                           // so min(h8[0], h8[1]) is a valid threshold for the row (8 + 8 scores reach it): each
+                           // warpgroup filters with (nearly) the 16th best of the UNION instead of the 16th
+                           // best of its own half (measured: appends per row 441 -> see profiles/README.md)
     int debug_mode;     // measurement aid: 1 = threshold +inf (filter only), 2 = skip the tile entirely
     unsigned long long* debug_counters;  // measurement aid: [chunks, hit chunks, hit groups, shrink rounds, appends]
     int trig;           // a shrink round starts when some row of the warp holds more than this (<= TRIG)
@@ -189,6 +196,8 @@ struct EpiTopK {
     unsigned dc[5];   // debug counters (per thread; lane 0's are warp-level events)
     int dense_tiles;  // warp-uniform: upcoming tiles to run without the filter (see Params::dense)
     unsigned pre_key; // shared threshold key fetched while waiting for the accumulator (see prefetch)
+    unsigned pre_h8;  // the other warpgroup's 8th-best key, fetched alongside
+    unsigned own_h8;  // this list's 8th-best key (after its last shrink)
   };
   static constexpr int DTRIG = C - 16;   // dense mode appends 16 columns between checks
 
@@ -199,6 +208,8 @@ struct EpiTopK {
     for (int i = 0; i < 5; ++i) st.dc[i] = 0;
     st.dense_tiles = (MODE == 0 && P.dense == 2) ? 4 : 0;
     st.pre_key = 0u;
+    st.pre_h8 = 0u;
+    st.own_h8 = 0u;
     st.vb = smem_u32(c.smem) + static_cast<uint32_t>(c.et) * LDSW * 4;
     st.ib = st.vb + kIdxOff;
   }
@@ -223,7 +234,9 @@ struct EpiTopK {
   // unless scores tie.  (A cheaper bound -- the minimum of 16 strided quad maxima -- keeps 36 of 64
   // on average: the threshold then sits at the 36th best and twice as many later scores pass it.)
   // Ties that leave the list too full fall through to the bisection shrink.
-  __device__ __noinline__ static unsigned long long quad_shrink(float thr_in, int n, uint32_t vb, uint32_t ib) {
+  // h8 (optional, global): receives atomicMax of the key of this list's 8th best score (see Params::row_h8).
+  __device__ __noinline__ static unsigned long long quad_shrink(float thr_in, int n, uint32_t vb, uint32_t ib,
+                                                               unsigned* h8 = nullptr) {
     float x[C];
 #pragma unroll
     for (int s = 0; s < C; ++s) {
@@ -240,9 +253,16 @@ struct EpiTopK {
     } else {
       top16_of_two(x, x + 16, false);
     }
-    float tau = x[0];
+    float tau;
+    if (WGS > 1) {
+      bitonic_merge_desc<16>(x);  // top16_of_two leaves a bitonic sequence: one merge sorts it
+      tau = x[15];
+      if (h8 != nullptr && x[7] > -CUDART_INF_F) atomicMax(h8, f32_key(x[7]));
+    } else {
+      tau = x[0];
 #pragma unroll
-    for (int k = 1; k < 16; ++k) tau = fminf(tau, x[k]);
+      for (int k = 1; k < 16; ++k) tau = fminf(tau, x[k]);
+    }
     // an adopted (shared) threshold may already exceed tau: then everything below it is dead too
     const float te = fmaxf(tau, thr_in);
     int j = 0;
@@ -323,6 +343,11 @@ struct EpiTopK {
   __device__ static void prefetch(State& st, const Params& P, const ItemCtx& c) {
     if (P.row_thr[c.p] != nullptr && c.row < c.n_rows)
       st.pre_key = *reinterpret_cast<volatile unsigned*>(P.row_thr[c.p] + c.row);
+    if (WGS > 1 && P.row_h8[c.p] != nullptr && c.row < c.n_rows) {
+      const volatile unsigned* h = P.row_h8[c.p] + 2 * static_cast<long long>(c.row);
+      st.pre_h8 = h[c.wg ^ 1];
+      st.own_h8 = max(st.own_h8, h[c.wg]);  // other column chunks of the row publish here too
+    }
   }
 
   __device__ static void tile(State& st, const Params& P, const ItemCtx& c, uint32_t taddr, int col0) {
@@ -332,11 +357,17 @@ struct EpiTopK {
     // that large) is valid for every chunk: adopt the best one published so far.  Stale reads are fine.
     unsigned* shared_thr = (P.row_thr[c.p] != nullptr && c.row < c.n_rows) ? P.row_thr[c.p] + c.row : nullptr;
     if (st.pre_key > f32_key(st.thr)) st.thr = key_f32(st.pre_key);  // fetched by prefetch() during the wait
+    if (WGS > 1) {
+      const unsigned u = min(st.own_h8, st.pre_h8);  // 8 scores here + 8 scores there reach this key
+      if (u > f32_key(st.thr)) st.thr = key_f32(u);
+    }
+    unsigned* my_h8 = (WGS > 1 && P.row_h8[c.p] != nullptr && c.row < c.n_rows)
+                          ? P.row_h8[c.p] + 2 * static_cast<long long>(c.row) + c.wg : nullptr;
     const bool dense = MODE == 1 || P.dense == 1 || st.dense_tiles > 0;  // warp-uniform
     if (st.dense_tiles > 0) --st.dense_tiles;
     if (dense && __any_sync(0xffffffffu, st.cnt > DTRIG)) {  // the dense path appends up to 16 between checks
       if (st.cnt > JOIN) {
-        const unsigned long long r = quad_shrink(st.thr, st.cnt, st.vb, st.ib);
+        const unsigned long long r = quad_shrink(st.thr, st.cnt, st.vb, st.ib, my_h8);
         st.thr = __uint_as_float(static_cast<unsigned>(r >> 32));
         st.cnt = static_cast<int>(r & 0xffffffffu);
         if (shared_thr != nullptr) atomicMax(shared_thr, f32_key(st.thr));
@@ -366,7 +397,7 @@ struct EpiTopK {
           if (__any_sync(0xffffffffu, cnt > DTRIG)) {
             ++st.dc[3];
             if (cnt > JOIN) {
-              const unsigned long long r = quad_shrink(st.thr, cnt, st.vb, st.ib);
+              const unsigned long long r = quad_shrink(st.thr, cnt, st.vb, st.ib, my_h8);
               st.thr = __uint_as_float(static_cast<unsigned>(r >> 32));
               st.cnt = static_cast<int>(r & 0xffffffffu);
               if (shared_thr != nullptr) atomicMax(shared_thr, f32_key(st.thr));
@@ -407,7 +438,7 @@ struct EpiTopK {
           if (__any_sync(0xffffffffu, cnt > P.trig)) {
             ++st.dc[3];
             if (cnt > JOIN) {
-              const unsigned long long r = quad_shrink(st.thr, cnt, st.vb, st.ib);
+              const unsigned long long r = quad_shrink(st.thr, cnt, st.vb, st.ib, my_h8);
               st.thr = __uint_as_float(static_cast<unsigned>(r >> 32));
               st.cnt = static_cast<int>(r & 0xffffffffu);
               if (shared_thr != nullptr) atomicMax(shared_thr, f32_key(st.thr));
@@ -415,7 +446,7 @@ struct EpiTopK {
           }
         }
       }
-    });
+    }, BN / 32 / kWGs);
     if (MODE == 0 && P.dense == 2 && hit_chunks >= 6) st.dense_tiles = 4;
   }
 
@@ -471,6 +502,7 @@ struct EpiLse {
     int n_sub[2];                  // partials per row: n_chunks * kWGs
   };
   static constexpr int kWGs = 2;
+  static constexpr bool kSplitCols = false;
   static constexpr int kSmemBytes = 2 * BN * 8;
   struct State {
     float m, l, w, pz, cnt, sc;
@@ -584,6 +616,7 @@ struct EpiGrad {
     int fmt;                    // 0 fp16, 1 bf16
   };
   static constexpr int kWGs = 2;
+  static constexpr bool kSplitCols = false;
   static constexpr int kBufBytes = BN * 16;  // idx (8) + lse (4) + rcnt (4) per column
   static constexpr int kSmemBytes = 2 * kBufBytes;
   struct State {

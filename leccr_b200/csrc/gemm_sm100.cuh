@@ -6,8 +6,9 @@
 // One persistent CTA per SM.  Warp 0 feeds shared memory with TMA (128-byte swizzle), warp 1
 // issues tcgen05.mma (128 x 256 x 16, fp32 accumulators in TMEM, two 256-column buffers so the
 // epilogue of tile t overlaps the MMAs of tile t+1), the remaining warps are the epilogue: one or
-// two warpgroups (Epi::kWGs); with two, warpgroup g drains the tiles whose TMEM buffer is g, so a
-// single warp per scheduler never has to keep pace with the tensor core alone.  Epilogue thread
+// two warpgroups (Epi::kWGs); with two, either warpgroup g drains the tiles whose TMEM buffer is g
+// (kSplitCols false) or both drain every tile, half its columns each (kSplitCols true: the next tile's
+// MMAs still overlap), so a single warp per scheduler never has to keep pace with the tensor core alone.  Epilogue thread
 // <-> one row of the tile (TMEM lane), so every per-row reduction the reference performs
 // (top-k, log-sum-exp, min/max, label sums) is thread-local and the N x M matrix never has to
 // exist in HBM.  The epilogue is a policy class (see epilogues.cuh).
@@ -29,6 +30,16 @@ constexpr int kAStageBytes = BM * BK * 2;
 constexpr int kBStageBytes = BN * BK * 2;
 constexpr int kStageBytes = kAStageBytes + kBStageBytes;
 constexpr int kTmemCols = 512;
+// The K depth of a pipeline stage is a kernel parameter: 64 (one 128-byte swizzle atom per row, the default)
+// or 32 (64-byte swizzle): half-size stages leave room for a second epilogue warpgroup's shared memory.
+template <int kBK>
+struct StageGeom {
+  static_assert(kBK == 64 || kBK == 32, "stage depth is one 128-byte or one 64-byte swizzle row");
+  static constexpr int kA = BM * kBK * 2;
+  static constexpr int kB = BN * kBK * 2;
+  static constexpr int kBytes = kA + kB;
+  static constexpr int kAlign = kBK == 64 ? 1024 : 512;  // swizzle atom: 8 rows x row bytes
+};
 
 struct SimProblem {
   CUtensorMap tm_rows;  // box {BK, BM}
@@ -91,13 +102,16 @@ __device__ __forceinline__ void decode_item(const SimLaunch& L, int item, int& p
   }
 }
 
-template <class Epi, int kStages>
+template <class Epi, int kStages, int kBK = BK>
 __global__ void __launch_bounds__(gemm_threads(Epi::kWGs), 1)
 sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typename Epi::Params EP) {
   extern __shared__ uint8_t smem_raw[];
-  // 128-byte swizzle atoms need 1024-byte alignment.
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  using SG = StageGeom<kBK>;
+  constexpr int kStageBytes = SG::kBytes;
+  constexpr int kAStageBytes = SG::kA;
+  // swizzle atoms need 1024-byte (128 B rows) / 512-byte (64 B rows) alignment.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + (SG::kAlign - 1)) &
+                                             ~static_cast<uintptr_t>(SG::kAlign - 1));
   uint8_t* stage_base = smem;
   constexpr int kWGs = Epi::kWGs;
   uint8_t* epi_smem = smem + kStages * kStageBytes;
@@ -122,7 +136,8 @@ sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typ
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], kEpiThreads);
+      // split-column policies: both warpgroups drain every tile (half the columns each)
+      mbar_init(&tempty_bar[b], kEpiThreads * (Epi::kSplitCols ? Epi::kWGs : 1));
     }
     fence_barrier_init();
   }
@@ -151,8 +166,8 @@ sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typ
             uint8_t* sa = stage_base + stage * kStageBytes;
             uint8_t* sb = sa + kAStageBytes;
             mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-            tma_load_2d(sa, tmr, &full_bar[stage], kc * BK, rb * BM);
-            tma_load_2d(sb, tmc, &full_bar[stage], kc * BK, ct * BN);
+            tma_load_2d(sa, tmr, &full_bar[stage], kc * kBK, rb * BM);
+            tma_load_2d(sb, tmc, &full_bar[stage], kc * kBK, ct * BN);
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1u;
@@ -181,10 +196,10 @@ sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typ
             mbar_wait(&full_bar[stage], phase, 300 + stage);
             tc_fence_after();
             const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
-            const uint64_t adesc = make_sw128_kmajor_desc(sa);
-            const uint64_t bdesc = make_sw128_kmajor_desc(sa + kAStageBytes);
+            const uint64_t adesc = make_kmajor_desc<kBK>(sa);
+            const uint64_t bdesc = make_kmajor_desc<kBK>(sa + kAStageBytes);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
+            for (int k = 0; k < kBK / UMMA_K; ++k) {
               // +32 bytes per K step inside the swizzle atom == +2 in the (addr >> 4) field
               umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kc > kc0 || k > 0) ? 1u : 0u);
             }
@@ -217,15 +232,16 @@ sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typ
       c.sub = c.cc * kWGs + c.wg;
       Epi::begin(st, EP, c);
       for (int ct = ct0; ct < ct1; ++ct, ++tile_n) {
-        if (kWGs == 2 && (tile_n & 1u) != static_cast<uint32_t>(c.wg)) continue;
+        if (!Epi::kSplitCols && kWGs == 2 && (tile_n & 1u) != static_cast<uint32_t>(c.wg)) continue;
         const uint32_t buf = tile_n & 1u;
         const uint32_t use = tile_n >> 1;
         Epi::prefetch(st, EP, c);  // loads whose latency should hide behind the wait
         mbar_wait(&tfull_bar[buf], use & 1u, 400 + buf, 32);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + buf * BN + (static_cast<uint32_t>(c.warp_q * 32) << 16);
+        const int col_off = Epi::kSplitCols ? c.wg * (BN / kWGs) : 0;  // this warpgroup's columns of the tile
+        const uint32_t taddr = tmem_base + buf * BN + col_off + (static_cast<uint32_t>(c.warp_q * 32) << 16);
         c.tile_n = tile_n;
-        Epi::tile(st, EP, c, taddr, ct * BN);
+        Epi::tile(st, EP, c, taddr, ct * BN + col_off);
         tc_fence_before();
         mbar_arrive(&tempty_bar[buf]);
       }
@@ -238,9 +254,9 @@ sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typ
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-template <class Epi, int kStages>
+template <class Epi, int kStages, int kBK = BK>
 constexpr size_t sim_gemm_smem_bytes() {
-  return 1024 + static_cast<size_t>(kStages) * kStageBytes + Epi::kWGs * Epi::kSmemBytes +
+  return StageGeom<kBK>::kAlign + static_cast<size_t>(kStages) * StageGeom<kBK>::kBytes + Epi::kWGs * Epi::kSmemBytes +
          (2 * kStages + 4) * 8 + 16;
 }
 

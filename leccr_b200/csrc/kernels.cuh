@@ -502,7 +502,7 @@ __global__ void infonce_finalize_kernel(const FinalizeLseParams P) {
 //      than kRankCap definitely-greater items are known) the row is flagged for exact_rank_rows.
 // --------------------------------------------------------------------------------
 constexpr int kRankCap = 10;   // Recall@1/5/10 only ever asks whether rank < 10
-constexpr int kMaxSlots = 16;   // candidate slots per lane in topk_finalize: n_lists * (list_cap / 32) <= 16
+constexpr int kMaxSlots = 32;   // candidate slots per lane in topk_finalize: n_lists * (list_cap / 32) <= 32
 constexpr int kFinalizeWarps = 8;
 
 struct TopkFinalizeParams {

@@ -158,6 +158,20 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   return d;
 }
 
+// The same for rows of kRowBytes = 2 * kBK bytes: 128 (SWIZZLE_128B, 1024-byte atoms) or 64 (SWIZZLE_64B,
+// layout type 4, 8-row x 64 B atoms 512 B apart).  A K step of 16 elements is +32 bytes inside the row either way.
+template <int kBK>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
+  if (kBK == 64) return make_sw128_kmajor_desc(smem_addr);
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;  // SWIZZLE_64B
+  return d;
+}
+
 // Instruction descriptor for kind::f16, fp32 accumulate, both operands K-major.
 // fmt: 0 = fp16, 1 = bf16.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int fmt, int m, int n) {
