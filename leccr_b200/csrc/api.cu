@@ -166,16 +166,16 @@ void prof_dump() {
 }
 
 // As many pipeline stages as fit beside the epilogue's own shared memory (227 KB per CTA).
-template <class Epi, int kBK = BK>
+template <class Epi, int kBK = BK, bool kARes = false>
 constexpr int stages_for() {
-  return sim_gemm_smem_bytes<Epi, 4, kBK>() <= 232448 ? 4 : 3;
+  return sim_gemm_smem_bytes<Epi, 4, kBK, kARes>() <= 232448 ? 4 : 3;
 }
 
-template <class Epi, int kBK = BK>
+template <class Epi, int kBK = BK, bool kARes = false>
 int launch_gemm(const SimLaunch& L, const typename Epi::Params& EP, cudaStream_t stream) {
-  constexpr int kStages = stages_for<Epi, kBK>();
-  auto kern = sim_gemm_kernel<Epi, kStages, kBK>;
-  constexpr size_t smem = sim_gemm_smem_bytes<Epi, kStages, kBK>();
+  constexpr int kStages = stages_for<Epi, kBK, kARes>();
+  auto kern = sim_gemm_kernel<Epi, kStages, kBK, kARes>;
+  constexpr size_t smem = sim_gemm_smem_bytes<Epi, kStages, kBK, kARes>();
   static_assert(smem <= 232448, "exceeds the 227 KB shared memory limit of sm_100");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -458,6 +458,14 @@ static bool topk_two_wgs_allowed() {
   }
   return v == 1;
 }
+static bool topk_a_resident() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LECCR_TOPK_ARES");  // measurement aid: 0 streams the row block with the gallery
+    v = (e != nullptr && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
 // Dense mode (and with it the two-warpgroup shape) is chosen when every tensor-core problem of the launch has
 // short column chunks; decided from the plans alone so that workspace sizing and launch agree.
 static bool topk_dense(const Plan* plans, int n_prob, const int* gemm_mask) {
@@ -607,6 +615,8 @@ static int topk_core(const leccr_topk_problem* probs, const leccr_topk_stream* s
       static_assert(sizeof(TopK1D::Params) == sizeof(TopK1::Params), "parameter layouts must agree");
       memcpy(&EPD, &EP, sizeof(EPD));
       rc = launch_gemm<TopK1D>(L, EPD, stream);
+    } else if (L.k_chunks <= kAResChunks && topk_a_resident()) {
+      rc = launch_gemm<TopK1, BK, true>(L, EP, stream);  // row block resident, only the gallery streams
     } else {
       rc = launch_gemm<TopK1>(L, EP, stream);
     }

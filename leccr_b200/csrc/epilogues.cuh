@@ -407,18 +407,25 @@ struct EpiTopK {
         return;
       }
       if (MODE == 1) return;  // compile-time: nothing below exists in the dense-only kernel
+      // level 1: one maximum over the whole chunk (3-input FMNMX3 tree, ~16 instructions) and one vote;
+      // on long rows five chunks out of six end here
+      float cm[8];
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        cm[g] = fmaxf(fmaxf(v[4 * g], v[4 * g + 1]), fmaxf(v[4 * g + 2], v[4 * g + 3]));
+      const float cmax = fmaxf(fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])),
+                               fmaxf(fmaxf(cm[4], cm[5]), fmaxf(cm[6], cm[7])));
+      ++st.dc[0];
+      if (!__any_sync(0xffffffffu, cmax > st.thr)) return;  // warp-uniform
+      // level 2: which of the four 8-column groups hold a candidate for some row
       float gm[4];
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
-        gm[g] = fmaxf(fmaxf(fmaxf(v[8 * g], v[8 * g + 1]), fmaxf(v[8 * g + 2], v[8 * g + 3])),
-                      fmaxf(fmaxf(v[8 * g + 4], v[8 * g + 5]), fmaxf(v[8 * g + 6], v[8 * g + 7])));
+      for (int g = 0; g < 4; ++g) gm[g] = fmaxf(cm[2 * g], cm[2 * g + 1]);
       // ONE warp collective decides the whole chunk: which of the four 8-column groups contain a
       // candidate for some row (votes and branches are the latency that bounds this epilogue)
       unsigned hm = (gm[0] > st.thr ? 1u : 0u) | (gm[1] > st.thr ? 2u : 0u) | (gm[2] > st.thr ? 4u : 0u) |
                     (gm[3] > st.thr ? 8u : 0u);
       hm = __reduce_or_sync(0xffffffffu, hm);
-      ++st.dc[0];
-      if (hm == 0u) return;  // warp-uniform; on long rows almost every chunk ends here
       ++st.dc[1];
       ++hit_chunks;
 #pragma unroll
@@ -426,13 +433,11 @@ struct EpiTopK {
         if (hm & (1u << g)) {  // warp-uniform
           ++st.dc[2];
           const float thr = st.thr;
-          int cnt = st.cnt;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {  // predicated appends: straight-line code beats any branch here
-            const float x = v[8 * g + e];
-            sts_pair_if_gt(x, thr, st.vb + cnt * ES, st.ib + cnt * ES, col + 8 * g + e);
-            cnt += (x > thr) ? 1 : 0;
-          }
+          // predicated appends, four at a time: straight-line code beats any branch here
+          uint32_t cur = st.vb + st.cnt * ES;
+          cur = append4_if_gt(v[8 * g], v[8 * g + 1], v[8 * g + 2], v[8 * g + 3], thr, cur, col + 8 * g);
+          cur = append4_if_gt(v[8 * g + 4], v[8 * g + 5], v[8 * g + 6], v[8 * g + 7], thr, cur, col + 8 * g + 4);
+          const int cnt = static_cast<int>(cur - st.vb) / ES;
           st.dc[4] += cnt - st.cnt;
           st.cnt = cnt;
           if (__any_sync(0xffffffffu, cnt > P.trig)) {

@@ -102,25 +102,36 @@ __device__ __forceinline__ void decode_item(const SimLaunch& L, int item, int& p
   }
 }
 
-template <class Epi, int kStages, int kBK = BK>
+// kARes: the row-block operand of a work item (all of K, at most kAResChunks stage-deep chunks) stays
+// resident in shared memory for the item's whole column chunk and only the column operand streams through
+// the stages: a third less L2 -> SM traffic per tile (the mainloop's limit when the epilogue is cheap).
+// Chunk kc of the next item's row block is loaded as soon as the last tile of the current item has consumed
+// chunk kc (a_empty / a_full barriers per chunk), so items follow each other without draining the pipeline.
+constexpr int kAResChunks = 4;
+
+template <class Epi, int kStages, int kBK = BK, bool kARes = false>
 __global__ void __launch_bounds__(gemm_threads(Epi::kWGs), 1)
 sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typename Epi::Params EP) {
   extern __shared__ uint8_t smem_raw[];
   using SG = StageGeom<kBK>;
-  constexpr int kStageBytes = SG::kBytes;
   constexpr int kAStageBytes = SG::kA;
+  constexpr int kStageBytes = kARes ? SG::kB : SG::kBytes;   // resident A: the stages hold B only
+  constexpr int kAResBytes = kARes ? kAResChunks * SG::kA : 0;
   // swizzle atoms need 1024-byte (128 B rows) / 512-byte (64 B rows) alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + (SG::kAlign - 1)) &
                                              ~static_cast<uintptr_t>(SG::kAlign - 1));
-  uint8_t* stage_base = smem;
+  uint8_t* a_res = smem;                       // resident row-block chunks (kARes)
+  uint8_t* stage_base = smem + kAResBytes;
   constexpr int kWGs = Epi::kWGs;
-  uint8_t* epi_smem = smem + kStages * kStageBytes;
+  uint8_t* epi_smem = stage_base + kStages * kStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + kWGs * Epi::kSmemBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tfull_bar = bars + 2 * kStages;
   uint64_t* tempty_bar = bars + 2 * kStages + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* afull_bar = bars + 2 * kStages + 4;                 // kARes only
+  uint64_t* aempty_bar = bars + 2 * kStages + 4 + kAResChunks;  // kARes only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4 + (kARes ? 2 * kAResChunks : 0));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -139,6 +150,12 @@ sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typ
       // split-column policies: both warpgroups drain every tile (half the columns each)
       mbar_init(&tempty_bar[b], kEpiThreads * (Epi::kSplitCols ? Epi::kWGs : 1));
     }
+    if (kARes) {
+      for (int kc = 0; kc < kAResChunks; ++kc) {
+        mbar_init(&afull_bar[kc], 1);
+        mbar_init(&aempty_bar[kc], 1);
+      }
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -155,18 +172,24 @@ sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typ
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < L.n_items; item += gridDim.x) {
+      uint32_t item_n = 0;
+      for (int item = blockIdx.x; item < L.n_items; item += gridDim.x, ++item_n) {
         int p, rb, ct0, ct1, cc, kc0, kc1;
         decode_item(L, item, p, rb, ct0, ct1, cc, kc0, kc1);
         const CUtensorMap* tmr = &L.prob[p].tm_rows;
         const CUtensorMap* tmc = &L.prob[p].tm_cols;
         for (int ct = ct0; ct < ct1; ++ct) {
           for (int kc = kc0; kc < kc1; ++kc) {
+            if (kARes && ct == ct0) {  // this item's row-block chunk kc, once the previous item is done with the slot
+              if (item_n > 0) mbar_wait(&aempty_bar[kc], (item_n - 1) & 1u, 500 + kc, 64);
+              mbar_arrive_expect_tx(&afull_bar[kc], kAStageBytes);
+              tma_load_2d(a_res + kc * kAStageBytes, tmr, &afull_bar[kc], kc * kBK, rb * BM);
+            }
             mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + stage, 64);
             uint8_t* sa = stage_base + stage * kStageBytes;
-            uint8_t* sb = sa + kAStageBytes;
+            uint8_t* sb = kARes ? sa : sa + kAStageBytes;
             mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-            tma_load_2d(sa, tmr, &full_bar[stage], kc * kBK, rb * BM);
+            if (!kARes) tma_load_2d(sa, tmr, &full_bar[stage], kc * kBK, rb * BM);
             tma_load_2d(sb, tmc, &full_bar[stage], kc * kBK, ct * BN);
             if (++stage == kStages) {
               stage = 0;
@@ -183,7 +206,8 @@ sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typ
       int stage = 0;
       uint32_t phase = 0;
       uint32_t tile_n = 0;
-      for (int item = blockIdx.x; item < L.n_items; item += gridDim.x) {
+      uint32_t item_n = 0;
+      for (int item = blockIdx.x; item < L.n_items; item += gridDim.x, ++item_n) {
         int p, rb, ct0, ct1, cc, kc0, kc1;
         decode_item(L, item, p, rb, ct0, ct1, cc, kc0, kc1);
         for (int ct = ct0; ct < ct1; ++ct, ++tile_n) {
@@ -193,17 +217,19 @@ sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typ
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * BN;
           for (int kc = kc0; kc < kc1; ++kc) {
+            if (kARes && ct == ct0) mbar_wait(&afull_bar[kc], item_n & 1u, 600 + kc);
             mbar_wait(&full_bar[stage], phase, 300 + stage);
             tc_fence_after();
             const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
-            const uint64_t adesc = make_kmajor_desc<kBK>(sa);
-            const uint64_t bdesc = make_kmajor_desc<kBK>(sa + kAStageBytes);
+            const uint64_t adesc = make_kmajor_desc<kBK>(kARes ? smem_u32(a_res + kc * kAStageBytes) : sa);
+            const uint64_t bdesc = make_kmajor_desc<kBK>(kARes ? sa : sa + kAStageBytes);
 #pragma unroll
             for (int k = 0; k < kBK / UMMA_K; ++k) {
               // +32 bytes per K step inside the swizzle atom == +2 in the (addr >> 4) field
               umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kc > kc0 || k > 0) ? 1u : 0u);
             }
             umma_commit(&empty_bar[stage]);  // stage reusable once these MMAs have read it
+            if (kARes && ct == ct1 - 1) umma_commit(&aempty_bar[kc]);  // the item's last use of row chunk kc
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1u;
@@ -254,10 +280,12 @@ sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typ
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-template <class Epi, int kStages, int kBK = BK>
+template <class Epi, int kStages, int kBK = BK, bool kARes = false>
 constexpr size_t sim_gemm_smem_bytes() {
-  return StageGeom<kBK>::kAlign + static_cast<size_t>(kStages) * StageGeom<kBK>::kBytes + Epi::kWGs * Epi::kSmemBytes +
-         (2 * kStages + 4) * 8 + 16;
+  return StageGeom<kBK>::kAlign +
+         (kARes ? static_cast<size_t>(kAResChunks) * StageGeom<kBK>::kA + static_cast<size_t>(kStages) * StageGeom<kBK>::kB
+                : static_cast<size_t>(kStages) * StageGeom<kBK>::kBytes) +
+         Epi::kWGs * Epi::kSmemBytes + (2 * kStages + 4 + (kARes ? 2 * kAResChunks : 0)) * 8 + 16;
 }
 
 }  // namespace leccr
