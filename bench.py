@@ -147,7 +147,7 @@ def run_reference(args, rank):
     sample = (f"per step: full {N_IMG}x{N_TXT} fp32 score matrix on {threads} threads + np.argsort ranking of "
               f"{int(frac * 100)}% of the rows of each direction on 1 thread (the reference's itm_eval is "
               f"single-threaded); oracle port of the reference CPU path")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -155,7 +155,7 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # ----------------------------------------------------------------------------- B200 path
@@ -291,8 +291,9 @@ def run_ours(args, rank, world, local_rank):
             "sample": f"1 step: full {N_IMG}x{N_TXT} fp32 score matrix on {threads} threads + np.argsort ranking "
                       f"of {int(frac * 100)}% of the rows of each direction on 1 thread (oracle port of "
                       f"image_Retrieval_caption.py:151-163,261-295), {dt:.2f} s"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
+        os.dup2(2, 1)  # teardown chatter stays off stdout
         dist.destroy_process_group()
 
 
@@ -358,6 +359,17 @@ def extras_single_gpu(torch, ops, synth, lib, dev, peak):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """Print the result line on the real stdout."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -369,7 +381,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
+    # stdout carries the one JSON line only: libraries that print to the C-level stdout (NCCL's version banner)
+    # are sent to stderr until the line is ready
+    sys.stdout.flush()
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank)
     else:

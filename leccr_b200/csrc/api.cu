@@ -658,11 +658,10 @@ static int topk_core(const leccr_topk_problem* probs, const leccr_topk_stream* s
     F.flag_list = flag[p] + 4;
     F.gt_score = q.gt_score;
     const unsigned grid = static_cast<unsigned>((q.n_rows + kFinalizeWarps - 1) / kFinalizeWarps);
-    const int slots = F.n_chunks * (cap / 32);
+    const int slots = F.n_chunks;  // one 32-entry slot per list
     if (slots <= 2) topk_finalize_kernel<2><<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
     else if (slots <= 4) topk_finalize_kernel<4><<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
     else if (slots <= 8) topk_finalize_kernel<8><<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
-    else if (slots <= 16) topk_finalize_kernel<16><<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
     else topk_finalize_kernel<kMaxSlots><<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
     LAUNCH_CHECK("topk_finalize_kernel");
     prof_mark("topk:finalize", stream);

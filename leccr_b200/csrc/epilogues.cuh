@@ -455,8 +455,20 @@ struct EpiTopK {
     if (MODE == 0 && P.dense == 2 && hit_chunks >= 6) st.dense_tiles = 4;
   }
 
-  // Dump the raw lists; rows of a warp are written one after another so stores coalesce.
+  // Dump the lists; rows of a warp are written one after another so stores coalesce.  A last shrink round
+  // (only when some row of the warp holds more than 32 entries) leaves every list with at most JOIN <= 32
+  // entries: half the write-out and half the candidate slots topk_finalize has to merge.
   __device__ static void end(State& st, const Params& P, const ItemCtx& c) {
+    __syncwarp();
+    if (__any_sync(0xffffffffu, st.cnt > 32)) {
+      if (st.cnt > JOIN) {
+        unsigned* shared_thr = (P.row_thr[c.p] != nullptr && c.row < c.n_rows) ? P.row_thr[c.p] + c.row : nullptr;
+        const unsigned long long r = quad_shrink(st.thr, st.cnt, st.vb, st.ib);
+        st.thr = __uint_as_float(static_cast<unsigned>(r >> 32));
+        st.cnt = static_cast<int>(r & 0xffffffffu);
+        if (shared_thr != nullptr) atomicMax(shared_thr, f32_key(st.thr));
+      }
+    }
     __syncwarp();
     if (P.debug_counters != nullptr) {
       const unsigned app = __reduce_add_sync(0xffffffffu, st.dc[4]);
@@ -475,9 +487,8 @@ struct EpiTopK {
       const long long o = (static_cast<long long>(row) * nch + P.sub_base[c.p] + c.sub) * C;
       const uint32_t vb = wbase + static_cast<uint32_t>(src) * LDSW * 4;
       const uint32_t ib = vb + kIdxOff;
-#pragma unroll
-      for (int h = 0; h < C / 32; ++h) {
-        const int s = c.lane + 32 * h;
+      {
+        const int s = c.lane;  // cnt_src <= 32 after the final round
         if (s < cnt_src) {
           P.out_val[c.p][o + s] = lds_f32(vb + s * ES);
           P.out_idx[c.p][o + s] = lds_s32(ib + s * ES);

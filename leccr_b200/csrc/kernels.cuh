@@ -502,7 +502,7 @@ __global__ void infonce_finalize_kernel(const FinalizeLseParams P) {
 //      than kRankCap definitely-greater items are known) the row is flagged for exact_rank_rows.
 // --------------------------------------------------------------------------------
 constexpr int kRankCap = 10;   // Recall@1/5/10 only ever asks whether rank < 10
-constexpr int kMaxSlots = 32;   // candidate slots per lane in topk_finalize: n_lists * (list_cap / 32) <= 32
+constexpr int kMaxSlots = 16;   // candidate slots per lane in topk_finalize: one per list (lists leave the epilogue with <= 32 entries)
 constexpr int kFinalizeWarps = 8;
 
 struct TopkFinalizeParams {
@@ -510,7 +510,7 @@ struct TopkFinalizeParams {
   const int* cand_idx;
   const int* cand_cnt;    // [n_rows][n_chunks]
   int n_rows, n_cols, n_chunks, KP, k;
-  int list_cap;           // 32 or 64 (EpiTopK::C)
+  int list_cap;           // stride between lists in entries (EpiTopK::C); the epilogue leaves at most 32 entries in each
   float* topk_val;  // [n_rows][k]
   int* topk_idx;
   // exact recall (all optional; gt_off == nullptr disables)
@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(kFinalizeWarps * 32) topk_finalize_kernel(cons
   const int row = blockIdx.x * kFinalizeWarps + wib;
   if (row >= P.n_rows) return;
   const int KP = P.KP;
-  const int sh = P.list_cap >> 6;             // slots per list and lane: 1 (cap 32) or 2 (cap 64), as a shift
+  const int sh = 0;                           // slots per list and lane, as a shift: lists arrive with <= 32 entries
   const int per_lane = P.n_chunks << sh;
   const long long cbase = static_cast<long long>(row) * P.n_chunks;
   // all loads are issued before any is consumed: list lengths (one lane each), then every slot

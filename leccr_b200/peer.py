@@ -133,10 +133,11 @@ def itc_slot(B: int, D: int, fmt: int, device):
     return pb.table(off), pb.table(off + rows_bytes), pb.flag_table, pb.epoch, pb.buf.data_ptr() + off
 
 
-def merge_topk_peers(val, idx, shard_offset: int, k: int, all_queries: bool = True):
+def merge_topk_peers(val, idx, shard_offset: int, k: int, all_queries: bool = True, offsets=None):
     """Row-partitioned gallery exchange: publish this rank's [Q, k_in] local lists, barrier, then pull + merge.
     Returns (val [Q', k], idx int32 [Q', k] global columns, (q_begin, q_end)) where Q' is all queries
-    (all_queries) or this rank's balanced slice.  None when peer exchange is not available."""
+    (all_queries) or this rank's balanced slice.  offsets: optional list of every rank's shard_offset.
+    None when peer exchange is not available."""
     from .sharding import shard_range
 
     dev = val.device
@@ -152,10 +153,13 @@ def merge_topk_peers(val, idx, shard_offset: int, k: int, all_queries: bool = Tr
     off = pb.slot_offset(slot)
     pb.local(off, (Q, k_in), torch.float32).copy_(val)
     pb.local(off + Q * k_in * 4, (Q, k_in), torch.int32).copy_(idx)
-    offs = torch.tensor([shard_offset], dtype=torch.int64, device=dev)
-    all_offs = torch.empty(world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(all_offs, offs)  # 8 bytes per rank, once per call (host needs them)
-    host_offs = all_offs.cpu().tolist()
+    if offsets is not None:  # every rank's first gallery row, known to the caller (no exchange, no host sync)
+        host_offs = [int(o) for o in offsets]
+    else:
+        offs = torch.tensor([shard_offset], dtype=torch.int64, device=dev)
+        all_offs = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_offs, offs)  # 8 bytes per rank (the host needs them)
+        host_offs = all_offs.cpu().tolist()
     pb.barrier()
     qb, qe = (0, Q) if all_queries else shard_range(Q, rank, world)
     out_v = torch.empty((qe - qb, k), dtype=torch.float32, device=dev)

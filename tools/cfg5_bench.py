@@ -1,0 +1,118 @@
+"""cfg5 (BASELINE.json configs[4]): 1,000,000-item gallery x 100,000 queries, D = 256 bf16, top-10, on N GPUs.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/cfg5_bench.py
+      [--gallery 1000000] [--queries 100000] [--reps 3]
+
+Two decompositions, both timed on the device as the max over ranks:
+  query   : every rank holds the whole gallery (512 MB) and Q / N queries; no exchange at all.
+  gallery : the gallery is row-partitioned (1M / N rows per rank), every rank ranks ALL queries against its
+            shard, publishes its per-query top-10 in peer memory, one barrier, and merges the lists of its
+            Q / N query slice from all ranks in one kernel (leccr_topk_merge_peers).
+Every rank generates the same seeded data (synthetic), a sample of queries is checked against a plain fp32
+matmul + topk of the same bf16 inputs, and rank 0 prints one JSON line per decomposition.
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+from leccr_b200 import ops, peer, sharding, synth
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gallery", type=int, default=1_000_000)
+    ap.add_argument("--queries", type=int, default=100_000)
+    ap.add_argument("--reps", type=int, default=3)
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    try:
+        peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                           "MEASURED_PEAKS.json")))["bf16_tflops"]
+    except Exception:
+        peak = 1590.0
+    G, Q, k = args.gallery, args.queries, 10
+    gal, qry, _ = synth.cfg5_gallery(G, Q, device=dev)
+    flops = 2.0 * G * Q * 256
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ts = []
+        for _ in range(args.reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t = torch.tensor([min(ts)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), out
+
+    def check(val, idx, q0, q1, name):
+        """Sampled queries against fp32 matmul + topk of the same bf16 inputs."""
+        step = max(1, (q1 - q0) // 64)
+        rows = torch.arange(q0, q1, step, device=dev)
+        ref = qry[rows].float() @ gal.float().t()
+        rv, ri = ref.topk(k, dim=1)
+        got_i = idx[rows - q0].long()
+        true_at_got = torch.gather(ref, 1, got_i)
+        # identical up to ties inside the bf16-operand tolerance
+        ok = bool(((rv - true_at_got.sort(dim=1, descending=True).values).abs().max() < 1e-3))
+        same = float((got_i == ri).all(dim=1).float().mean())
+        assert ok, f"{name}: top-k differs from the fp32 reference beyond the tolerance"
+        return same
+
+    Qop, Gop = ops.prep(qry, want_stats=False), ops.prep(gal, want_stats=False)
+    results = []
+    # ---- query sharding: my slice of the queries against the whole gallery
+    qb, qe = sharding.shard_range(Q, rank, world)
+    Qs = Qop.rows(qb, qe)
+    ms, (res,) = timed(lambda: ops.sim_topk([(Qs, Gop, None)], k=k))
+    same = check(res.val, res.idx, qb, qe, "query")
+    results.append(("query", ms, same))
+    # ---- gallery partition: all queries against my shard, merge of my query slice over peer memory
+    if world > 1:
+        gb, ge = sharding.shard_range(G, rank, world)
+        Gs = Gop.rows(gb, ge)
+        offs = [sharding.shard_range(G, r, world)[0] for r in range(world)]
+
+        def gallery_step():
+            (r,) = ops.sim_topk([(Qop, Gs, None)], k=k)
+            m = peer.merge_topk_peers(r.val, r.idx, gb, k, all_queries=False, offsets=offs)
+            if m is None:  # no peer memory: NCCL all-gather + merge of everything
+                v, i = sharding.allgather_topk(r.val, r.idx.long() + gb, k)
+                return v[qb:qe], i[qb:qe].int(), (qb, qe)
+            return m
+
+        ms, (mv, mi, (mb, me)) = timed(gallery_step)
+        same = check(mv, mi, mb, me, "gallery")
+        results.append(("gallery", ms, same))
+    if rank == 0:
+        for name, ms, same in results:
+            print(json.dumps({
+                "workload": f"cfg5 {G} gallery x {Q} queries d256 bf16 top{k}", "decomposition": name, "n_gpus": world,
+                "ms": ms, "queries_per_s": Q / (ms * 1e-3), "tflops_total": flops / ms / 1e9,
+                "frac_of_peak": flops / ms / 1e9 / (peak * world), "peak_tflops_per_gpu": peak,
+                "sampled_rows_identical_to_fp32_topk": same, "timing": "CUDA events, best of reps, max over ranks",
+                "peer_memory": bool(peer._cache.get(("topk", Q, k)) is not None) if name == "gallery" else None}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
