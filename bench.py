@@ -331,6 +331,20 @@ def extras_single_gpu(torch, ops, synth, lib, dev, peak):
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / 20 * 1e3
     flops = 2.0 * 2 * 4096 * 4096 * 256 + 2.0 * 2 * 2 * 512 * 4096 * 256  # fwd both orientations + strips + grads
+    # the reference's CPU path for the same call (oracle port of models/xvlm.py:260-292 + autograd), all host threads
+    import time as _time
+
+    from oracle import oracle as _oracle
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    _oracle.contrastive_loss_and_grads(cb.image, cb.text, cb.temp, cb.idx, rank=0, batch_size=512)
+    cpu_ts = []
+    for _ in range(3):
+        t0 = _time.perf_counter()
+        _oracle.contrastive_loss_and_grads(cb.image, cb.text, cb.temp, cb.idx, rank=0, batch_size=512)
+        cpu_ts.append(_time.perf_counter() - t0)
+    out["contrastive_cpu_baseline"] = {"us_per_step": min(cpu_ts) * 1e6, "cores": os.cpu_count() or 1, "kind": "port",
+                                       "sample": "full cfg3 call, N = 4096, fp32, fwd + autograd bwd, best of 3"}
     out["contrastive_fwd_bwd"] = {"config": "cfg3: global batch 4096 (8 x 512), D=256, idx labels, rank 0's rows",
                                   "us_per_step": us, "tflops": flops / us / 1e6, "frac_of_peak": flops / us / 1e6 / peak,
                                   "includes": "fp32->fp16 cast of 2 x 4096 rows, forward, transposes, backward of 512 local rows"}

@@ -324,7 +324,17 @@ class StreamedEvalPlan:
             fracs = [1.0 / max(1, windows)] * max(1, windows)
         else:
             fracs = [float(f) / sum(windows) for f in windows]  # shrinking windows shorten the un-overlapped tail
-        fracs = fracs[:max(1, 8 // img_subs)]
+        # column chunks of a streamed launch must stay short (<= 32 tiles of 256 columns, the dense two-warpgroup
+        # epilogue): raise the sub-list counts when a window or the image set is longer, within 8 slots per row
+        max_win = max(fracs) * n_txt
+        img_subs = max(img_subs, -(-int(max_win + 255) // 256 // 32))
+        txt_subs = max(txt_subs, -(-((n_img + 255) // 256) // 32))
+        if img_subs * len(fracs) > 8:
+            fracs = [1.0 / max(1, 8 // img_subs)] * max(1, 8 // img_subs)
+            img_subs = max(img_subs, -(-int(max(fracs) * n_txt + 255) // 256 // 32))
+        if img_subs * len(fracs) > 8 or txt_subs > 8:
+            raise N.LeccrError("StreamedEvalPlan handles up to ~65k x 65k evaluation sets; shard larger ones "
+                               "(fused_eval_sharded / topk_gallery_sharded)")
         self.gt = gt if gt is not None else prepare_gt(txt2img, img2txt, n_img, n_txt, self.dev)
         dev = self.dev
         dt16 = torch.float16 if self.fmt == N.FMT_F16 else torch.bfloat16

@@ -49,10 +49,14 @@ class PeerBuffer:
         self.slot_bytes = (nbytes + 255) // 256 * 256
         total = self.FLAG_BYTES + 2 * self.slot_bytes
         group = dist.group.WORLD
-        try:
-            symm_mem.enable_symm_mem_for_group(group.group_name)
-        except Exception:
-            pass  # newer torch enables it implicitly
+        import warnings
+
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")  # deprecated no-op on current torch, required on older ones
+            try:
+                symm_mem.enable_symm_mem_for_group(group.group_name)
+            except Exception:
+                pass
         self.buf = symm_mem.empty(total, dtype=torch.uint8, device=device)
         self.buf.zero_()
         self.hdl = symm_mem.rendezvous(self.buf, group)
