@@ -265,6 +265,30 @@ int leccr_itc_backward(const void* both16, const int64_t* idx_all, int64_t n, in
                        const float* grad_out, float* dA, float* dB, float* dtemp, void* workspace,
                        size_t workspace_bytes, leccr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * leccr_caploss_fwd / leccr_caploss_bwd: caption contrastive loss of the LOCAL batch (no gather).
+ * Replaces: RetrievalModel.get_caption_contrastive_loss  models/model_retrieval_caption.py:145-152
+ * (== models/video_model_retrieval_caption.py:171-178): sim = caption.reshape(n*B, d) @ text.T,
+ * logits = max_n sim / temp, arange labels, symmetric cross entropy; backward = autograd of the same lines
+ * (the max routes each gradient to its arg-max caption query, first index on ties).
+ *   cap16 : [n_cap * B][K] 16-bit caption queries, row a * B + i = query a of sample i
+ *   txt16 : [B][K] 16-bit text features.  Forward: K = 3D split-precision operands (leccr_prep layouts
+ *           X3_ROWS / X3_COLS) so the arg max is the fp32 one; backward: the plain [.][D] halves of the same
+ *           buffers (ld = 3D).
+ *   out   : [2] loss, d loss / d temp;  L: [B][B] fp32 max_n sim;  amax: [B][B] arg max;  stats: [4][B]
+ *           (row / column log-sum-exp in log2 units, row / column E_softmax[z]) -- saved for the backward
+ *   dcap  : [n_cap * B][D], dtxt: [B][D] fp32 (overwritten), dtemp scalar = grad_out * out[1] (may be NULL)
+ * ------------------------------------------------------------------------------------------ */
+size_t leccr_caploss_fwd_workspace(int n_cap, int64_t B);
+int leccr_caploss_fwd(const void* cap16, int64_t ld_cap, const void* txt16, int64_t ld_txt, int n_cap, int64_t B, int K,
+                      int fmt, const float* temp, float* out, float* L, uint8_t* amax, float* stats, void* workspace,
+                      size_t workspace_bytes, leccr_stream_t stream);
+size_t leccr_caploss_bwd_workspace(int n_cap, int64_t B, int D);
+int leccr_caploss_bwd(const float* L, const uint8_t* amax, const float* stats, const void* cap16, int64_t ld_cap,
+                      const void* txt16, int64_t ld_txt, int n_cap, int64_t B, int D, int fmt, const float* temp,
+                      const float* out, const float* grad_out, float* dcap, float* dtxt, float* dtemp, void* workspace,
+                      size_t workspace_bytes, leccr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,7 @@ include/leccr_b200.h).  There is no CPU path: calls raise if the library or a B2
 __version__ = "0.1.0"
 
 from .allgather import AllGather, allgather  # noqa: E402,F401
+from .caption_loss import caption_contrastive_loss, get_caption_contrastive_loss  # noqa: E402,F401
 from .contrastive import contrastive_loss, get_contrastive_loss  # noqa: E402,F401
 from .evaluation import (FusedEvalPlan, StreamedEvalPlan, double_sim_matrix, evaluation_coarse, evaluation_coarse_video, fused_eval,  # noqa: E402,F401
                          fused_eval_sharded, itm_eval, prepare_gt, score_matrix, topk_gallery_sharded)

@@ -1134,4 +1134,87 @@ int leccr_itc_backward(const void* both16, const int64_t* idx_all, int64_t n, in
                           dtemp != nullptr ? out + 1 : nullptr, dtemp, stream_);
 }
 
+// ------------------------------------------------------------------------------------ caption contrastive loss
+size_t leccr_caploss_fwd_workspace(int n_cap, int64_t B) {
+  if (n_cap < 1 || B <= 0) return 0;
+  return align256(static_cast<size_t>(n_cap) * B * B * 4);
+}
+
+int leccr_caploss_fwd(const void* cap16, int64_t ld_cap, const void* txt16, int64_t ld_txt, int n_cap, int64_t B, int K,
+                      int fmt, const float* temp, float* out, float* L, uint8_t* amax, float* stats, void* workspace,
+                      size_t workspace_bytes, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (cap16 == nullptr || txt16 == nullptr || temp == nullptr || out == nullptr || L == nullptr || amax == nullptr ||
+      stats == nullptr || n_cap < 1 || n_cap > 255 || B <= 0 || K <= 0 || bad_fmt(fmt))
+    return LECCR_ERR_ARG;
+  int rc = leccr_check_device();
+  if (rc != LECCR_OK) return rc;
+  if (workspace == nullptr || workspace_bytes < leccr_caploss_fwd_workspace(n_cap, B)) return LECCR_ERR_WORKSPACE;
+  float* S = static_cast<float*>(workspace);
+  StoreProblem sp = {cap16, txt16, ld_cap, ld_txt, static_cast<int64_t>(n_cap) * B, B, S, B, nullptr};
+  rc = launch_store(&sp, 1, K, fmt, 1.0f, nullptr, nullptr, 1, stream);
+  if (rc != LECCR_OK) return rc;
+  const int b = static_cast<int>(B);
+  capmax_rows_kernel<<<b, 256, 0, stream>>>(S, n_cap, b, temp, L, amax, stats, stats + 2 * B);
+  LAUNCH_CHECK("capmax_rows_kernel");
+  capmax_cols_kernel<<<(b + 31) / 32, dim3(32, 8), 0, stream>>>(L, b, temp, stats + B, stats + 3 * B);
+  LAUNCH_CHECK("capmax_cols_kernel");
+  caploss_finalize_kernel<<<1, 256, 0, stream>>>(L, b, temp, stats, stats + B, stats + 2 * B, stats + 3 * B, out);
+  LAUNCH_CHECK("caploss_finalize_kernel");
+  return LECCR_OK;
+}
+
+size_t leccr_caploss_bwd_workspace(int n_cap, int64_t B, int D) {
+  if (n_cap < 1 || B <= 0 || D <= 0) return 0;
+  const int64_t nb = static_cast<int64_t>(n_cap) * B;
+  const size_t g = align256(static_cast<size_t>(nb) * round_up8(B) * 2);   // G'  [nB][B8]
+  const size_t gt = align256(static_cast<size_t>(B) * round_up8(nb) * 2);  // G'^T [B][nB8]
+  const size_t tt = align256(static_cast<size_t>(D) * round_up8(B) * 2);   // text^T [D][B8]
+  const size_t ct = align256(static_cast<size_t>(D) * round_up8(nb) * 2);  // caption^T [D][nB8]
+  return g + gt + tt + ct + 256;
+}
+
+int leccr_caploss_bwd(const float* L, const uint8_t* amax, const float* stats, const void* cap16, int64_t ld_cap,
+                      const void* txt16, int64_t ld_txt, int n_cap, int64_t B, int D, int fmt, const float* temp,
+                      const float* out, const float* grad_out, float* dcap, float* dtxt, float* dtemp, void* workspace,
+                      size_t workspace_bytes, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (L == nullptr || amax == nullptr || stats == nullptr || cap16 == nullptr || txt16 == nullptr || temp == nullptr ||
+      out == nullptr || grad_out == nullptr || dcap == nullptr || dtxt == nullptr || n_cap < 1 || B <= 0 || D <= 0 ||
+      bad_fmt(fmt))
+    return LECCR_ERR_ARG;
+  if (workspace == nullptr || workspace_bytes < leccr_caploss_bwd_workspace(n_cap, B, D)) return LECCR_ERR_WORKSPACE;
+  const int64_t nb = static_cast<int64_t>(n_cap) * B;
+  const int64_t b8 = round_up8(B), nb8 = round_up8(nb);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  uint16_t* G = reinterpret_cast<uint16_t*>(ws);
+  ws += align256(static_cast<size_t>(nb) * b8 * 2);
+  uint16_t* GT = reinterpret_cast<uint16_t*>(ws);
+  ws += align256(static_cast<size_t>(B) * nb8 * 2);
+  uint16_t* TT = reinterpret_cast<uint16_t*>(ws);
+  ws += align256(static_cast<size_t>(D) * b8 * 2);
+  uint16_t* CT = reinterpret_cast<uint16_t*>(ws);
+  ws += align256(static_cast<size_t>(D) * nb8 * 2);
+  float* scale = reinterpret_cast<float*>(ws);
+  const int b = static_cast<int>(B);
+  if (fmt == LECCR_FMT_F16)
+    capgrad_kernel<0><<<b, 256, 0, stream>>>(L, amax, n_cap, b, (int)b8, temp, stats, stats + B, grad_out, G, scale);
+  else
+    capgrad_kernel<1><<<b, 256, 0, stream>>>(L, amax, n_cap, b, (int)b8, temp, stats, stats + B, grad_out, G, scale);
+  LAUNCH_CHECK("capgrad_kernel");
+  int rc = leccr_transpose16(G, nb, b, b8, GT, nb8, stream_);      // [nB][B] -> [B][nB8]
+  if (rc != LECCR_OK) return rc;
+  rc = leccr_transpose16(txt16, B, D, ld_txt, TT, b8, stream_);   // [B][D]  -> [D][B8]
+  if (rc != LECCR_OK) return rc;
+  rc = leccr_transpose16(cap16, nb, D, ld_cap, CT, nb8, stream_); // [nB][D] -> [D][nB8]
+  if (rc != LECCR_OK) return rc;
+  // d caption = G' text * s ;  d text = G'^T caption * s   (s = grad_out / (2 B temp), fp32, in the epilogue)
+  StoreProblem p0 = {G, TT, b8, b8, nb, D, dcap, D, nullptr};
+  rc = launch_store(&p0, 1, b, fmt, 1.0f, scale, nullptr, 1, stream);
+  if (rc != LECCR_OK) return rc;
+  StoreProblem p1 = {GT, CT, nb8, nb8, B, D, dtxt, D, nullptr};
+  rc = launch_store(&p1, 1, static_cast<int>(nb), fmt, 1.0f, scale, nullptr, 1, stream, grad_out, out + 1, dtemp);
+  return rc;
+}
+
 }  // extern "C"

@@ -1075,4 +1075,146 @@ __global__ void scalar_product_kernel(const float* __restrict__ a, const float* 
   if (threadIdx.x == 0) *o = *a * *b;
 }
 
+// --------------------------------------------------------------------------------
+// Caption contrastive loss: models/model_retrieval_caption.py:145-152
+//   sim    = caption.reshape(n * B, d) @ text.T          (tensor cores, split precision, materialised: n*B*B small)
+//   logits = max_n sim / temp ; labels = arange(B) ; loss = (CE(logits) + CE(logits.T)) / 2
+// The kernels below take the materialised sim [n][B][B] and produce the max / argmax, both log-sum-exp
+// families (rows and columns, log2 units) with E_softmax[z] for d loss / d temp, the loss, and in the backward
+// the gradient strip G' routed to the arg-max plane (what autograd's max does).
+// --------------------------------------------------------------------------------
+__device__ __forceinline__ void lse_combine(float& m, float& l, float& w, float m2, float l2, float w2) {
+  const float mn = fmaxf(m, m2);
+  const float a = (m == -CUDART_INF_F) ? 0.f : exp2f(m - mn), b = (m2 == -CUDART_INF_F) ? 0.f : exp2f(m2 - mn);
+  l = l * a + l2 * b;
+  w = w * a + w2 * b;
+  m = mn;
+}
+
+// One block per row i: L[i][j] = max_a S[a][i][j], amax = first arg max (torch.max semantics on ties),
+// row log-sum-exp of z2 = L * log2e / temp and sum_j softmax_ij * z2_ij.
+__global__ void capmax_rows_kernel(const float* __restrict__ S, int n_cap, int B, const float* __restrict__ temp,
+                                   float* __restrict__ L, unsigned char* __restrict__ amax,
+                                   float* __restrict__ lse_row, float* __restrict__ e_row) {
+  __shared__ float sm[8], sl[8], sw[8];
+  const int i = blockIdx.x;
+  const float sc = 1.4426950408889634f / __ldg(temp);
+  float m = -CUDART_INF_F, l = 0.f, w = 0.f;
+  for (int j = threadIdx.x; j < B; j += blockDim.x) {
+    float best = S[(static_cast<long long>(0) * B + i) * B + j];
+    int arg = 0;
+    for (int a = 1; a < n_cap; ++a) {
+      const float v = S[(static_cast<long long>(a) * B + i) * B + j];
+      if (v > best) {
+        best = v;
+        arg = a;
+      }
+    }
+    L[static_cast<long long>(i) * B + j] = best;
+    amax[static_cast<long long>(i) * B + j] = static_cast<unsigned char>(arg);
+    const float z = best * sc;
+    lse_combine(m, l, w, z, 1.f, z);
+  }
+  for (int o = 16; o > 0; o >>= 1)
+    lse_combine(m, l, w, __shfl_xor_sync(0xffffffffu, m, o), __shfl_xor_sync(0xffffffffu, l, o),
+                __shfl_xor_sync(0xffffffffu, w, o));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    sm[warp] = m;
+    sl[warp] = l;
+    sw[warp] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < (blockDim.x >> 5); ++k) lse_combine(m, l, w, sm[k], sl[k], sw[k]);
+    lse_row[i] = m + log2f(l);
+    e_row[i] = w / l;
+  }
+}
+
+// Columns: block = 32 columns x 8 row phases; same statistics down the columns of L.
+__global__ void capmax_cols_kernel(const float* __restrict__ L, int B, const float* __restrict__ temp,
+                                   float* __restrict__ lse_col, float* __restrict__ e_col) {
+  __shared__ float sm[8][33], sl[8][33], sw[8][33];
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  const float sc = 1.4426950408889634f / __ldg(temp);
+  float m = -CUDART_INF_F, l = 0.f, w = 0.f;
+  if (j < B)
+    for (int i = threadIdx.y; i < B; i += blockDim.y) {
+      const float z = L[static_cast<long long>(i) * B + j] * sc;
+      lse_combine(m, l, w, z, 1.f, z);
+    }
+  sm[threadIdx.y][threadIdx.x] = m;
+  sl[threadIdx.y][threadIdx.x] = l;
+  sw[threadIdx.y][threadIdx.x] = w;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < B) {
+    for (int k = 1; k < blockDim.y; ++k) lse_combine(m, l, w, sm[k][threadIdx.x], sl[k][threadIdx.x], sw[k][threadIdx.x]);
+    lse_col[j] = m + log2f(l);
+    e_col[j] = w / l;
+  }
+}
+
+// One block: loss and d loss / d temp (per unit upstream gradient), fp64 sums.
+//   loss  = 1/(2B) sum_i [(lse_row_i - z_ii) + (lse_col_i - z_ii)]
+//   dtemp = -(1/temp) [ 1/(2B) (sum_i E_row_i[z] + sum_j E_col_j[z]) - 1/B sum_i z_ii ]
+__global__ void caploss_finalize_kernel(const float* __restrict__ L, int B, const float* __restrict__ temp,
+                                        const float* __restrict__ lse_row, const float* __restrict__ lse_col,
+                                        const float* __restrict__ e_row, const float* __restrict__ e_col,
+                                        float* __restrict__ out) {
+  __shared__ double r0[8], r1[8];
+  const double sc = 1.4426950408889634 / static_cast<double>(*temp);
+  double a0 = 0.0, a1 = 0.0;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const double zii = static_cast<double>(L[static_cast<long long>(i) * B + i]) * sc;
+    a0 += static_cast<double>(lse_row[i]) + static_cast<double>(lse_col[i]) - 2.0 * zii;
+    a1 += static_cast<double>(e_row[i]) + static_cast<double>(e_col[i]) - 2.0 * zii;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    r0[threadIdx.x >> 5] = a0;
+    r1[threadIdx.x >> 5] = a1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int k = 0; k < (blockDim.x >> 5); ++k) {
+      t0 += r0[k];
+      t1 += r1[k];
+    }
+    const double ln2 = 0.6931471805599453;
+    out[0] = static_cast<float>(ln2 * t0 / (2.0 * B));
+    out[1] = static_cast<float>(-ln2 * t1 / (2.0 * B) / static_cast<double>(*temp));
+  }
+}
+
+// Backward strip: G'_ij = softmax_row_ij + softmax_col_ij - 2 delta_ij in [-2, 2], stored 16-bit in the plane of
+// the arg max ([n][B][ld], other planes and the pad columns zero); scale[0] = grad_out / (2 B temp) is applied
+// in fp32 by the gradient products' epilogue.
+template <int FMT>
+__global__ void capgrad_kernel(const float* __restrict__ L, const unsigned char* __restrict__ amax, int n_cap, int B,
+                               int ld, const float* __restrict__ temp, const float* __restrict__ lse_row,
+                               const float* __restrict__ lse_col, const float* __restrict__ grad_out,
+                               uint16_t* __restrict__ G, float* __restrict__ scale) {
+  const int i = blockIdx.x;
+  const float t = __ldg(temp);
+  const float sc = 1.4426950408889634f / t;
+  if (i == 0 && threadIdx.x == 0) scale[0] = __ldg(grad_out) / (2.f * static_cast<float>(B) * t);
+  const float lr = lse_row[i];
+  for (int j = threadIdx.x; j < ld; j += blockDim.x) {
+    float g = 0.f;
+    int arg = -1;
+    if (j < B) {
+      const float z = L[static_cast<long long>(i) * B + j] * sc;
+      g = exp2f(z - lr) + exp2f(z - lse_col[j]) - (i == j ? 2.f : 0.f);
+      arg = amax[static_cast<long long>(i) * B + j];
+    }
+    for (int a = 0; a < n_cap; ++a)
+      G[(static_cast<long long>(a) * B + i) * ld + j] = f32_to_16<FMT>(a == arg ? g : 0.f);
+  }
+}
+
 }  // namespace leccr

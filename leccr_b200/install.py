@@ -10,6 +10,7 @@ rebinding is all a maintainer has to do; nothing else in the reference changes.
 import importlib
 
 from . import allgather as _ag
+from . import caption_loss as _cl
 from . import contrastive as _ct
 from . import evaluation as _ev
 
@@ -32,6 +33,22 @@ def install(modules=("models.xvlm", "models.xvlm_video")):
             continue
         _patch_xvlm(mod, base)
         done.append(name)
+    return done
+
+
+def install_caption_loss(modules=("models.model_retrieval_caption", "models.video_model_retrieval_caption")):
+    """Rebind RetrievalModel.get_caption_contrastive_loss (models/model_retrieval_caption.py:145,
+    models/video_model_retrieval_caption.py:171) in the model modules that are importable."""
+    done = []
+    for name in modules:
+        try:
+            mod = importlib.import_module(name)
+        except Exception:
+            continue
+        cls = getattr(mod, "RetrievalModel", None)
+        if cls is not None and hasattr(cls, "get_caption_contrastive_loss"):
+            cls.get_caption_contrastive_loss = _cl.get_caption_contrastive_loss
+            done.append(name)
     return done
 
 

@@ -67,6 +67,28 @@ def contrastive_loss_and_grads(image_feat_all, text_feat_all, temp: float, idx_a
             t.grad.detach())
 
 
+def caption_contrastive_loss(caption_embeds: torch.Tensor, text_feats: torch.Tensor, temp) -> torch.Tensor:
+    """models/model_retrieval_caption.py:145-152 (== video_model_retrieval_caption.py:171-178), statement for
+    statement: local batch only, max over the n caption queries, arange labels, symmetric cross entropy."""
+    n, bsz, d = caption_embeds.shape
+    sim = caption_embeds.reshape(-1, d) @ text_feats.transpose(0, 1)
+    logits = torch.max(sim.reshape(n, bsz, bsz), dim=0)[0] / temp
+    labels = torch.arange(bsz, device=caption_embeds.device)
+    loss_i2t = F.cross_entropy(logits, labels)
+    loss_t2i = F.cross_entropy(logits.t(), labels)
+    return (loss_t2i + loss_i2t) / 2
+
+
+def caption_contrastive_loss_and_grads(caption_embeds, text_feats, temp: float, dtype=torch.float32):
+    """Loss and autograd gradients (d caption, d text, d temp); dtype=float64 for tolerance setting."""
+    c = caption_embeds.detach().to(dtype).clone().requires_grad_(True)
+    t = text_feats.detach().to(dtype).clone().requires_grad_(True)
+    tp = torch.tensor(float(temp), dtype=dtype, requires_grad=True)
+    loss = caption_contrastive_loss(c, t, tp)
+    loss.backward()
+    return loss.detach(), c.grad, t.grad, tp.grad.detach()
+
+
 # ----------------------------------------------------------------------------- evaluation score matrices
 def score_matrices(image_embeds: torch.Tensor, text_embeds: torch.Tensor):
     """image_Retrieval_caption.py:151-152,163: i2t = image @ text.T, t2i = its transpose VIEW, as numpy."""

@@ -349,3 +349,37 @@ def test_streamed_eval_plan_equals_reference_and_fused_eval(golden, cfg, windows
         for d_ in ("i2t", "t2i"):
             assert torch.equal(topk[d_][0], want_topk[d_][0]), d_
             assert torch.equal(topk[d_][1], want_topk[d_][1]), d_
+
+
+# ----------------------------------------------------------------------------- caption contrastive loss (8f rank 1)
+def _check_caption_loss(cap, text, temp_v, want, tol_loss=1e-3, tol_grad=3e-3):
+    temp = torch.nn.Parameter(torch.tensor(float(temp_v), device="cuda"))
+    c = cap.cuda().requires_grad_(True)
+    t = text.cuda().requires_grad_(True)
+    me = types.SimpleNamespace(temp=temp)
+    loss = leccr_b200.get_caption_contrastive_loss(me, c, t)
+    loss.backward()
+    w_loss, w_dc, w_dt, w_dtemp = want
+    assert abs(loss.item() - float(w_loss)) <= tol_loss * abs(float(w_loss)), (loss.item(), float(w_loss))
+    for got, ref in ((c.grad.cpu().double(), torch.as_tensor(w_dc).double()), (t.grad.cpu().double(), torch.as_tensor(w_dt).double())):
+        assert (got - ref).norm() <= tol_grad * ref.norm(), ((got - ref).norm().item(), ref.norm().item())
+    assert abs(temp.grad.item() - float(w_dtemp)) <= tol_grad * abs(float(w_dtemp)), (temp.grad.item(), float(w_dtemp))
+
+
+def test_caption_contrastive_loss_against_reference_golden(golden):
+    """get_caption_contrastive_loss vs the reference's own function and autograd (tests/golden/caption_loss.npz);
+    tolerances as for get_contrastive_loss: loss 1e-3 relative, gradients 3e-3 relative (16-bit gradient strips)."""
+    g = golden("caption_loss.npz")
+    for c in "abc":
+        _check_caption_loss(torch.from_numpy(g[f"{c}_caption"]), torch.from_numpy(g[f"{c}_text"]), float(g[f"{c}_temp"]),
+                            (g[f"{c}_loss"], g[f"{c}_dcaption"], g[f"{c}_dtext"], g[f"{c}_dtemp"]))
+
+
+@pytest.mark.parametrize("n,bsz,d", [(2, 512, 256), (4, 512, 256), (3, 257, 128)])
+def test_caption_contrastive_loss_against_oracle(n, bsz, d):
+    """Training-size batches (per-GPU batch 512, num_queries 2 / 4) against the fp64 oracle."""
+    g = torch.Generator().manual_seed(100 + n)
+    text = torch.nn.functional.normalize(torch.randn(bsz, d, generator=g), dim=-1)
+    cap = text[None] + (2.0 / d ** 0.5) * torch.randn(n, bsz, d, generator=g)
+    want = oracle.caption_contrastive_loss_and_grads(cap, text, 0.07, dtype=torch.float64)
+    _check_caption_loss(cap, text, 0.07, want)

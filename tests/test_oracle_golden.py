@@ -106,3 +106,16 @@ def test_cfg3_itc(golden):
         np.testing.assert_allclose(da[:8].numpy(), g[f"cfg3_{name}_dA_rows"], rtol=1e-4, atol=1e-8)
         np.testing.assert_allclose(db[:8].numpy(), g[f"cfg3_{name}_dB_rows"], rtol=1e-4, atol=1e-8)
         assert abs(da.norm().item() - float(g[f"cfg3_{name}_dA_norm"])) <= 1e-4 * float(g[f"cfg3_{name}_dA_norm"])
+
+
+def test_caption_contrastive_loss_matches_reference(golden):
+    """oracle.caption_contrastive_loss vs the reference's get_caption_contrastive_loss run by
+    oracle/make_golden_caption.py (loss and autograd gradients)."""
+    g = golden("caption_loss.npz")
+    for c in "abc":
+        cap, text, temp = torch.from_numpy(g[f"{c}_caption"]), torch.from_numpy(g[f"{c}_text"]), float(g[f"{c}_temp"])
+        loss, dc, dt, dtemp = oracle.caption_contrastive_loss_and_grads(cap, text, temp)
+        assert abs(loss.item() - float(g[f"{c}_loss"])) <= 1e-6 * abs(float(g[f"{c}_loss"]))
+        assert np.abs(dc.numpy() - g[f"{c}_dcaption"]).max() <= 1e-6 * max(1e-6, np.abs(g[f"{c}_dcaption"]).max())
+        assert np.abs(dt.numpy() - g[f"{c}_dtext"]).max() <= 1e-6 * max(1e-6, np.abs(g[f"{c}_dtext"]).max())
+        assert abs(dtemp.item() - float(g[f"{c}_dtemp"])) <= 1e-5 * abs(float(g[f"{c}_dtemp"]))
