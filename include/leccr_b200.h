@@ -289,6 +289,12 @@ int leccr_caploss_bwd(const float* L, const uint8_t* amax, const float* stats, c
                       const float* out, const float* grad_out, float* dcap, float* dtxt, float* dtemp, void* workspace,
                       size_t workspace_bytes, leccr_stream_t stream);
 
+/* leccr_topk_dense: top-k (k <= 16) of every row -- or, with by_columns, every column -- of a MATERIALISED
+ * fp32 score matrix S [R][ld]; used for the double_sim fusion (video_Retrieval_caption_double_sim.py:178-179),
+ * whose matrix is materialised.  out: [R or C][k], score descending, ties by lower index, -1 / -inf padding. */
+int leccr_topk_dense(const float* S, int64_t ld, int64_t R, int64_t C, int by_columns, int k, float* out_val,
+                     int32_t* out_idx, leccr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1217,4 +1217,19 @@ int leccr_caploss_bwd(const float* L, const uint8_t* amax, const float* stats, c
   return rc;
 }
 
+int leccr_topk_dense(const float* S, int64_t ld, int64_t R, int64_t C, int by_columns, int k, float* out_val,
+                     int32_t* out_idx, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (S == nullptr || out_val == nullptr || out_idx == nullptr || R <= 0 || C <= 0 || ld < C || k < 1 ||
+      k > kDenseTopkMax)
+    return LECCR_ERR_ARG;
+  // by_columns: rank the columns of S (the reference's t2i matrix is the transpose VIEW of i2t, :152 / :179)
+  const long long ld_r = by_columns ? 1 : ld, ld_c = by_columns ? ld : 1;
+  const int n_rank = static_cast<int>(by_columns ? C : R), n_scan = static_cast<int>(by_columns ? R : C);
+  const int wpb = 8;
+  topk_dense_kernel<<<(n_rank + wpb - 1) / wpb, wpb * 32, 0, stream>>>(S, ld_r, ld_c, n_rank, n_scan, k, out_val, out_idx);
+  LAUNCH_CHECK("topk_dense_kernel");
+  return LECCR_OK;
+}
+
 }  // extern "C"

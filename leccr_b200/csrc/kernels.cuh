@@ -1217,4 +1217,72 @@ __global__ void capgrad_kernel(const float* __restrict__ L, const unsigned char*
   }
 }
 
+// --------------------------------------------------------------------------------
+// Top-k of the rows (or, through the strides, the columns) of a MATERIALISED score matrix: the double_sim
+// fusion produces one (video_Retrieval_caption_double_sim.py:178; cfg4 = 1000 x 1000), and fused_eval returns
+// top-k lists for it like for the plain similarity.  One warp per row: every lane keeps a sorted top-KMAX of
+// its strided share, then k rounds of a warp arg-max pop the winners.  Order: score descending, ties by
+// lower column (the rule of topk_finalize).
+// --------------------------------------------------------------------------------
+constexpr int kDenseTopkMax = 16;
+__global__ void topk_dense_kernel(const float* __restrict__ S, long long ld_r, long long ld_c, int R, int C, int k,
+                                  float* __restrict__ out_val, int* __restrict__ out_idx) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
+  float v[kDenseTopkMax];
+  int id[kDenseTopkMax];
+#pragma unroll
+  for (int i = 0; i < kDenseTopkMax; ++i) {
+    v[i] = -CUDART_INF_F;
+    id[i] = 0x7fffffff;
+  }
+  const float* base = S + static_cast<long long>(row) * ld_r;
+  for (int c = lane; c < C; c += 32) {
+    const float x = base[static_cast<long long>(c) * ld_c];
+    if (x > v[kDenseTopkMax - 1]) {  // columns arrive in increasing order: a tie never displaces an earlier column
+      v[kDenseTopkMax - 1] = x;
+      id[kDenseTopkMax - 1] = c;
+#pragma unroll
+      for (int i = kDenseTopkMax - 1; i > 0; --i) {
+        const bool sw = v[i] > v[i - 1];
+        const float tv = v[i];
+        const int ti = id[i];
+        if (sw) {
+          v[i] = v[i - 1];
+          id[i] = id[i - 1];
+          v[i - 1] = tv;
+          id[i - 1] = ti;
+        }
+      }
+    }
+  }
+  for (int s = 0; s < k; ++s) {
+    // the warp's best head: (score desc, column asc)
+    float bv = v[0];
+    int bi = id[0];
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) {
+        bv = ov;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      out_val[static_cast<long long>(row) * k + s] = bv;
+      out_idx[static_cast<long long>(row) * k + s] = bi == 0x7fffffff ? -1 : bi;
+    }
+    if (id[0] == bi && bi != 0x7fffffff) {  // the owner pops its head (columns are unique across lanes)
+#pragma unroll
+      for (int i = 0; i < kDenseTopkMax - 1; ++i) {
+        v[i] = v[i + 1];
+        id[i] = id[i + 1];
+      }
+      v[kDenseTopkMax - 1] = -CUDART_INF_F;
+      id[kDenseTopkMax - 1] = 0x7fffffff;
+    }
+  }
+}
+
 }  // namespace leccr

@@ -214,16 +214,43 @@ def prepare_gt(txt2img, img2txt, n_img, n_txt, device=None):
 
 
 @torch.no_grad()
+def _fused_eval_double_sim(image_embeds, text_embeds, caption_embeds, txt2img, img2txt, k, alpha, fusion, return_topk, gt):
+    """double_sim variant of fused_eval: the fused matrix alpha * f(S) + (1 - alpha) * f(max_n C_n) is
+    materialised on the device (max_n needs every C_n tile beside the S tile: (n + 1) * 256 TMEM columns,
+    DESIGN.md section 7), ranked exactly there (leccr_rank_rows / leccr_rank_cols) and its top-k lists read by
+    leccr_topk_dense; only the six counts cross PCIe."""
+    dev = _device()
+    F_ = double_sim_matrix(image_embeds, text_embeds, caption_embeds, alpha, fusion)
+    n_img, n_txt = F_.shape
+    if gt is None:
+        gt = prepare_gt(txt2img, img2txt, n_img, n_txt, dev)
+    r_i = ops.rank_rows(F_, *gt[0])
+    r_t = ops.rank_cols(F_, *gt[1])
+    host = torch.cat([ops.recall_counts(r_i), ops.recall_counts(r_t)]).cpu().tolist()
+    ev = metrics_from_counts(host[0:3], n_img, host[3:6], n_txt)
+    if not return_topk:
+        return ev
+    return ev, {'i2t': ops.topk_dense(F_, k), 't2i': ops.topk_dense(F_, k, by_columns=True)}
+
+
+@torch.no_grad()
 def fused_eval(image_embeds, text_embeds, txt2img=None, img2txt=None, k=10, precision="f16", tiles_per_chunk=0,
-               return_topk=True, gt=None):
+               return_topk=True, gt=None, caption_embeds=None, alpha=0.9, fusion="none"):
     """Similarity + per-row top-k + exact Recall@1/5/10 for both directions in one tensor-core launch.
 
     image_embeds [N, D], text_embeds [M, D]: numpy / CPU / CUDA, fp32 (cast to 16-bit operands here) or
     fp16 / bf16 (used as they are).  gt: optional prepare_gt(...) result (else built from the dicts).
+    caption_embeds [n, N, D] with fusion "norm" (video_Retrieval_caption_double_sim.py:175-179, alpha 0.9) or
+    "raw" (image_Retrieval_caption.py:239-246, alpha 0.8) evaluates the double_sim fusion instead.
     Returns (eval dict with the reference's 13 keys, topk) where topk is
     {'i2t': (val [N, k], idx [N, k]), 't2i': (val [M, k], idx [M, k])} CUDA tensors (approximate scores,
     ties inside the 16-bit rounding may be ordered differently from fp32).
     """
+    if fusion not in ("none", "raw", "norm"):
+        raise ValueError("fusion must be 'none', 'raw' or 'norm'")
+    if caption_embeds is not None and fusion != "none":
+        return _fused_eval_double_sim(image_embeds, text_embeds, caption_embeds, txt2img, img2txt, k, alpha, fusion,
+                                      return_topk, gt)
     dev = _device()
     img = _to_device(image_embeds, dev)
     txt = _to_device(text_embeds, dev)

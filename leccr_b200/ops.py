@@ -272,3 +272,18 @@ def double_sim_fuse(S: torch.Tensor, Cn: torch.Tensor, alpha: float, mode: int) 
                                       float(alpha), float(1.0 - alpha), mode, N.stream_ptr()),
             "leccr_double_sim_fuse")
     return S
+
+
+def topk_dense(S: torch.Tensor, k: int, by_columns: bool = False):
+    """Top-k of the rows (or columns) of a materialised fp32 matrix: (val, idx int32), score descending."""
+    lib = N.load()
+    _require_cuda(S, "S")
+    if S.dtype != torch.float32 or S.stride(1) != 1:
+        raise N.LeccrError("topk_dense needs a row-major fp32 matrix")
+    R, C = S.shape
+    n = C if by_columns else R
+    val = torch.empty((n, k), dtype=torch.float32, device=S.device)
+    idx = torch.empty((n, k), dtype=torch.int32, device=S.device)
+    N.check(lib.leccr_topk_dense(N.ptr(S), S.stride(0), R, C, int(by_columns), k, N.ptr(val), N.ptr(idx),
+                                 N.stream_ptr()), "leccr_topk_dense")
+    return val, idx

@@ -383,3 +383,39 @@ def test_caption_contrastive_loss_against_oracle(n, bsz, d):
     cap = text[None] + (2.0 / d ** 0.5) * torch.randn(n, bsz, d, generator=g)
     want = oracle.caption_contrastive_loss_and_grads(cap, text, 0.07, dtype=torch.float64)
     _check_caption_loss(cap, text, 0.07, want)
+
+
+# ----------------------------------------------------------------------------- fused_eval, double_sim mode
+def test_fused_eval_double_sim_cfg4_and_small_golden(golden):
+    """fused_eval(..., caption_embeds, alpha, fusion) (SURVEY 8b signature): the reference's Recall dict for cfg4 and
+    the small video case, and top-k lists equal to a sort of the oracle's fused matrix (ties aside)."""
+    g = golden("baseline_configs.npz")
+    rs = synth.cfg4_msrvtt()
+    ev, topk = leccr_b200.fused_eval(rs.image, rs.text, rs.txt2img, rs.img2txt, k=10, caption_embeds=rs.caption,
+                                     alpha=0.9, fusion="norm")
+    assert_ev_equal(ev, ev_of(g, "cfg4_ev_"))
+    want_i2t, want_t2i = oracle.double_sim_matrices(rs.image, rs.text, rs.caption, alpha=0.9)
+    for name, want in (("i2t", want_i2t), ("t2i", np.ascontiguousarray(want_t2i))):
+        val, idx = topk[name][0].cpu().numpy(), topk[name][1].cpu().numpy().astype(np.int64)
+        wv = np.sort(want, axis=1)[:, ::-1][:, :10]
+        assert np.abs(val - wv).max() < 2e-5
+        assert np.abs(np.take_along_axis(want, idx, 1) - wv).max() < 2e-5       # the columns named carry those scores
+        assert (np.diff(val, axis=1) <= 0).all()
+    gs = golden("video_small.npz")
+    n = gs["image"].shape[0]
+    txt2img = {t: t for t in range(n)}
+    img2txt = {i: [i] for i in range(n)}
+    ev_s = leccr_b200.fused_eval(gs["image"], gs["text"], txt2img, img2txt, caption_embeds=gs["caption"], alpha=0.9,
+                                 fusion="norm", return_topk=False)
+    assert_ev_equal(ev_s, ev_of(gs, "ev_"))
+
+
+def test_topk_dense_rows_and_columns_with_ties():
+    g = torch.Generator().manual_seed(3)
+    S = (torch.randint(0, 40, (70, 333), generator=g).float() / 40).cuda()   # many exact ties
+    for by_cols in (False, True):
+        val, idx = ops.topk_dense(S, 16, by_columns=by_cols)
+        M = (S.t() if by_cols else S).contiguous().cpu()
+        order = torch.argsort(M, dim=1, descending=True, stable=True)[:, :16]   # stable: ties by lower column
+        assert torch.equal(idx.cpu().long(), order)
+        assert torch.equal(val.cpu(), torch.gather(M, 1, order))
