@@ -34,6 +34,7 @@ extern "C" {
 #define LECCR_ERR_CUDA (-4)       /* a CUDA runtime call failed (see leccr_last_cuda_error)    */
 #define LECCR_ERR_WORKSPACE (-5)  /* workspace too small                                       */
 #define LECCR_ERR_DRIVER (-6)     /* cuTensorMapEncodeTiled unavailable or failed              */
+#define LECCR_ERR_NCCL (-7)       /* libnccl.so.2 unavailable or an NCCL call failed           */
 
 /* element types of caller tensors */
 #define LECCR_F32 0
@@ -294,6 +295,23 @@ int leccr_caploss_bwd(const float* L, const uint8_t* amax, const float* stats, c
  * whose matrix is materialised.  out: [R or C][k], score descending, ties by lower index, -1 / -inf padding. */
 int leccr_topk_dense(const float* S, int64_t ld, int64_t R, int64_t C, int by_columns, int k, float* out_val,
                      int32_t* out_idx, leccr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * NCCL collectives behind the C ABI, for hosts without torch.distributed and for groups that span nodes
+ * (inside one NVLink node the peer-memory entries above are used instead).  Replaces the transport of
+ * AllGather.forward, models/xvlm.py:53-59 (dist.all_gather + torch.cat -> one ncclAllGather into the
+ * gathered buffer); the top-k lists of a row-partitioned gallery are exchanged with the same call and merged
+ * by leccr_topk_merge_peers over a table of pointers into the gathered buffer.
+ *   leccr_comm_unique_id : rank 0 creates the 128-byte id and ships it to the others (any side channel)
+ *   leccr_comm_init      : collective; one communicator per process / GPU (current device)
+ *   leccr_allgather      : recv[r * bytes_per_rank ...] = rank r's send, stream-ordered
+ * libnccl.so.2 is resolved at run time (LECCR_ERR_NCCL when it is missing).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct leccr_nccl_id { char internal[128]; } leccr_nccl_id;
+int leccr_comm_unique_id(leccr_nccl_id* id_host);
+int leccr_comm_init(const leccr_nccl_id* id_host, int rank, int world, void** comm);
+int leccr_comm_destroy(void* comm);
+int leccr_allgather(void* comm, const void* send, void* recv, size_t bytes_per_rank, leccr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -43,7 +43,7 @@ def build(force=False, verbose=False):
         "-gencode", "arch=compute_100a,code=sm_100a",
         "-O3", "-lineinfo", "-std=c++17",
         "-shared", "-Xcompiler", "-fPIC",
-        "-o", LIB, SRC,
+        "-o", LIB, SRC, "-ldl",
     ]
     if verbose:
         cmd.insert(1, "-Xptxas")

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <mutex>
 
 #include "epilogues.cuh"
@@ -220,6 +221,7 @@ const char* leccr_strerror(int code) {
     case LECCR_ERR_CUDA: return "CUDA runtime error (see leccr_last_cuda_error)";
     case LECCR_ERR_WORKSPACE: return "workspace too small";
     case LECCR_ERR_DRIVER: return "cuTensorMapEncodeTiled unavailable or failed";
+    case LECCR_ERR_NCCL: return "libnccl.so.2 unavailable or an NCCL call failed (see leccr_last_cuda_error)";
     default: return "unknown leccr error code";
   }
 }
@@ -1230,6 +1232,80 @@ int leccr_topk_dense(const float* S, int64_t ld, int64_t R, int64_t C, int by_co
   topk_dense_kernel<<<(n_rank + wpb - 1) / wpb, wpb * 32, 0, stream>>>(S, ld_r, ld_c, n_rank, n_scan, k, out_val, out_idx);
   LAUNCH_CHECK("topk_dense_kernel");
   return LECCR_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------ NCCL collectives
+// For hosts without torch.distributed (and for node-crossing groups, where peer memory does not reach): the two
+// collectives of the path as thin C entries over NCCL.  libnccl.so.2 is resolved at run time (dlopen: the copy
+// the process already loaded, e.g. torch's, is reused), so the library has no link-time dependency on it.
+namespace {
+struct NcclApi {
+  int (*get_unique_id)(void*);
+  int (*comm_init_rank)(void**, int, leccr_nccl_id, int);
+  int (*comm_destroy)(void*);
+  int (*all_gather)(const void*, void*, size_t, int, void*, cudaStream_t);
+  const char* (*get_error_string)(int);
+  bool ok;
+};
+NcclApi& nccl_api() {
+  static NcclApi api = {};
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (h == nullptr) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h == nullptr) return;
+    api.get_unique_id = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclGetUniqueId"));
+    api.comm_init_rank = reinterpret_cast<int (*)(void**, int, leccr_nccl_id, int)>(dlsym(h, "ncclCommInitRank"));
+    api.comm_destroy = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclCommDestroy"));
+    api.all_gather =
+        reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(dlsym(h, "ncclAllGather"));
+    api.get_error_string = reinterpret_cast<const char* (*)(int)>(dlsym(h, "ncclGetErrorString"));
+    api.ok = api.get_unique_id && api.comm_init_rank && api.comm_destroy && api.all_gather;
+  });
+  return api;
+}
+int nccl_fail(int r, const char* what) {
+  NcclApi& a = nccl_api();
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: NCCL error %d (%s)", what, r,
+           a.get_error_string != nullptr ? a.get_error_string(r) : "?");
+  return LECCR_ERR_NCCL;
+}
+}  // namespace
+
+extern "C" {
+
+int leccr_comm_unique_id(leccr_nccl_id* id_host) {
+  if (id_host == nullptr) return LECCR_ERR_ARG;
+  NcclApi& a = nccl_api();
+  if (!a.ok) return LECCR_ERR_NCCL;
+  const int r = a.get_unique_id(id_host);
+  return r == 0 ? LECCR_OK : nccl_fail(r, "ncclGetUniqueId");
+}
+
+int leccr_comm_init(const leccr_nccl_id* id_host, int rank, int world, void** comm) {
+  if (id_host == nullptr || comm == nullptr || world < 1 || rank < 0 || rank >= world) return LECCR_ERR_ARG;
+  NcclApi& a = nccl_api();
+  if (!a.ok) return LECCR_ERR_NCCL;
+  const int r = a.comm_init_rank(comm, world, *id_host, rank);
+  return r == 0 ? LECCR_OK : nccl_fail(r, "ncclCommInitRank");
+}
+
+int leccr_comm_destroy(void* comm) {
+  if (comm == nullptr) return LECCR_ERR_ARG;
+  NcclApi& a = nccl_api();
+  if (!a.ok) return LECCR_ERR_NCCL;
+  const int r = a.comm_destroy(comm);
+  return r == 0 ? LECCR_OK : nccl_fail(r, "ncclCommDestroy");
+}
+
+int leccr_allgather(void* comm, const void* send, void* recv, size_t bytes_per_rank, leccr_stream_t stream_) {
+  if (comm == nullptr || send == nullptr || recv == nullptr || bytes_per_rank == 0) return LECCR_ERR_ARG;
+  NcclApi& a = nccl_api();
+  if (!a.ok) return LECCR_ERR_NCCL;
+  const int r = a.all_gather(send, recv, bytes_per_rank, /*ncclUint8*/ 1, comm, static_cast<cudaStream_t>(stream_));
+  return r == 0 ? LECCR_OK : nccl_fail(r, "ncclAllGather");
 }
 
 }  // extern "C"

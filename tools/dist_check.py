@@ -52,6 +52,38 @@ paths = {str(k_[0]): (v_ is not None) for k_, v_ in _peer._cache.items()}
 print(f"rank {rank}: sharded eval == golden {ev_ok}; gallery-partition merge == single pass {merge_ok}; peer-memory paths used: {paths}", flush=True)
 if os.environ.get("LECCR_PEER", "1") != "0":
     ok &= paths.get("itc", False) and paths.get("topk", False)  # on a B200 NVLink box the peer kernels must be what ran
+# ---- the C-ABI NCCL entries (hosts without torch.distributed): communicator from a broadcast unique id,
+# all-gather of this rank's top-k lists, merge over a table of pointers into the gathered buffer
+import ctypes
+from leccr_b200 import _native as _N
+_lib = _N.load()
+uid = torch.zeros(128, dtype=torch.uint8)
+if rank == 0:
+    buf = ctypes.create_string_buffer(128)
+    _N.check(_lib.leccr_comm_unique_id(buf), "leccr_comm_unique_id")
+    uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+uid_d = uid.cuda()
+dist.broadcast(uid_d, 0)
+idbuf = ctypes.create_string_buffer(bytes(uid_d.cpu().tolist()), 128)
+comm = ctypes.c_void_p()
+_N.check(_lib.leccr_comm_init(idbuf, rank, world, ctypes.byref(comm)), "leccr_comm_init")
+local_res, = _ops.sim_topk([(_ops.prep(qry), _ops.prep(gal[b0:e0]), None)], k=10)
+Qn = qry.shape[0]
+send = torch.cat([local_res.val.reshape(-1).view(torch.int32), local_res.idx.reshape(-1)]).contiguous()   # [Q*k vals | Q*k idx]
+recv = torch.empty(world * send.numel(), dtype=torch.int32, device="cuda")
+_N.check(_lib.leccr_allgather(comm, _N.ptr(send), _N.ptr(recv), send.numel() * 4, _N.stream_ptr()), "leccr_allgather")
+per = send.numel() * 4
+vt = torch.tensor([recv.data_ptr() + r * per for r in range(world)], dtype=torch.int64, device="cuda")
+it = torch.tensor([recv.data_ptr() + r * per + Qn * 10 * 4 for r in range(world)], dtype=torch.int64, device="cuda")
+offs = (ctypes.c_int64 * world)(*[sharding.shard_range(40000, r, world)[0] for r in range(world)])
+ov = torch.empty((Qn, 10), dtype=torch.float32, device="cuda")
+oi = torch.empty((Qn, 10), dtype=torch.int32, device="cuda")
+_N.check(_lib.leccr_topk_merge_peers(_N.ptr(vt), _N.ptr(it), world, 10, 0, Qn, offs, 10, _N.ptr(ov), _N.ptr(oi),
+                                     _N.stream_ptr()), "leccr_topk_merge_peers")
+nccl_ok = bool(torch.equal(oi.long(), full.idx.long())) and bool(torch.equal(ov, full.val))
+_N.check(_lib.leccr_comm_destroy(comm), "leccr_comm_destroy")
+ok &= nccl_ok
+print(f"rank {rank}: C-ABI NCCL all-gather + merge == single pass {nccl_ok}", flush=True)
 # timing of the training step (fwd + bwd) on this rank, max over ranks
 def step():
     me.temp.grad = None
