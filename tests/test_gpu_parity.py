@@ -419,3 +419,35 @@ def test_topk_dense_rows_and_columns_with_ties():
         order = torch.argsort(M, dim=1, descending=True, stable=True)[:, :16]   # stable: ties by lower column
         assert torch.equal(idx.cpu().long(), order)
         assert torch.equal(val.cpu(), torch.gather(M, 1, order))
+
+
+# ----------------------------------------------------------------------------- kernel-variant sweep
+# Every top-k launch shape: dense two-warpgroup kernel with K = 32 stages (short column chunks), filter kernel
+# with the resident row block (long chunks, D <= 256) and with the streamed row block (D > 256); embedding
+# dimensions that are not multiples of the stage depth; ragged rows / columns; tiles_per_chunk forcing each path.
+@pytest.mark.parametrize("n_per,d,tpc", [
+    (5, 64, 0), (5, 72, 0), (3, 136, 1), (5, 256, 2), (2, 512, 0), (7, 40, 0),
+])
+def test_fused_eval_kernel_variants_small(n_per, d, tpc):
+    n = 211
+    rs = synth.retrieval_set(n, n_per, d=d, seed=40 + d)
+    i2t, t2i = oracle.score_matrices(rs.image, rs.text)
+    want = oracle.itm_eval_by_count(i2t, t2i, rs.txt2img, rs.img2txt)
+    ev, topk = leccr_b200.fused_eval(rs.image, rs.text, rs.txt2img, rs.img2txt, k=10, tiles_per_chunk=tpc)
+    assert_ev_equal(ev, want)
+    tol = 2e-3 if d < 64 else F16_TOL  # fp16 rounding relative to the row norms; short vectors are not special-cased
+    check_topk_against(i2t, *topk["i2t"], 10, tol)
+    check_topk_against(np.ascontiguousarray(t2i), *topk["t2i"], 10, tol)
+
+
+@pytest.mark.parametrize("d", [64, 200, 256, 320])
+def test_topk_long_rows_filter_kernels(d):
+    """Long column chunks (> 32 tiles): the filter epilogue, with the resident row block (D <= 256) or the streamed
+    one (D > 256; 200 is not a multiple of the stage depth).  Sampled rows against fp32 matmul."""
+    g = torch.Generator(device="cuda").manual_seed(d)
+    gal = torch.nn.functional.normalize(torch.randn(70_000, d, device="cuda", generator=g), dim=-1)
+    qry = torch.nn.functional.normalize(gal[torch.randint(0, 70_000, (300,), device="cuda", generator=g)]
+                                        + 0.05 * torch.randn(300, d, device="cuda", generator=g), dim=-1)
+    res, = ops.sim_topk([(ops.prep(qry), ops.prep(gal), None)], k=10, tiles_per_chunk=64)
+    ref = (qry @ gal.t()).cpu().numpy()
+    check_topk_against(ref, res.val, res.idx, 10, F16_TOL)
