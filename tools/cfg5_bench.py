@@ -37,10 +37,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     try:
-        peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
-                                           "MEASURED_PEAKS.json")))["bf16_tflops"]
+        pk = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                         "MEASURED_PEAKS.json")))
+        peak, peak_sus = pk["bf16_tflops"], pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
     except Exception:
-        peak = 1590.0
+        peak = peak_sus = 1590.0
     G, Q, k = args.gallery, args.queries, 10
     gal, qry, _ = synth.cfg5_gallery(G, Q, device=dev)
     flops = 2.0 * G * Q * 256
@@ -108,6 +109,8 @@ def main():
                 "workload": f"cfg5 {G} gallery x {Q} queries d256 bf16 top{k}", "decomposition": name, "n_gpus": world,
                 "ms": ms, "queries_per_s": Q / (ms * 1e-3), "tflops_total": flops / ms / 1e9,
                 "frac_of_peak": flops / ms / 1e9 / (peak * world), "peak_tflops_per_gpu": peak,
+                # launches of tens of milliseconds run at sustained clocks: the back-to-back cuBLAS figure
+                "frac_of_sustained_peak": flops / ms / 1e9 / (peak_sus * world), "sustained_peak_tflops_per_gpu": peak_sus,
                 "sampled_rows_identical_to_fp32_topk": same, "timing": "CUDA events, best of reps, max over ranks",
                 "peer_memory": bool(peer._cache.get(("topk", Q, k)) is not None) if name == "gallery" else None}))
     if world > 1:
