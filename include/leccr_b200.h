@@ -313,6 +313,28 @@ int leccr_comm_init(const leccr_nccl_id* id_host, int rank, int world, void** co
 int leccr_comm_destroy(void* comm);
 int leccr_allgather(void* comm, const void* send, void* recv, size_t bytes_per_rank, leccr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * leccr_dstl_fwd / leccr_dstl_bwd: the distillation loss on ALL-GATHERED tensors (N = world * B rows).
+ * Replaces: RetrievalModel.dstl_loss  models/model_retrieval_caption.py:99-116 after its four allgathers
+ * (:95-98; the gathers stay with the host): logits_tv = text_t image^T, labels = softmax_rows(alpha *
+ * norm(text_s image^T) + (1 - alpha) * norm(max_n caption_n text_s^T)) (norm_score :87-90), loss =
+ * kl_div(log_softmax(logits_tv), labels, batchmean).  Backward = autograd of the same lines followed by
+ * AllGather.backward (models/xvlm.py:62-67): the local rows of d image and d text_t (labels are detached).
+ *   16-bit operands with K = 3D split precision (leccr_prep): tt16 / ts16_rows / cap16 in layout X3_ROWS,
+ *   img16 / ts16_cols in layout X3_COLS; cap16 is [n_cap * N][K], row a * N + i = query a of sample i
+ *   out: [1] loss;  Fm, TV: [N][N] fp32 label logits / text_t-image logits;  lse: [2][N]  (saved for backward)
+ *   backward: img16 / tt16 = the plain [N][D] halves of the same buffers (equal ld), dimg / dtt [row_count][D]
+ * ------------------------------------------------------------------------------------------ */
+size_t leccr_dstl_fwd_workspace(int n_cap, int64_t N);
+int leccr_dstl_fwd(const void* tt16, int64_t ld_tt, const void* ts16_rows, int64_t ld_tsr, const void* ts16_cols,
+                   int64_t ld_tsc, const void* img16, int64_t ld_img, const void* cap16, int64_t ld_cap, int n_cap,
+                   int64_t N, int K, int fmt, float alpha, float* out, float* Fm, float* TV, float* lse, void* workspace,
+                   size_t workspace_bytes, leccr_stream_t stream);
+size_t leccr_dstl_bwd_workspace(int64_t N, int64_t row_count, int D);
+int leccr_dstl_bwd(const float* Fm, const float* TV, const float* lse, const void* img16, int64_t ld_img, const void* tt16,
+                   int64_t ld_tt, int64_t N, int D, int fmt, int64_t row_begin, int64_t row_count, const float* grad_out,
+                   float* dimg, float* dtt, void* workspace, size_t workspace_bytes, leccr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,11 @@ _SIGNATURES = {
     "leccr_comm_init": (c_int, [vp, c_int, c_int, ctypes.POINTER(vp)]),
     "leccr_comm_destroy": (c_int, [vp]),
     "leccr_allgather": (c_int, [vp, vp, vp, sz, vp]),
+    "leccr_dstl_fwd_workspace": (sz, [c_int, i64]),
+    "leccr_dstl_fwd": (c_int, [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, c_int, i64, c_int, c_int, c_float, vp, vp, vp,
+                               vp, vp, sz, vp]),
+    "leccr_dstl_bwd_workspace": (sz, [i64, i64, c_int]),
+    "leccr_dstl_bwd": (c_int, [vp, vp, vp, vp, i64, vp, i64, i64, c_int, c_int, i64, i64, vp, vp, vp, vp, sz, vp]),
     "leccr_peer_barrier": (c_int, [vp, c_int, c_int, ctypes.c_uint32, vp]),
     "leccr_topk_merge_peers": (c_int, [vp, vp, c_int, c_int, i64, i64, ctypes.POINTER(i64), c_int, vp, vp, vp]),
     "leccr_stats16": (c_int, [vp, c_int, i64, c_int, i64, vp, vp, vp, vp]),

@@ -1236,6 +1236,114 @@ int leccr_topk_dense(const float* S, int64_t ld, int64_t R, int64_t C, int by_co
 
 }  // extern "C"
 
+// ------------------------------------------------------------------------------------ dstl_loss
+extern "C" {
+
+size_t leccr_dstl_fwd_workspace(int n_cap, int64_t N) {
+  if (n_cap < 1 || N <= 0) return 0;
+  const size_t nn = static_cast<size_t>(N) * N * 4;
+  return align256(nn * n_cap) + align256(nn) + align256(static_cast<size_t>(N) * 4) + 256;  // SIM, Cmax, row_loss, mm
+}
+
+int leccr_dstl_fwd(const void* tt16, int64_t ld_tt, const void* ts16_rows, int64_t ld_tsr, const void* ts16_cols,
+                   int64_t ld_tsc, const void* img16, int64_t ld_img, const void* cap16, int64_t ld_cap, int n_cap,
+                   int64_t N, int K, int fmt, float alpha, float* out, float* Fm, float* TV, float* lse, void* workspace,
+                   size_t workspace_bytes, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (tt16 == nullptr || ts16_rows == nullptr || ts16_cols == nullptr || img16 == nullptr || cap16 == nullptr ||
+      out == nullptr || Fm == nullptr || TV == nullptr || lse == nullptr || n_cap < 1 || N <= 0 || K <= 0 || bad_fmt(fmt))
+    return LECCR_ERR_ARG;
+  int rc = leccr_check_device();
+  if (rc != LECCR_OK) return rc;
+  if (workspace == nullptr || workspace_bytes < leccr_dstl_fwd_workspace(n_cap, N)) return LECCR_ERR_WORKSPACE;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const size_t nn = static_cast<size_t>(N) * N * 4;
+  float* SIM = reinterpret_cast<float*>(ws);
+  ws += align256(nn * n_cap);
+  float* Cmax = reinterpret_cast<float*>(ws);
+  ws += align256(nn);
+  float* row_loss = reinterpret_cast<float*>(ws);
+  ws += align256(static_cast<size_t>(N) * 4);
+  uint32_t* mm = reinterpret_cast<uint32_t*>(ws);
+  // logits_tv and logits_sv share one tensor-core launch; the caption similarities take a second one
+  StoreProblem sp[2] = {{tt16, img16, ld_tt, ld_img, N, N, TV, N, nullptr}, {ts16_rows, img16, ld_tsr, ld_img, N, N, Fm, N, nullptr}};
+  rc = launch_store(sp, 2, K, fmt, 1.0f, nullptr, nullptr, 1, stream);
+  if (rc != LECCR_OK) return rc;
+  StoreProblem sc = {cap16, ts16_cols, ld_cap, ld_tsc, static_cast<int64_t>(n_cap) * N, N, SIM, N, nullptr};
+  rc = launch_store(&sc, 1, K, fmt, 1.0f, nullptr, nullptr, 1, stream);
+  if (rc != LECCR_OK) return rc;
+  rc = leccr_double_sim_fuse(Fm, SIM, n_cap, static_cast<int64_t>(N) * N, Cmax, mm, alpha, 1.0f - alpha, LECCR_FUSE_NORM,
+                             stream_);
+  if (rc != LECCR_OK) return rc;
+  const int n = static_cast<int>(N);
+  dstl_rows_kernel<<<n, 256, 0, stream>>>(Fm, TV, n, lse, lse + N, row_loss);
+  LAUNCH_CHECK("dstl_rows_kernel");
+  dstl_finalize_kernel<<<1, 256, 0, stream>>>(row_loss, n, out);
+  LAUNCH_CHECK("dstl_finalize_kernel");
+  return LECCR_OK;
+}
+
+size_t leccr_dstl_bwd_workspace(int64_t N, int64_t row_count, int D) {
+  if (N <= 0 || row_count <= 0 || D <= 0) return 0;
+  const int k_chunks = static_cast<int>((N + BK - 1) / BK);
+  const int row_blocks = static_cast<int>((row_count + BM - 1) / BM);
+  const size_t parts = 2 * static_cast<size_t>(bwd_splits(k_chunks, row_blocks)) * row_count * D * 4;
+  return 2 * align256(static_cast<size_t>(row_count) * round_up8(N) * 2) +
+         2 * align256(static_cast<size_t>(D) * round_up8(N) * 2) + align256(parts) + 256;
+}
+
+int leccr_dstl_bwd(const float* Fm, const float* TV, const float* lse, const void* img16, int64_t ld_img, const void* tt16,
+                   int64_t ld_tt, int64_t N, int D, int fmt, int64_t row_begin, int64_t row_count, const float* grad_out,
+                   float* dimg, float* dtt, void* workspace, size_t workspace_bytes, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (Fm == nullptr || TV == nullptr || lse == nullptr || img16 == nullptr || tt16 == nullptr || grad_out == nullptr ||
+      dimg == nullptr || dtt == nullptr || N <= 0 || D <= 0 || bad_fmt(fmt) || row_begin < 0 || row_count <= 0 ||
+      row_begin + row_count > N)
+    return LECCR_ERR_ARG;
+  if (workspace == nullptr || workspace_bytes < leccr_dstl_bwd_workspace(N, row_count, D)) return LECCR_ERR_WORKSPACE;
+  const int64_t n8 = round_up8(N);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  uint16_t* Gr = reinterpret_cast<uint16_t*>(ws);
+  ws += align256(static_cast<size_t>(row_count) * n8 * 2);
+  uint16_t* GcT = reinterpret_cast<uint16_t*>(ws);
+  ws += align256(static_cast<size_t>(row_count) * n8 * 2);
+  uint16_t* imgT = reinterpret_cast<uint16_t*>(ws);
+  ws += align256(static_cast<size_t>(D) * n8 * 2);
+  uint16_t* ttT = reinterpret_cast<uint16_t*>(ws);
+  ws += align256(static_cast<size_t>(D) * n8 * 2);
+  const int k_chunks = static_cast<int>((N + BK - 1) / BK);
+  const int row_blocks = static_cast<int>((row_count + BM - 1) / BM);
+  const int splits = bwd_splits(k_chunks, row_blocks);
+  float* parts0 = reinterpret_cast<float*>(ws);
+  float* parts1 = parts0 + static_cast<size_t>(splits) * row_count * D;
+  ws += align256(2 * static_cast<size_t>(splits) * row_count * D * 4);
+  float* scale = reinterpret_cast<float*>(ws);
+  const int n = static_cast<int>(N);
+  if (fmt == LECCR_FMT_F16)
+    dstl_grad_kernel<0><<<n, 256, 0, stream>>>(Fm, TV, n, (int)n8, lse, lse + N, (int)row_begin, (int)row_count, grad_out,
+                                              Gr, GcT, scale);
+  else
+    dstl_grad_kernel<1><<<n, 256, 0, stream>>>(Fm, TV, n, (int)n8, lse, lse + N, (int)row_begin, (int)row_count, grad_out,
+                                              Gr, GcT, scale);
+  LAUNCH_CHECK("dstl_grad_kernel");
+  {
+    dim3 grid(static_cast<unsigned>((n8 + 31) / 32), static_cast<unsigned>((D + 31) / 32), 2);
+    dim3 block(32, 8);
+    if (ld_img != ld_tt) return LECCR_ERR_ARG;
+    transpose16_pair_kernel<<<grid, block, 0, stream>>>(static_cast<const uint16_t*>(img16), static_cast<const uint16_t*>(tt16),
+                                                       ld_img, n, D, imgT, ttT, n8);
+    LAUNCH_CHECK("transpose16_pair_kernel");
+  }
+  // d text_t[loc] = Gr image * s ;  d image[loc] = GcT text_t * s    (s = grad_out / N^2)
+  StoreProblem sp[2] = {
+      {Gr, imgT, n8, n8, row_count, D, dtt, D, parts0},
+      {GcT, ttT, n8, n8, row_count, D, dimg, D, parts1},
+  };
+  return launch_store(sp, 2, n, fmt, 1.0f, scale, nullptr, splits, stream);
+}
+
+}  // extern "C"
+
 // ------------------------------------------------------------------------------------ NCCL collectives
 // For hosts without torch.distributed (and for node-crossing groups, where peer memory does not reach): the two
 // collectives of the path as thin C entries over NCCL.  libnccl.so.2 is resolved at run time (dlopen: the copy

@@ -1285,4 +1285,106 @@ __global__ void topk_dense_kernel(const float* __restrict__ S, long long ld_r, l
   }
 }
 
+// --------------------------------------------------------------------------------
+// dstl_loss: models/model_retrieval_caption.py:94-116 on the gathered tensors
+//   labels = softmax_rows(alpha * norm(text_s image^T) + (1 - alpha) * norm(max_n caption_n text_s^T))
+//   loss   = KL(labels || softmax_rows(text_t image^T)), reduction batchmean
+// F (the fused label logits, from leccr_double_sim_fuse: its norm differs from the reference's positive variant
+// by the constant +1 per term, which a row softmax cancels) and TV = text_t image^T are materialised [N][N].
+// --------------------------------------------------------------------------------
+// One block per row: both log-sum-exps (natural units), then the row's KL term.
+__global__ void dstl_rows_kernel(const float* __restrict__ Fm, const float* __restrict__ TV, int N,
+                                 float* __restrict__ lse_f, float* __restrict__ lse_t, float* __restrict__ row_loss) {
+  __shared__ float sm[2][8], sl[2][8];
+  __shared__ float s_lse[2];
+  __shared__ float s_red[8];
+  const int r = blockIdx.x;
+  const float* f = Fm + static_cast<long long>(r) * N;
+  const float* t = TV + static_cast<long long>(r) * N;
+  const float L2E = 1.4426950408889634f;
+  float mf = -CUDART_INF_F, lf = 0.f, mt = -CUDART_INF_F, lt = 0.f, dummy = 0.f, d2 = 0.f;
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    lse_combine(mf, lf, dummy, f[c] * L2E, 1.f, 0.f);
+    lse_combine(mt, lt, d2, t[c] * L2E, 1.f, 0.f);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lse_combine(mf, lf, dummy, __shfl_xor_sync(0xffffffffu, mf, o), __shfl_xor_sync(0xffffffffu, lf, o), 0.f);
+    lse_combine(mt, lt, d2, __shfl_xor_sync(0xffffffffu, mt, o), __shfl_xor_sync(0xffffffffu, lt, o), 0.f);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    sm[0][warp] = mf;
+    sl[0][warp] = lf;
+    sm[1][warp] = mt;
+    sl[1][warp] = lt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < (blockDim.x >> 5); ++k) {
+      lse_combine(mf, lf, dummy, sm[0][k], sl[0][k], 0.f);
+      lse_combine(mt, lt, d2, sm[1][k], sl[1][k], 0.f);
+    }
+    s_lse[0] = (mf + log2f(lf)) * 0.6931471805599453f;
+    s_lse[1] = (mt + log2f(lt)) * 0.6931471805599453f;
+    lse_f[r] = s_lse[0];
+    lse_t[r] = s_lse[1];
+  }
+  __syncthreads();
+  const float LF = s_lse[0], LT = s_lse[1];
+  float acc = 0.f;
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    const float lf_c = f[c] - LF;  // log labels
+    acc += __expf(lf_c) * (lf_c - (t[c] - LT));
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) s_red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int k = 0; k < (blockDim.x >> 5); ++k) tot += s_red[k];
+    row_loss[r] = tot;
+  }
+}
+
+__global__ void dstl_finalize_kernel(const float* __restrict__ row_loss, int N, float* __restrict__ out) {
+  __shared__ double red[8];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) a += static_cast<double>(row_loss[i]);
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < (blockDim.x >> 5); ++k) t += red[k];
+    out[0] = static_cast<float>(t / N);
+  }
+}
+
+// Backward strips for the local rows [row0, row0 + nloc): G''_rc = (softmax(TV)_rc - labels_rc) * N  (O(1)),
+// rows -> Gr [nloc][ld] (for d text_t = Gr image), columns -> GcT [nloc][ld] (GcT[c - row0][r], for
+// d image = GcT text_t); scale[0] = grad_out / N^2 is applied in fp32 by the products' epilogue.
+template <int FMT>
+__global__ void dstl_grad_kernel(const float* __restrict__ Fm, const float* __restrict__ TV, int N, int ld,
+                                 const float* __restrict__ lse_f, const float* __restrict__ lse_t, int row0, int nloc,
+                                 const float* __restrict__ grad_out, uint16_t* __restrict__ Gr,
+                                 uint16_t* __restrict__ GcT, float* __restrict__ scale) {
+  const int r = blockIdx.x;
+  if (r == 0 && threadIdx.x == 0) scale[0] = __ldg(grad_out) / (static_cast<float>(N) * static_cast<float>(N));
+  const float LF = lse_f[r], LT = lse_t[r];
+  const float* f = Fm + static_cast<long long>(r) * N;
+  const float* t = TV + static_cast<long long>(r) * N;
+  const bool local_row = r >= row0 && r < row0 + nloc;
+  const float fn = static_cast<float>(N);
+  if (local_row) {
+    uint16_t* o = Gr + static_cast<long long>(r - row0) * ld;
+    for (int c = threadIdx.x; c < ld; c += blockDim.x)
+      o[c] = f32_to_16<FMT>(c < N ? (__expf(t[c] - LT) - __expf(f[c] - LF)) * fn : 0.f);
+  }
+  for (int c = row0 + threadIdx.x; c < row0 + nloc; c += blockDim.x)
+    GcT[static_cast<long long>(c - row0) * ld + r] = f32_to_16<FMT>((__expf(t[c] - LT) - __expf(f[c] - LF)) * fn);
+  if (r == 0)  // pad columns of the transposed strip
+    for (int i = threadIdx.x; i < nloc * (ld - N); i += blockDim.x)
+      GcT[static_cast<long long>(i / (ld - N)) * ld + N + i % (ld - N)] = 0;
+}
+
 }  // namespace leccr

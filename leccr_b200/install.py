@@ -12,6 +12,7 @@ import importlib
 from . import allgather as _ag
 from . import caption_loss as _cl
 from . import contrastive as _ct
+from . import dstl_loss as _dl
 from . import evaluation as _ev
 
 
@@ -38,7 +39,8 @@ def install(modules=("models.xvlm", "models.xvlm_video")):
 
 def install_caption_loss(modules=("models.model_retrieval_caption", "models.video_model_retrieval_caption")):
     """Rebind RetrievalModel.get_caption_contrastive_loss (models/model_retrieval_caption.py:145,
-    models/video_model_retrieval_caption.py:171) in the model modules that are importable."""
+    models/video_model_retrieval_caption.py:171) and RetrievalModel.dstl_loss (:94) in the model modules that
+    are importable."""
     done = []
     for name in modules:
         try:
@@ -48,6 +50,8 @@ def install_caption_loss(modules=("models.model_retrieval_caption", "models.vide
         cls = getattr(mod, "RetrievalModel", None)
         if cls is not None and hasattr(cls, "get_caption_contrastive_loss"):
             cls.get_caption_contrastive_loss = _cl.get_caption_contrastive_loss
+            if hasattr(cls, "dstl_loss"):
+                cls.dstl_loss = _dl.dstl_loss  # models/model_retrieval_caption.py:94
             done.append(name)
     return done
 

@@ -89,6 +89,42 @@ def caption_contrastive_loss_and_grads(caption_embeds, text_feats, temp: float, 
     return loss.detach(), c.grad, t.grad, tp.grad.detach()
 
 
+def norm_score_pos(score: torch.Tensor) -> torch.Tensor:
+    """models/model_retrieval_caption.py:87-90 (the POSITIVE variant used in training): (x - min) / max(x - min)."""
+    score = score - torch.min(score)
+    score = score / torch.max(score)
+    return score
+
+
+def dstl_loss(image_all, caption_all, text_s_all, text_t_all, alpha: float = 0.8) -> torch.Tensor:
+    """models/model_retrieval_caption.py:94-116 on the ALL-GATHERED tensors (the gathers themselves are
+    allgather_forward), statement for statement, including the reference's mixed orientation of the two label
+    terms (logits_sv is text x image, logits_sc is caption-sample x text)."""
+    logits_tv = text_t_all @ image_all.t()
+    logits_sv = text_s_all @ image_all.t()
+    n, bsz, d = caption_all.shape
+    sim = caption_all.reshape(-1, d) @ text_s_all.transpose(0, 1)
+    logits_sc = torch.max(sim.reshape(n, bsz, bsz), dim=0)[0]
+    logits_sc = norm_score_pos(logits_sc)
+    logits_sv = norm_score_pos(logits_sv)
+    labels = alpha * logits_sv + (1. - alpha) * logits_sc
+    labels = F.softmax(labels, 1)
+    logits_tv = F.log_softmax(logits_tv, 1)
+    return F.kl_div(logits_tv, labels.detach(), reduction='batchmean')
+
+
+def dstl_loss_and_grads(image_all, caption_all, text_s_all, text_t_all, alpha: float = 0.8, rank: int = 0,
+                        batch_size: Optional[int] = None, dtype=torch.float32):
+    """Loss and what autograd hands back to rank `rank`: the local rows of d image and d text_t (labels are
+    detached, so text_s and the captions get no gradient)."""
+    im = image_all.detach().to(dtype).clone().requires_grad_(True)
+    tt = text_t_all.detach().to(dtype).clone().requires_grad_(True)
+    loss = dstl_loss(im, caption_all.detach().to(dtype), text_s_all.detach().to(dtype), tt, alpha)
+    loss.backward()
+    bs = im.shape[0] if batch_size is None else batch_size
+    return loss.detach(), allgather_backward(im.grad, rank, bs), allgather_backward(tt.grad, rank, bs)
+
+
 # ----------------------------------------------------------------------------- evaluation score matrices
 def score_matrices(image_embeds: torch.Tensor, text_embeds: torch.Tensor):
     """image_Retrieval_caption.py:151-152,163: i2t = image @ text.T, t2i = its transpose VIEW, as numpy."""

@@ -451,3 +451,54 @@ def test_topk_long_rows_filter_kernels(d):
     res, = ops.sim_topk([(ops.prep(qry), ops.prep(gal), None)], k=10, tiles_per_chunk=64)
     ref = (qry @ gal.t()).cpu().numpy()
     check_topk_against(ref, res.val, res.idx, 10, F16_TOL)
+
+
+# ----------------------------------------------------------------------------- dstl_loss (8f rank 2)
+def test_dstl_loss_against_reference_golden(golden):
+    """dstl_loss vs the reference's own function under gloo with 1 and 2 ranks (tests/golden/dstl_loss.npz): the
+    2-rank case is replayed on one GPU from the gathered tensors, rank by rank.  Loss 1e-3 relative, gradients
+    3e-3 relative (16-bit gradient strips)."""
+    g = golden("dstl_loss.npz")
+    for name in ("w1", "w2"):
+        world = int(g[f"{name}_world"])
+        image, cap = torch.from_numpy(g[f"{name}_image"]), torch.from_numpy(g[f"{name}_caption"])
+        ts, tt = torch.from_numpy(g[f"{name}_text_s"]), torch.from_numpy(g[f"{name}_text_t"])
+        B = image.shape[0] // world
+        for rank in range(world):
+            im = image.cuda().requires_grad_(True)
+            t_t = tt.cuda().requires_grad_(True)
+            if world == 1:   # through the drop-in method itself
+                loss = leccr_b200.dstl_loss(types.SimpleNamespace(), im, cap.cuda(), ts.cuda(), t_t, None,
+                                            alpha=float(g[f"{name}_alpha"]))
+            else:
+                loss = leccr_b200.dstl_loss_gathered(im, cap.cuda(), ts.cuda(), t_t, float(g[f"{name}_alpha"]), rank * B, B)
+            loss.backward()
+            want = float(g[f"{name}_r{rank}_loss"])
+            assert abs(loss.item() - want) <= 1e-3 * abs(want), (loss.item(), want)
+            sl = slice(rank * B, (rank + 1) * B)
+            for got, ref in ((im.grad[sl].cpu().double(), torch.from_numpy(g[f"{name}_r{rank}_dimage"]).double()),
+                             (t_t.grad[sl].cpu().double(), torch.from_numpy(g[f"{name}_r{rank}_dtext_t"]).double())):
+                assert (got - ref).norm() <= 3e-3 * ref.norm(), ((got - ref).norm().item(), ref.norm().item())
+            if world > 1:   # rows outside the rank's slice get no gradient (AllGather.backward drops them)
+                mask = torch.ones(image.shape[0], dtype=torch.bool)
+                mask[sl] = False
+                assert not im.grad.cpu()[mask].any() and not t_t.grad.cpu()[mask].any()
+
+
+def test_dstl_loss_training_size_against_oracle():
+    """N = 1024 gathered rows (2 x 512), n = 2 caption queries, D = 256, local rows of rank 1, vs the fp64 oracle."""
+    g = torch.Generator().manual_seed(77)
+    nrm = torch.nn.functional.normalize
+    N_, d, n = 1024, 256, 2
+    image = nrm(torch.randn(N_, d, generator=g), dim=-1)
+    ts = nrm(image + (1.5 * 4 / d ** 0.5) * torch.randn(N_, d, generator=g), dim=-1)
+    tt = nrm(image + (1.5 * 4 / d ** 0.5) * torch.randn(N_, d, generator=g), dim=-1)
+    cap = ts[None] + (2.0 / d ** 0.5) * torch.randn(n, N_, d, generator=g)
+    w_loss, w_dim, w_dtt = oracle.dstl_loss_and_grads(image, cap, ts, tt, 0.8, rank=1, batch_size=512, dtype=torch.float64)
+    im = image.cuda().requires_grad_(True)
+    t_t = tt.cuda().requires_grad_(True)
+    loss = leccr_b200.dstl_loss_gathered(im, cap.cuda(), ts.cuda(), t_t, 0.8, 512, 512)
+    loss.backward()
+    assert abs(loss.item() - w_loss.item()) <= 1e-3 * abs(w_loss.item()), (loss.item(), w_loss.item())
+    for got, ref in ((im.grad[512:].cpu().double(), w_dim), (t_t.grad[512:].cpu().double(), w_dtt)):
+        assert (got - ref).norm() <= 3e-3 * ref.norm(), ((got - ref).norm().item(), ref.norm().item())

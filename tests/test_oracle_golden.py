@@ -119,3 +119,19 @@ def test_caption_contrastive_loss_matches_reference(golden):
         assert np.abs(dc.numpy() - g[f"{c}_dcaption"]).max() <= 1e-6 * max(1e-6, np.abs(g[f"{c}_dcaption"]).max())
         assert np.abs(dt.numpy() - g[f"{c}_dtext"]).max() <= 1e-6 * max(1e-6, np.abs(g[f"{c}_dtext"]).max())
         assert abs(dtemp.item() - float(g[f"{c}_dtemp"])) <= 1e-5 * abs(float(g[f"{c}_dtemp"]))
+
+
+def test_dstl_loss_matches_reference(golden):
+    """oracle.dstl_loss vs the reference's dstl_loss run under gloo with 1 and 2 ranks (oracle/make_golden_dstl.py)."""
+    g = golden("dstl_loss.npz")
+    for name in ("w1", "w2"):
+        world = int(g[f"{name}_world"])
+        image, cap = torch.from_numpy(g[f"{name}_image"]), torch.from_numpy(g[f"{name}_caption"])
+        ts, tt = torch.from_numpy(g[f"{name}_text_s"]), torch.from_numpy(g[f"{name}_text_t"])
+        B = image.shape[0] // world
+        for rank in range(world):
+            loss, dim, dtt = oracle.dstl_loss_and_grads(image, cap, ts, tt, float(g[f"{name}_alpha"]), rank, B)
+            want = float(g[f"{name}_r{rank}_loss"])
+            assert abs(loss.item() - want) <= 2e-6 * abs(want) + 1e-9
+            for got, ref in ((dim, g[f"{name}_r{rank}_dimage"]), (dtt, g[f"{name}_r{rank}_dtext_t"])):
+                assert np.abs(got.numpy() - ref).max() <= 1e-5 * np.abs(ref).max() + 1e-10

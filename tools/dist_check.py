@@ -52,6 +52,25 @@ paths = {str(k_[0]): (v_ is not None) for k_, v_ in _peer._cache.items()}
 print(f"rank {rank}: sharded eval == golden {ev_ok}; gallery-partition merge == single pass {merge_ok}; peer-memory paths used: {paths}", flush=True)
 if os.environ.get("LECCR_PEER", "1") != "0":
     ok &= paths.get("itc", False) and paths.get("topk", False)  # on a B200 NVLink box the peer kernels must be what ran
+# ---- dstl_loss and the caption contrastive loss through their drop-ins on W ranks, vs the oracle on the gathered batch
+gd = torch.Generator().manual_seed(5)
+nrm = torch.nn.functional.normalize
+Nd, nq = B * world, 2
+d_img = nrm(torch.randn(Nd, 256, generator=gd), dim=-1)
+d_ts = nrm(d_img + 0.4 * torch.randn(Nd, 256, generator=gd), dim=-1)
+d_tt = nrm(d_img + 0.4 * torch.randn(Nd, 256, generator=gd), dim=-1)
+d_cap = d_ts[None] + 0.1 * torch.randn(nq, Nd, 256, generator=gd)
+sl = slice(rank * B, (rank + 1) * B)
+im_l = d_img[sl].cuda().requires_grad_(True)
+tt_l = d_tt[sl].cuda().requires_grad_(True)
+dl = leccr_b200.dstl_loss(types.SimpleNamespace(), im_l, d_cap[:, sl].cuda(), d_ts[sl].cuda(), tt_l, None, alpha=0.8)
+dl.backward()
+w_l, w_dim, w_dtt = oracle.dstl_loss_and_grads(d_img, d_cap, d_ts, d_tt, 0.8, rank=rank, batch_size=B, dtype=torch.float64)
+e = [abs(dl.item() - w_l.item()) / abs(w_l.item()), ((im_l.grad.cpu().double() - w_dim).norm() / w_dim.norm()).item(),
+     ((tt_l.grad.cpu().double() - w_dtt).norm() / w_dtt.norm()).item()]
+dstl_ok = e[0] < 1e-3 and e[1] < 3e-3 and e[2] < 3e-3
+ok &= dstl_ok
+print(f"rank {rank}: dstl_loss {dl.item():.6f} rel {e[0]:.1e} dimage {e[1]:.1e} dtext_t {e[2]:.1e} {'PASS' if dstl_ok else 'FAIL'}", flush=True)
 # ---- the C-ABI NCCL entries (hosts without torch.distributed): communicator from a broadcast unique id,
 # all-gather of this rank's top-k lists, merge over a table of pointers into the gathered buffer
 import ctypes
