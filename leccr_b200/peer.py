@@ -137,11 +137,13 @@ def itc_slot(B: int, D: int, fmt: int, device):
     return pb.table(off), pb.table(off + rows_bytes), pb.flag_table, pb.epoch, pb.buf.data_ptr() + off
 
 
-def merge_topk_peers(val, idx, shard_offset: int, k: int, all_queries: bool = True, offsets=None):
+def merge_topk_peers(val, idx, shard_offset: int, k: int, all_queries: bool = True, offsets=None, ranks=None):
     """Row-partitioned gallery exchange: publish this rank's [Q, k_in] local lists, barrier, then pull + merge.
     Returns (val [Q', k], idx int32 [Q', k] global columns, (q_begin, q_end)) where Q' is all queries
     (all_queries) or this rank's balanced slice.  offsets: optional list of every rank's shard_offset.
-    None when peer exchange is not available."""
+    ranks: optional sub-group (a 2-D decomposition: the ranks that hold the other gallery parts for the SAME
+    query shard); lists are pulled from those ranks only, offsets then lists THEIR shard offsets, and the
+    slice is balanced over them.  None when peer exchange is not available."""
     from .sharding import shard_range
 
     dev = val.device
@@ -165,13 +167,26 @@ def merge_topk_peers(val, idx, shard_offset: int, k: int, all_queries: bool = Tr
         dist.all_gather_into_tensor(all_offs, offs)  # 8 bytes per rank (the host needs them)
         host_offs = all_offs.cpu().tolist()
     pb.barrier()
-    qb, qe = (0, Q) if all_queries else shard_range(Q, rank, world)
-    out_v = torch.empty((qe - qb, k), dtype=torch.float32, device=dev)
-    out_i = torch.empty((qe - qb, k), dtype=torch.int32, device=dev)
     import ctypes
 
-    arr = (ctypes.c_int64 * world)(*host_offs)
-    N.check(lib.leccr_topk_merge_peers(N.ptr(pb.table(off)), N.ptr(pb.table(off + Q * k_in * 4)), world, k_in, qb,
-                                       qe - qb, arr, k, N.ptr(out_v), N.ptr(out_i), N.stream_ptr()),
-            "leccr_topk_merge_peers")
+    if ranks is None:
+        group = list(range(world))
+        vt, it = pb.table(off), pb.table(off + Q * k_in * 4)
+    else:
+        group = [int(r) for r in ranks]
+        key = (off, tuple(group))
+        tabs = pb._tables.get(key)
+        if tabs is None:
+            tabs = (torch.tensor([pb.ptrs[r] + off for r in group], dtype=torch.int64, device=dev),
+                    torch.tensor([pb.ptrs[r] + off + Q * k_in * 4 for r in group], dtype=torch.int64, device=dev))
+            pb._tables[key] = tabs
+        vt, it = tabs
+        if len(host_offs) != len(group):
+            host_offs = [host_offs[r] for r in group]
+    qb, qe = (0, Q) if all_queries else shard_range(Q, group.index(rank), len(group))
+    out_v = torch.empty((qe - qb, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((qe - qb, k), dtype=torch.int32, device=dev)
+    arr = (ctypes.c_int64 * len(group))(*host_offs)
+    N.check(lib.leccr_topk_merge_peers(N.ptr(vt), N.ptr(it), len(group), k_in, qb, qe - qb, arr, k, N.ptr(out_v),
+                                       N.ptr(out_i), N.stream_ptr()), "leccr_topk_merge_peers")
     return out_v, out_i, (qb, qe)

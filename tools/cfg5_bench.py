@@ -103,6 +103,26 @@ def main():
         ms, (mv, mi, (mb, me)) = timed(gallery_step)
         same = check(mv, mi, mb, me, "gallery")
         results.append(("gallery", ms, same))
+    # ---- 2-D: query shards x gallery parts (P = 2 gallery halves): rows stay long (G / 2 columns), the merge
+    #      involves only the P ranks that share a query shard
+    if world >= 4 and world % 2 == 0:
+        P = 2
+        qs, gp = rank // P, rank % P
+        qb2, qe2 = sharding.shard_range(Q, qs, world // P)
+        gb2, ge2 = sharding.shard_range(G, gp, P)
+        Q2, G2 = Qop.rows(qb2, qe2), Gop.rows(gb2, ge2)
+        grp = [qs * P + i for i in range(P)]
+        offs2 = [sharding.shard_range(G, i, P)[0] for i in range(P)]
+
+        def step2d():
+            (r,) = ops.sim_topk([(Q2, G2, None)], k=k)
+            return peer.merge_topk_peers(r.val, r.idx, gb2, k, all_queries=False, offsets=offs2, ranks=grp)
+
+        ms, out2 = timed(step2d)
+        if out2 is not None:
+            mv, mi, (mb, me) = out2
+            same = check(mv, mi, qb2 + mb, qb2 + me, "2d")
+            results.append((f"query x gallery ({world // P} x {P})", ms, same))
     if rank == 0:
         for name, ms, same in results:
             print(json.dumps({
@@ -112,7 +132,7 @@ def main():
                 # launches of tens of milliseconds run at sustained clocks: the back-to-back cuBLAS figure
                 "frac_of_sustained_peak": flops / ms / 1e9 / (peak_sus * world), "sustained_peak_tflops_per_gpu": peak_sus,
                 "sampled_rows_identical_to_fp32_topk": same, "timing": "CUDA events, best of reps, max over ranks",
-                "peer_memory": bool(peer._cache.get(("topk", Q, k)) is not None) if name == "gallery" else None}))
+                "peer_memory": None if name == "query" else any(kk[0] == "topk" and v is not None for kk, v in peer._cache.items())}))
     if world > 1:
         dist.destroy_process_group()
 
