@@ -502,3 +502,23 @@ def test_dstl_loss_training_size_against_oracle():
     assert abs(loss.item() - w_loss.item()) <= 1e-3 * abs(w_loss.item()), (loss.item(), w_loss.item())
     for got, ref in ((im.grad[512:].cpu().double(), w_dim), (t_t.grad[512:].cpu().double(), w_dtt)):
         assert (got - ref).norm() <= 3e-3 * ref.norm(), ((got - ref).norm().item(), ref.norm().item())
+
+
+# ----------------------------------------------------------------------------- edge cases of the fused path
+@pytest.mark.parametrize("n,per,d,k", [(1, 1, 8, 1), (2, 3, 16, 6), (17, 1, 64, 16), (130, 2, 256, 16), (300, 1, 24, 10)])
+def test_fused_eval_tiny_shapes_and_k_extremes(n, per, d, k):
+    """Fewer columns than k, single rows, k = 1 and k = 16 (the list length), D below one pipeline stage."""
+    rs = synth.retrieval_set(n, per, d=d, seed=n * 7 + d)
+    i2t, t2i = oracle.score_matrices(rs.image, rs.text)
+    want = oracle.itm_eval_by_count(i2t, t2i, rs.txt2img, rs.img2txt)
+    ev, topk = leccr_b200.fused_eval(rs.image, rs.text, rs.txt2img, rs.img2txt, k=k)
+    assert_ev_equal(ev, want)
+    for name, S in (("i2t", i2t), ("t2i", np.ascontiguousarray(t2i))):
+        val, idx = topk[name][0].cpu().numpy(), topk[name][1].cpu().numpy().astype(np.int64)
+        kk = min(k, S.shape[1])
+        wv = np.sort(S, axis=1)[:, ::-1][:, :kk]
+        tol = 3e-3 if d < 64 else F16_TOL
+        assert np.abs(val[:, :kk] - wv).max() < tol
+        assert np.abs(np.take_along_axis(S, idx[:, :kk], 1) - wv).max() < 2 * tol
+        if kk < k:   # fewer columns than k: the tail is padding
+            assert (idx[:, kk:] == -1).all() and np.isneginf(val[:, kk:]).all()
