@@ -9,16 +9,17 @@ rebinding is all a maintainer has to do; nothing else in the reference changes.
 """
 import importlib
 
-from . import allgather as _ag
+from .allgather import AllGather as _AllGather  # (the package attribute `allgather` is the function, not the module)
+from .allgather import allgather as _allgather
 from . import caption_loss as _cl
 from . import contrastive as _ct
-from . import dstl_loss as _dl
+from .dstl_loss import dstl_loss as _dstl_loss  # (same shadowing: the package attribute is the function)
 from . import evaluation as _ev
 
 
 def _patch_xvlm(mod, base_name):
-    mod.AllGather = _ag.AllGather
-    mod.allgather = _ag.allgather
+    mod.AllGather = _AllGather
+    mod.allgather = _allgather
     base = getattr(mod, base_name, None)
     if base is not None:
         base.get_contrastive_loss = _ct.get_contrastive_loss
@@ -51,7 +52,7 @@ def install_caption_loss(modules=("models.model_retrieval_caption", "models.vide
         if cls is not None and hasattr(cls, "get_caption_contrastive_loss"):
             cls.get_caption_contrastive_loss = _cl.get_caption_contrastive_loss
             if hasattr(cls, "dstl_loss"):
-                cls.dstl_loss = _dl.dstl_loss  # models/model_retrieval_caption.py:94
+                cls.dstl_loss = _dstl_loss  # models/model_retrieval_caption.py:94
             done.append(name)
     return done
 

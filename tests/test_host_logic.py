@@ -142,3 +142,41 @@ def test_merge_topk_lists_matches_global_topk():
     mv, mi = sharding.merge_topk(torch.stack(parts_v), torch.stack(parts_i), k)
     wv, wi = torch.topk(scores, k, dim=1)
     assert torch.equal(mv, wv) and torch.equal(mi, wi)
+
+
+def test_install_rebinds_the_reference_names():
+    """install() / install_caption_loss() / install_scripts() replace exactly the names the
+    reference resolves at call time.  Needs the reference tree (build container only)."""
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        pytest.skip("reference tree not present on this machine")
+    import importlib
+    import types
+
+    import leccr_b200
+    import leccr_b200.install as inst
+
+    ref_loader.load()  # stubs for the reference's missing third-party modules + sys.path
+    done = inst.install()
+    assert "models.xvlm" in done
+    xvlm = importlib.import_module("models.xvlm")
+    assert xvlm.AllGather is leccr_b200.AllGather and xvlm.allgather is leccr_b200.allgather
+    assert xvlm.XVLMBase.get_contrastive_loss is leccr_b200.get_contrastive_loss
+    done = inst.install_caption_loss()
+    assert "models.model_retrieval_caption" in done
+    mrc = importlib.import_module("models.model_retrieval_caption")
+    assert mrc.RetrievalModel.get_caption_contrastive_loss is leccr_b200.get_caption_contrastive_loss
+    assert mrc.RetrievalModel.dstl_loss is leccr_b200.dstl_loss
+    script = types.ModuleType("fake_task_script")
+    inst.install_scripts(image_module=script)
+    assert script.itm_eval is leccr_b200.itm_eval and callable(script.evaluation_coarse)
+    # the signatures the reference calls with still bind (models/model_retrieval_caption.py:187-193,
+    # image_Retrieval_caption.py:453-459)
+    import inspect
+
+    assert list(inspect.signature(leccr_b200.get_contrastive_loss).parameters) == ["self", "image_feat", "text_feat", "idx"]
+    assert list(inspect.signature(leccr_b200.get_caption_contrastive_loss).parameters) == ["self", "caption_embeds", "text_feats"]
+    assert list(inspect.signature(leccr_b200.dstl_loss).parameters) == ["self", "image_embeds", "caption_embeds", "text_embeds_s", "text_embeds_t", "idx", "alpha"]
+    assert list(inspect.signature(leccr_b200.itm_eval).parameters) == ["scores_i2t", "scores_t2i", "txt2img", "img2txt"]
+    assert list(inspect.signature(script.evaluation_coarse).parameters) == ["model", "data_loader", "tokenizer", "device", "config"]
