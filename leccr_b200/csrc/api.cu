@@ -450,6 +450,11 @@ using TopK1D = EpiTopK<LECCR_TOPK_KP, 64, 1, 1>;  // dense-only build of TopK1 (
 // their 130 KB of lists fit beside the pipeline because its stages are half as deep (K = 32, 64-byte swizzle).
 using TopK2D = EpiTopK<LECCR_TOPK_KP, 64, 2, 1>;
 constexpr int kBK2 = 32;
+// Long column chunks (cfg5): the filter epilogue on ONE warp per scheduler costs 6-8 % against the mainloop and
+// its hit handling another 10 %; TopK2F runs it on two warpgroups (half the columns of every tile each) with
+// 31-entry lists, which fit beside the resident row block and three K = 64 stages (hits are rare on long rows,
+// so short lists cost few extra shrink rounds).
+using TopK2F = EpiTopK<LECCR_TOPK_KP, 31, 2, 0>;
 constexpr int kMaxTopkChunks = 8;  // topk_finalize holds n_chunks * kWGs * (C / 32) <= 16 slots per lane
 
 static bool topk_two_wgs_allowed() {
@@ -537,22 +542,25 @@ static int topk_core(const leccr_topk_problem* probs, const leccr_topk_stream* s
   const bool dense_launch = topk_dense(plans, n_prob, gemm_mask);
   // a problem's lists must have ONE shape over all its calls: streamed problems (two_hint) say so themselves
   const bool two = two_hint >= 0 ? (two_hint == 1) : (topk_two_wgs_allowed() && dense_launch);
-  const int wgs = two ? 2 : 1;
-  const int cap = TopK1::C;
+  const bool two_f = !two && topk_two_wgs_allowed();  // filter epilogue on two warpgroups
+  const int wgs = (two || two_f) ? 2 : 1;
+  const int cap = two_f ? TopK2F::C : TopK1::C;
   const int bk = two ? kBK2 : BK;
   L.k_chunks = (D + bk - 1) / bk;
   TopK1::Params EP;  // all shapes share the parameter layout
-  static_assert(sizeof(TopK1::Params) == sizeof(TopK2D::Params), "parameter layouts must agree");
+  static_assert(sizeof(TopK1::Params) == sizeof(TopK2D::Params) && sizeof(TopK1::Params) == sizeof(TopK2F::Params),
+                "parameter layouts must agree");
   memset(&EP, 0, sizeof(EP));
   if (const char* dbg = getenv("LECCR_TOPK_DEBUG")) EP.debug_mode = atoi(dbg);  // measurement aid only
   // shrink rounds start when a list holds more than `trig`; long chunks prefer fresher thresholds
   // (fewer candidates pass), short ones fewer rounds (measured optimum is flat between 36 and 56)
-  EP.trig = plans[0].tiles_per_chunk >= 64 ? 40 : TopK1::TRIG;
+  EP.trig = two_f ? TopK2F::TRIG : (plans[0].tiles_per_chunk >= 64 ? 40 : TopK1::TRIG);
   // short column chunks never leave the warm-up regime: run them without the filter (measured: cfg2
   // 342 -> 304 us; long chunks are better off filtering: 12,500 x 1M 1202 vs 832 TFLOP/s)
   EP.dense = dense_launch ? 1 : 0;
   if (const char* dn = getenv("LECCR_TOPK_DENSE")) EP.dense = atoi(dn);  // measurement aid
-  if (two) EP.dense = 1;  // the two-warpgroup shape exists as a dense-only build
+  if (two) EP.dense = 1;  // the two-warpgroup shape for short chunks exists as a dense-only build
+  if (two_f) EP.dense = 0;
   if (const char* tg = getenv("LECCR_TOPK_TRIG")) EP.trig = std::min(EP.trig, std::max(LECCR_TOPK_KP + 4, atoi(tg)));
   if (const char* dc = getenv("LECCR_TOPK_COUNTERS")) {  // measurement aid only: device address (hex) of 5 x u64
     EP.debug_counters = reinterpret_cast<unsigned long long*>(strtoull(dc, nullptr, 16));
@@ -593,8 +601,8 @@ static int topk_core(const leccr_topk_problem* probs, const leccr_topk_stream* s
       item_base += plans[p].row_blocks * plans[p].n_chunks;
       // every owner of a row (column chunks of this call, earlier calls, the other warpgroup) cooperates
       // through a shared per-row threshold
-      if (o.sub_total > 1 || two) EP.row_thr[g] = row_thr;
-      if (two) EP.row_h8[g] = row_thr + q.n_rows;
+      if (o.sub_total > 1 || wgs == 2) EP.row_thr[g] = row_thr;
+      if (wgs == 2) EP.row_h8[g] = row_thr + q.n_rows;
       EP.out_val[g] = cand_val[p];
       EP.out_idx[g] = cand_idx[p];
       EP.out_cnt[g] = cand_cnt[p];
@@ -617,6 +625,11 @@ static int topk_core(const leccr_topk_problem* probs, const leccr_topk_stream* s
       static_assert(sizeof(TopK1D::Params) == sizeof(TopK1::Params), "parameter layouts must agree");
       memcpy(&EPD, &EP, sizeof(EPD));
       rc = launch_gemm<TopK1D>(L, EPD, stream);
+    } else if (two_f) {
+      TopK2F::Params EPF;
+      memcpy(&EPF, &EP, sizeof(EPF));
+      if (L.k_chunks <= kAResChunks && topk_a_resident()) rc = launch_gemm<TopK2F, BK, true>(L, EPF, stream);
+      else rc = launch_gemm<TopK2F>(L, EPF, stream);
     } else if (L.k_chunks <= kAResChunks && topk_a_resident()) {
       rc = launch_gemm<TopK1, BK, true>(L, EP, stream);  // row block resident, only the gallery streams
     } else {

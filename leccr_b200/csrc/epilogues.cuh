@@ -158,13 +158,16 @@ struct EpiTopK {
   static constexpr bool kSplitCols = WGS > 1;  // two warpgroups: each takes half the columns of every tile
   static constexpr int C = C_;           // list capacity
   static constexpr int ES = 8;           // bytes per list entry: (score, column) interleaved so an append is ONE 64-bit store
-  static constexpr int LDSW = 2 * C + 2; // row pitch in words (even: 8-byte aligned entries; 64-bit per-thread accesses conflict-free)
+  // row pitch in words: even (8-byte aligned entries) and twice an odd number (64-bit per-thread accesses of a
+  // half-warp then fall on 16 distinct bank pairs)
+  static constexpr int LDSW = (C % 2 == 1) ? 2 * C : 2 * C + 2;
   static constexpr int TRIG = C - 8;     // a group of 8 columns must always fit
-  static constexpr int G = C / 16;       // strided group size of the cheap shrink (16 groups)
+  static constexpr int G = (C + 15) / 16; // groups of 16 the shrink sorts
   static constexpr int KEEP = KP + 2;    // the bisection fallback stops once this few remain
   static constexpr int JOIN = KP + 4;    // every row fuller than this shrinks whenever any row of the warp must:
                                           // one round refreshes (nearly) all 32 thresholds, so rounds stay rare
-  static_assert(KP == 16 && (C == 64 || C == 32), "the cheap shrink takes 16 strided groups of a 32/64-entry list");
+  static constexpr int CP = (C + 15) / 16 * 16;  // list length padded to whole groups of 16 for the sorting networks
+  static_assert(KP == 16 && (CP == 64 || CP == 32), "the shrink sorts 2 or 4 groups of 16");
   static_assert(KP <= KEEP && KEEP < JOIN && JOIN <= TRIG, "inconsistent list policy");
   struct Params {
     float* out_val[2];  // [n_rows][n_sub][C]
@@ -237,10 +240,10 @@ struct EpiTopK {
   // h8 (optional, global): receives atomicMax of the key of this list's 8th best score (see Params::row_h8).
   __device__ __noinline__ static unsigned long long quad_shrink(float thr_in, int n, uint32_t vb, uint32_t ib,
                                                                unsigned* h8 = nullptr) {
-    float x[C];
+    float x[CP];
 #pragma unroll
-    for (int s = 0; s < C; ++s) {
-      x[s] = lds_f32(vb + s * ES);
+    for (int s = 0; s < CP; ++s) {
+      x[s] = s < C ? lds_f32(vb + s * ES) : -CUDART_INF_F;
       if (s >= n) x[s] = -CUDART_INF_F;
     }
     // exact 16th largest of the list: sort the C/16 groups of 16, merge keeping the top 16
@@ -363,7 +366,8 @@ struct EpiTopK {
     }
     unsigned* my_h8 = (WGS > 1 && P.row_h8[c.p] != nullptr && c.row < c.n_rows)
                           ? P.row_h8[c.p] + 2 * static_cast<long long>(c.row) + c.wg : nullptr;
-    const bool dense = MODE == 1 || P.dense == 1 || st.dense_tiles > 0;  // warp-uniform
+    // warp-uniform; lists shorter than 64 entries cannot take 16 unfiltered columns between checks
+    const bool dense = C >= 64 && (MODE == 1 || P.dense == 1 || st.dense_tiles > 0);
     if (st.dense_tiles > 0) --st.dense_tiles;
     if (dense && __any_sync(0xffffffffu, st.cnt > DTRIG)) {  // the dense path appends up to 16 between checks
       if (st.cnt > JOIN) {
