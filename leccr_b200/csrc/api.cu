@@ -476,6 +476,12 @@ static bool topk_a_resident() {
 // Dense mode (and with it the two-warpgroup shape) is chosen when every tensor-core problem of the launch has
 // short column chunks; decided from the plans alone so that workspace sizing and launch agree.
 static bool topk_dense(const Plan* plans, int n_prob, const int* gemm_mask) {
+  static int never = -1;
+  if (never < 0) {
+    const char* e = getenv("LECCR_TOPK_WGS");  // measurement aid: 3 = filter shapes even for short chunks
+    never = (e != nullptr && atoi(e) == 3) ? 1 : 0;
+  }
+  if (never) return false;
   for (int p = 0; p < n_prob; ++p)
     if ((gemm_mask == nullptr || gemm_mask[p]) && plans[p].tiles_per_chunk > 32) return false;
   return true;
