@@ -59,7 +59,7 @@ struct EpiStore {
     long long split_stride[2];  // elements between split-K partial planes (0 when not split)
   };
   static constexpr int kWGs = 2;
-  static constexpr bool kSplitCols = true;  // both warpgroups drain every tile, half its columns each
+  static constexpr bool kSplitCols = false;
   static constexpr int kTileLd = 33;
   static constexpr int kSmemBytes = 4 * 32 * kTileLd * 4;
   struct State {};
@@ -93,7 +93,7 @@ struct EpiStore {
         }
       }
       __syncwarp();
-    }, BN / 32 / kWGs);
+    });
   }
 };
 
@@ -522,10 +522,8 @@ struct EpiLse {
     int n_sub[2];                  // partials per row: n_chunks * kWGs
   };
   static constexpr int kWGs = 2;
-  static constexpr bool kSplitCols = true;  // both warpgroups drain every tile, half its columns each
-  static constexpr int W = BN / kWGs;       // columns of a tile per warpgroup (= threads per warpgroup)
-  static_assert(W == kEpiThreads, "one staged label per epilogue thread");
-  static constexpr int kSmemBytes = 2 * W * 8;
+  static constexpr bool kSplitCols = false;
+  static constexpr int kSmemBytes = 2 * BN * 8;
   struct State {
     float m, l, w, pz, cnt, sc;
     long long my_idx;
@@ -544,13 +542,16 @@ struct EpiLse {
   __device__ static void tile(State& st, const Params& P, const ItemCtx& c, uint32_t taddr, int col0) {
     const long long* ic = P.idx_cols[c.p];
     const int n_cols = c.n_cols;
-    const uint32_t sidx = smem_u32(c.smem) + (c.tile_n & 1u) * W * 8;
+    const uint32_t sidx = smem_u32(c.smem) + ((c.tile_n >> (kWGs - 1)) & 1u) * BN * 8;
     if (ic != nullptr) {
-      const int j = col0 + c.et;
-      sts_s64(sidx + c.et * 8, j < n_cols ? __ldg(ic + j) : 0);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = col0 + c.et + h * kEpiThreads;
+        sts_s64(sidx + (c.et + h * kEpiThreads) * 8, j < n_cols ? __ldg(ic + j) : 0);
+      }
       epi_bar_sync(c.wg);  // one barrier per tile; the staging buffers alternate tile by tile
     }
-    const bool ragged = col0 + W > n_cols;
+    const bool ragged = col0 + BN > n_cols;
     const float sc = st.sc;
     const long long my = st.my_idx;
     const int row = c.row;
@@ -596,7 +597,7 @@ struct EpiLse {
             }
         }
       }
-    }, W / 32);
+    });
   }
   __device__ static void end(State& st, const Params& P, const ItemCtx& c) {
     if (c.row < c.n_rows) {
@@ -635,10 +636,8 @@ struct EpiGrad {
     int fmt;                    // 0 fp16, 1 bf16
   };
   static constexpr int kWGs = 2;
-  static constexpr bool kSplitCols = true;  // both warpgroups drain every tile, half its columns each
-  static constexpr int W = BN / kWGs;
-  static_assert(W == kEpiThreads, "one staged column per epilogue thread");
-  static constexpr int kBufBytes = W * 16;  // idx (8) + lse (4) + rcnt (4) per column
+  static constexpr bool kSplitCols = false;
+  static constexpr int kBufBytes = BN * 16;  // idx (8) + lse (4) + rcnt (4) per column
   static constexpr int kSmemBytes = 2 * kBufBytes;
   struct State {
     float sc, lse, rc;
@@ -662,10 +661,11 @@ struct EpiGrad {
     const float* rcp = P.rcnt_cols[c.p];
     const int ld = static_cast<int>(P.ld[c.p]);
     const int n_cols = c.n_cols;
-    const uint32_t sbuf = smem_u32(c.smem) + (c.tile_n & 1u) * kBufBytes;
-    const uint32_t s_idx = sbuf, s_lse = sbuf + W * 8, s_rc = sbuf + W * 12;
-    {
-      const int t = c.et;
+    const uint32_t sbuf = smem_u32(c.smem) + ((c.tile_n >> (kWGs - 1)) & 1u) * kBufBytes;
+    const uint32_t s_idx = sbuf, s_lse = sbuf + BN * 8, s_rc = sbuf + BN * 12;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int t = c.et + h * kEpiThreads;
       const int j = col0 + t;
       const bool in = j < n_cols;
       sts_s64(s_idx + t * 8, in ? (ic != nullptr ? __ldg(ic + j) : static_cast<long long>(j)) : 0);
@@ -675,7 +675,7 @@ struct EpiGrad {
     epi_bar_sync(c.wg);
     uint16_t* srow = reinterpret_cast<uint16_t*>(P.strip[c.p]) +
                      static_cast<long long>(c.row - P.row0[c.p]) * ld;
-    const bool ragged = col0 + W > n_cols;
+    const bool ragged = col0 + BN > n_cols;
     const float sc = st.sc, lse_r = st.lse, rc_r = st.rc;
     const long long my = st.my_idx;
     const bool ok = st.ok;
@@ -716,7 +716,7 @@ struct EpiGrad {
               srow[col + e] = static_cast<uint16_t>((packed[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
         }
       }
-    }, W / 32);
+    });
   }
 };
 
