@@ -171,7 +171,7 @@ int leccr_sim_topk_stream(const leccr_topk_problem* probs, const leccr_topk_stre
  *   a16, b16     : [n][D] 16-bit all-gathered image / text operands (leccr_prep, layout HI)
  *   idx          : [n] int64 labels (idx_all, :285) or NULL for the arange labels of :277
  *   temp         : device scalar self.temp
- *   out          : [4] loss, dloss/dtemp, loss_i2t, loss_t2i
+ *   out          : [6] loss, dloss/dtemp, loss_i2t, loss_t2i, dloss_i2t/dtemp, dloss_t2i/dtemp
  *   lse2 / rcnt  : [2][n] per-row log2-domain log-sum-exp and 1/|positives| (saved for backward)
  * Backward (local rows [row_begin, row_begin + row_count) only):
  *   aT16, bT16   : [D][ldT] transposed operands (leccr_transpose16)
@@ -251,7 +251,9 @@ int leccr_topk_merge_peers(const float* const* val_ptrs_dev, const int32_t* cons
  *                The caller alternates two slots.  5 launches: push, barrier, copy, tensor-core pass, finalize.
  *   both16 : out, private [n][2D] 16-bit gathered operands [image | text] (saved for the backward)
  *   idx_all: out, [n] int64 (when idx != NULL);  out/lse2/rcnt as in leccr_infonce_fwd
- *   backward: dA, dB [row_count][D] fp32, dtemp scalar = grad_out * out[1] (may be NULL)
+ *   backward: dA, dB [row_count][D] fp32, dtemp scalar = grad_out * out[1] (may be NULL);
+ *             one_directional: gradient of out[2] = loss_i2t alone (caption_vision_loss,
+ *             models/model_retrieval_caption.py:141), dtemp = grad_out * out[4]
  * ------------------------------------------------------------------------------------------ */
 size_t leccr_itc_fwd_workspace(int64_t n, int tiles_per_chunk);
 int leccr_itc_forward(const float* image_feat, int64_t ld_img, const float* text_feat, int64_t ld_txt,
@@ -263,7 +265,7 @@ int leccr_itc_forward(const float* image_feat, int64_t ld_img, const float* text
 size_t leccr_itc_bwd_workspace(int64_t n, int64_t row_count, int D);
 int leccr_itc_backward(const void* both16, const int64_t* idx_all, int64_t n, int D, int fmt, const float* temp,
                        const float* lse2, const float* rcnt, const float* out, int64_t row_begin, int64_t row_count,
-                       const float* grad_out, float* dA, float* dB, float* dtemp, void* workspace,
+                       const float* grad_out, float* dA, float* dB, float* dtemp, int one_directional, void* workspace,
                        size_t workspace_bytes, leccr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

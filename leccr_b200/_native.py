@@ -69,7 +69,8 @@ _SIGNATURES = {
     "leccr_itc_forward": (c_int, [vp, i64, vp, i64, vp, i64, c_int, c_int, c_int, c_int, vp, vp, vp, ctypes.c_uint32,
                                   vp, sz, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "leccr_itc_bwd_workspace": (sz, [i64, i64, c_int]),
-    "leccr_itc_backward": (c_int, [vp, vp, i64, c_int, c_int, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, sz, vp]),
+    "leccr_itc_backward": (c_int, [vp, vp, i64, c_int, c_int, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, c_int, vp, sz,
+                                   vp]),
     "leccr_caploss_fwd_workspace": (sz, [c_int, i64]),
     "leccr_caploss_fwd": (c_int, [vp, i64, vp, i64, c_int, i64, c_int, c_int, vp, vp, vp, vp, vp, vp, sz, vp]),
     "leccr_caploss_bwd_workspace": (sz, [c_int, i64, c_int]),

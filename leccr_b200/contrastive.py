@@ -49,7 +49,7 @@ class _SymmetricInfoNCE(torch.autograd.Function):
     """forward = leccr_itc_forward, backward = leccr_itc_backward: two library calls per training step."""
 
     @staticmethod
-    def forward(ctx, image_feat, text_feat, temp, idx, rank, world, fmt):
+    def forward(ctx, image_feat, text_feat, temp, idx, rank, world, fmt, one_dir=False):
         if not image_feat.is_cuda:
             raise N.LeccrError("leccr_b200 has no CPU path: get_contrastive_loss needs CUDA tensors")
         lib = N.load()
@@ -104,13 +104,14 @@ class _SymmetricInfoNCE(torch.autograd.Function):
                                           base + o_lse, base + o_rc, N.ptr(ws), ws.numel(), N.stream_ptr()),
                     "leccr_itc_forward")
         ctx.save_for_backward(saved, temp_dev)
-        ctx.meta = (rank, B, D, n, fmt, idx is not None, (o_idx, o_out, o_lse, o_rc))
-        return saved[o_out:o_out + 4].view(torch.float32)[0].clone()
+        ctx.meta = (rank, B, D, n, fmt, idx is not None, (o_idx, o_out, o_lse, o_rc), bool(one_dir))
+        # out = [loss, dloss/dtemp, loss_i2t, loss_t2i, ...]: the one-directional loss is the i2t half
+        return saved[o_out:o_out + 16].view(torch.float32)[2 if one_dir else 0].clone()
 
     @staticmethod
     def backward(ctx, grad_out):
         saved, temp_dev = ctx.saved_tensors
-        rank, B, D, n, fmt, has_idx, (o_idx, o_out, o_lse, o_rc) = ctx.meta
+        rank, B, D, n, fmt, has_idx, (o_idx, o_out, o_lse, o_rc), one_dir = ctx.meta
         lib = N.load()
         dev = saved.device
         base = saved.data_ptr()
@@ -124,16 +125,63 @@ class _SymmetricInfoNCE(torch.autograd.Function):
         ws = _workspace("bwd", lib.leccr_itc_bwd_workspace(n, B, D), dev)
         N.check(lib.leccr_itc_backward(base, base + o_idx if has_idx else None, n, D, fmt, N.ptr(temp_dev),
                                        base + o_lse, base + o_rc, base + o_out, rank * B, B, N.ptr(go), N.ptr(dA),
-                                       N.ptr(dB), N.ptr(dtemp), N.ptr(ws), ws.numel(), N.stream_ptr()),
+                                       N.ptr(dB), N.ptr(dtemp), int(one_dir), N.ptr(ws), ws.numel(), N.stream_ptr()),
                 "leccr_itc_backward")
-        return dA, dB, dtemp, None, None, None, None
+        return dA, dB, dtemp, None, None, None, None, None
 
 
-def contrastive_loss(image_feat, text_feat, temp, idx=None, precision=None):
-    """Functional form: temp is a 0-d tensor (parameter); uses the default process group."""
+def contrastive_loss(image_feat, text_feat, temp, idx=None, precision=None, one_directional=False):
+    """Functional form: temp is a 0-d tensor (parameter); uses the default process group.
+    one_directional: only the first half, -mean_i sum_j log_softmax(image text^T / temp, 1)_ij labels_ij."""
     rank, world = _world()
     fmt = ops.fmt_of(precision or PRECISION)
-    return _SymmetricInfoNCE.apply(image_feat, text_feat, temp, idx, rank, world, fmt)
+    return _SymmetricInfoNCE.apply(image_feat, text_feat, temp, idx, rank, world, fmt, one_directional)
+
+
+class _SumGradAcrossRanks(torch.autograd.Function):
+    """Identity on a parameter; its gradient is summed over the ranks.  The reference applies cproj / vproj AFTER
+    the gather, so every rank's module sees all N rows and holds the full parameter gradient; projecting before
+    the gather leaves each rank with its own rows' share, and this sum restores the reference's per-rank value."""
+
+    @staticmethod
+    def forward(ctx, p):
+        return p.view_as(p)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        return g
+
+
+def _project(lin, x, world):
+    if world == 1:
+        return lin(x)
+    w = _SumGradAcrossRanks.apply(lin.weight)
+    b = _SumGradAcrossRanks.apply(lin.bias) if lin.bias is not None else None
+    return torch.nn.functional.linear(x, w, b)
+
+
+def caption_vision_loss(self, caption, image, idx):
+    """Drop-in for RetrievalModel.caption_vision_loss (models/model_retrieval_caption.py:118-143).
+
+    The reference gathers the raw token tensors of all ranks, projects and normalises them, multiplies every
+    caption token with every image token of every pair of samples ((N cn) x (N vn) x d) and then averages the
+    token pairs of each pair of samples.  The average of dot products is the dot product of the averages, and
+    projection / normalisation / averaging act on each sample alone, so they commute with the gather: here every
+    rank pools ITS samples first (self.cproj / self.vproj and F.normalize with the reference's default dim=1 stay
+    PyTorch) and the [B, d] pooled rows go through the library's gathered multi-positive InfoNCE, first half
+    only, temperature 1.  Same value and the same gradients for the local rows and -- through one all-reduce of
+    the two projections' parameter gradients -- for self.cproj / self.vproj; the token-level GEMM and the gather
+    of token tensors disappear."""
+    import torch.nn.functional as F
+
+    _, world = _world()
+    caption = caption.transpose(0, 1).contiguous()
+    c = F.normalize(_project(self.cproj, caption, world)).mean(dim=1)   # [B, d]; F.normalize's default dim=1 (:123)
+    v = F.normalize(_project(self.vproj, image, world)).mean(dim=1)
+    one = torch.ones((), dtype=torch.float32, device=c.device)
+    return contrastive_loss(c, v, one, idx.view(-1, 1), one_directional=True)
 
 
 def get_contrastive_loss(self, image_feat, text_feat, idx=None):

@@ -881,7 +881,7 @@ static int infonce_bwd_impl(const void* a16, const void* b16, int64_t ld16, cons
                             int64_t ldT, const int64_t* idx, int64_t n, int D, int fmt, const float* temp,
                             const float* lse2, const float* rcnt, int64_t row_begin, int64_t row_count,
                             const float* grad_out, float* dA, float* dB, void* workspace, size_t workspace_bytes,
-                            const float* prod_b, float* prod_out, leccr_stream_t stream_);
+                            const float* prod_b, float* prod_out, int one_dir, leccr_stream_t stream_);
 
 int leccr_infonce_bwd(const void* a16, const void* b16, int64_t ld16, const void* aT16, const void* bT16,
                       int64_t ldT, const int64_t* idx, int64_t n, int D, int fmt, const float* temp,
@@ -889,15 +889,16 @@ int leccr_infonce_bwd(const void* a16, const void* b16, int64_t ld16, const void
                       const float* grad_out, float* dA, float* dB, void* workspace, size_t workspace_bytes,
                       leccr_stream_t stream_) {
   return infonce_bwd_impl(a16, b16, ld16, aT16, bT16, ldT, idx, n, D, fmt, temp, lse2, rcnt, row_begin, row_count,
-                          grad_out, dA, dB, workspace, workspace_bytes, nullptr, nullptr, stream_);
+                          grad_out, dA, dB, workspace, workspace_bytes, nullptr, nullptr, 0, stream_);
 }
 
-// prod_out (optional) = grad_out * *prod_b, computed by the last launch
+// prod_out (optional) = grad_out * *prod_b, computed by the last launch.  one_dir: gradient of the i2t half only,
+// loss = -mean_i sum_j log_softmax(a b^T / temp, 1)_ij labels_ij  (models/model_retrieval_caption.py:141).
 static int infonce_bwd_impl(const void* a16, const void* b16, int64_t ld16, const void* aT16, const void* bT16,
                             int64_t ldT, const int64_t* idx, int64_t n, int D, int fmt, const float* temp,
                             const float* lse2, const float* rcnt, int64_t row_begin, int64_t row_count,
                             const float* grad_out, float* dA, float* dB, void* workspace, size_t workspace_bytes,
-                            const float* prod_b, float* prod_out, leccr_stream_t stream_) {
+                            const float* prod_b, float* prod_out, int one_dir, leccr_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (a16 == nullptr || b16 == nullptr || aT16 == nullptr || bT16 == nullptr || temp == nullptr ||
       lse2 == nullptr || rcnt == nullptr || dA == nullptr || dB == nullptr || n <= 0 || D <= 0 || bad_fmt(fmt) ||
@@ -941,6 +942,8 @@ static int infonce_bwd_impl(const void* a16, const void* b16, int64_t ld16, cons
       EP.ld[p] = ldS;
       EP.row0[p] = static_cast<int>(row_begin);
       EP.nrow[p] = static_cast<int>(row_count);
+      EP.row_w[p] = (one_dir && p == 1) ? 0.f : 1.f;
+      EP.col_w[p] = (one_dir && p == 0) ? 0.f : 1.f;
     }
     EP.strip[0] = strip0;
     EP.strip[1] = strip1;
@@ -958,7 +961,7 @@ static int infonce_bwd_impl(const void* a16, const void* b16, int64_t ld16, cons
         {strip0, bT16, ldS, ldT, row_count, D, dA, D, parts0},
         {strip1, aT16, ldS, ldT, row_count, D, dB, D, parts1},
     };
-    rc = launch_store(sp, 2, static_cast<int>(n), fmt, 1.0f / (2.0f * static_cast<float>(n)), grad_out, temp,
+    rc = launch_store(sp, 2, static_cast<int>(n), fmt, 1.0f / ((one_dir ? 1.0f : 2.0f) * static_cast<float>(n)), grad_out, temp,
                       splits, stream, grad_out, prod_b, prod_out);
     if (rc != LECCR_OK) return rc;
   }
@@ -1130,7 +1133,7 @@ size_t leccr_itc_bwd_workspace(int64_t n, int64_t row_count, int D) {
 
 int leccr_itc_backward(const void* both16, const int64_t* idx_all, int64_t n, int D, int fmt, const float* temp,
                        const float* lse2, const float* rcnt, const float* out, int64_t row_begin, int64_t row_count,
-                       const float* grad_out, float* dA, float* dB, float* dtemp, void* workspace,
+                       const float* grad_out, float* dA, float* dB, float* dtemp, int one_directional, void* workspace,
                        size_t workspace_bytes, leccr_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (both16 == nullptr || workspace == nullptr || n <= 0 || D <= 0 || out == nullptr || grad_out == nullptr)
@@ -1152,7 +1155,7 @@ int leccr_itc_backward(const void* both16, const int64_t* idx_all, int64_t n, in
   // dL/dtemp = grad_out * (d loss / d temp from the forward), written by the backward's last launch
   return infonce_bwd_impl(both, both + D, 2 * D, aT, bT, ldT, idx_all, n, D, fmt, temp, lse2, rcnt, row_begin,
                           row_count, grad_out, dA, dB, ws + 2 * tr, workspace_bytes - 2 * tr,
-                          dtemp != nullptr ? out + 1 : nullptr, dtemp, stream_);
+                          dtemp != nullptr ? out + (one_directional ? 4 : 1) : nullptr, dtemp, one_directional, stream_);
 }
 
 // ------------------------------------------------------------------------------------ caption contrastive loss

@@ -634,6 +634,9 @@ struct EpiGrad {
     int row0[2];                // first absolute row of the strip (need not be a multiple of 128)
     int nrow[2];                // rows in the strip
     int fmt;                    // 0 fp16, 1 bf16
+    float row_w[2], col_w[2];   // weights of the row / column softmax terms: (1, 1) for the symmetric loss; the
+                                // one-directional loss -sum(log_softmax(sim, 1) * labels) keeps only the softmax
+                                // over the rows of orientation 0: (1, 0) there and (0, 1) in orientation 1
   };
   static constexpr int kWGs = 2;
   static constexpr bool kSplitCols = false;
@@ -676,7 +679,9 @@ struct EpiGrad {
     uint16_t* srow = reinterpret_cast<uint16_t*>(P.strip[c.p]) +
                      static_cast<long long>(c.row - P.row0[c.p]) * ld;
     const bool ragged = col0 + BN > n_cols;
-    const float sc = st.sc, lse_r = st.lse, rc_r = st.rc;
+    const float sc = st.sc, lse_r = st.lse;
+    const float rw = P.row_w[c.p], cw = P.col_w[c.p];
+    const float rc_r = st.rc * rw;
     const long long my = st.my_idx;
     const bool ok = st.ok;
     const int fmt = P.fmt;
@@ -687,9 +692,9 @@ struct EpiGrad {
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
         const float z = v[e] * sc;
-        float g = ex2_approx(z - lse_r) + ex2_approx(z - lds_f32(s_lse + (cl + e) * 4));
+        float g = rw * ex2_approx(z - lse_r) + cw * ex2_approx(z - lds_f32(s_lse + (cl + e) * 4));
         const bool pos = lds_s64(s_idx + (cl + e) * 8) == my;
-        g -= pos ? (rc_r + lds_f32(s_rc + (cl + e) * 4)) : 0.f;
+        g -= pos ? (rc_r + cw * lds_f32(s_rc + (cl + e) * 4)) : 0.f;
         if (ragged && col + e >= n_cols) g = 0.f;
         v[e] = g;
       }

@@ -486,6 +486,8 @@ __global__ void infonce_finalize_kernel(const FinalizeLseParams P) {
     P.out[1] = static_cast<float>(-0.5 * (d0 + d1) / temp);
     P.out[2] = static_cast<float>(l0);
     P.out[3] = static_cast<float>(l1);
+    P.out[4] = static_cast<float>(-d0 / temp);  // d loss_i2t / d temp, d loss_t2i / d temp (one-directional losses)
+    P.out[5] = static_cast<float>(-d1 / temp);
   }
 }
 

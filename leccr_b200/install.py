@@ -53,6 +53,8 @@ def install_caption_loss(modules=("models.model_retrieval_caption", "models.vide
             cls.get_caption_contrastive_loss = _cl.get_caption_contrastive_loss
             if hasattr(cls, "dstl_loss"):
                 cls.dstl_loss = _dstl_loss  # models/model_retrieval_caption.py:94
+            if hasattr(cls, "caption_vision_loss"):
+                cls.caption_vision_loss = _ct.caption_vision_loss  # models/model_retrieval_caption.py:118
             done.append(name)
     return done
 

@@ -197,13 +197,14 @@ def sim_topk(problems, k: int = 10, tiles_per_chunk: int = 0):
 
 def infonce_forward(a: Operand, b: Operand, idx: Optional[torch.Tensor], temp: torch.Tensor,
                     tiles_per_chunk: int = 0):
-    """Returns (out[4] = loss, dloss/dtemp, loss_i2t, loss_t2i ; lse2 [2, n] ; rcnt [2, n])."""
+    """Returns (out[6] = loss, dloss/dtemp, loss_i2t, loss_t2i, dloss_i2t/dtemp, dloss_t2i/dtemp ; lse2 [2, n] ;
+    rcnt [2, n])."""
     lib = N.load()
     n = a.n
     if b.n != n or a.D != b.D or a.fmt != b.fmt:
         raise N.LeccrError("image and text operands must have the same shape and format")
     dev = a.t16.device
-    out = torch.empty(4, dtype=torch.float32, device=dev)
+    out = torch.empty(6, dtype=torch.float32, device=dev)
     lse2 = torch.empty((2, n), dtype=torch.float32, device=dev)
     rcnt = torch.empty((2, n), dtype=torch.float32, device=dev)
     ws_bytes = lib.leccr_infonce_fwd_workspace(n, tiles_per_chunk)

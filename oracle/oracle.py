@@ -125,6 +125,49 @@ def dstl_loss_and_grads(image_all, caption_all, text_s_all, text_t_all, alpha: f
     return loss.detach(), allgather_backward(im.grad, rank, bs), allgather_backward(tt.grad, rank, bs)
 
 
+def caption_vision_loss(caption_all, image_all, idx_all, cproj, vproj) -> torch.Tensor:
+    """models/model_retrieval_caption.py:122-143 on the ALL-GATHERED token tensors (caption_all is [N, cn, d], i.e.
+    after the reference's transpose and gather), statement for statement: F.normalize keeps the reference's
+    default dim=1 (the token axis), the token-pair similarities are formed and averaged as the reference does."""
+    caption = F.normalize(cproj(caption_all))
+    image = F.normalize(vproj(image_all))
+    bsz, vn, d = image.shape
+    _, cn, _ = caption.shape
+    _image = image.reshape(-1, d)
+    _caption = caption.reshape(-1, d)
+    sim = _caption @ _image.t()
+    sim = sim.reshape(bsz, cn, bsz, vn).transpose(1, 2)
+    sim = torch.mean(torch.mean(sim, dim=-1), dim=-1)
+    idx = idx_all.view(-1, 1)
+    pos_idx = torch.eq(idx, idx.t()).float()
+    labels = pos_idx / pos_idx.sum(1, keepdim=True)
+    return -torch.sum(F.log_softmax(sim, dim=1) * labels, dim=1).mean()
+
+
+def caption_vision_loss_and_grads(caption, image, idx, Wc, bc, Wv, bv, rank: int = 0, batch_size: Optional[int] = None,
+                                  dtype=torch.float32):
+    """caption: [cn, N, d] as the model holds it.  Returns loss, the local rows of d image and d caption
+    (AllGather.backward keeps the local slices) and this rank's gradients of the two projection weights."""
+    N_ = image.shape[0]
+    bs = N_ if batch_size is None else batch_size
+    sl = slice(rank * bs, (rank + 1) * bs)
+    d = image.shape[2]
+    cproj, vproj = torch.nn.Linear(d, d).to(dtype), torch.nn.Linear(d, d).to(dtype)
+    with torch.no_grad():
+        cproj.weight.copy_(Wc.to(dtype)); cproj.bias.copy_(bc.to(dtype))
+        vproj.weight.copy_(Wv.to(dtype)); vproj.bias.copy_(bv.to(dtype))
+    im_loc = image[sl].detach().to(dtype).clone().requires_grad_(True)
+    cp_loc = caption[:, sl].detach().to(dtype).clone().requires_grad_(True)
+    # other ranks' rows take part in the forward but return no gradient to THIS rank
+    im_all = torch.cat([image[:sl.start].to(dtype), im_loc, image[sl.stop:].to(dtype)], 0)
+    cp_all = torch.cat([caption[:, :sl.start].to(dtype), cp_loc, caption[:, sl.stop:].to(dtype)], 1).transpose(0, 1)
+    # the reference projects AFTER the gather (:123-124): every rank's module sees all N rows, so its parameter
+    # gradients are the full ones; only the gradients of the gathered INPUTS are cut to the local slice
+    loss = caption_vision_loss(cp_all, im_all, idx, cproj, vproj)
+    loss.backward()
+    return loss.detach(), im_loc.grad, cp_loc.grad, cproj.weight.grad, vproj.weight.grad
+
+
 # ----------------------------------------------------------------------------- evaluation score matrices
 def score_matrices(image_embeds: torch.Tensor, text_embeds: torch.Tensor):
     """image_Retrieval_caption.py:151-152,163: i2t = image @ text.T, t2i = its transpose VIEW, as numpy."""

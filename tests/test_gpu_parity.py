@@ -522,3 +522,24 @@ def test_fused_eval_tiny_shapes_and_k_extremes(n, per, d, k):
         assert np.abs(np.take_along_axis(S, idx[:, :kk], 1) - wv).max() < 2 * tol
         if kk < k:   # fewer columns than k: the tail is padding
             assert (idx[:, kk:] == -1).all() and np.isneginf(val[:, kk:]).all()
+
+
+# ----------------------------------------------------------------------------- caption_vision_loss (8f rank 4)
+def test_caption_vision_loss_against_reference_golden(golden):
+    """The pooled drop-in vs the reference's token-level function (1 rank; tests/golden/caption_vision_loss.npz):
+    loss, input gradients and the gradients of the two projections."""
+    g = golden("caption_vision_loss.npz")
+    t = lambda k: torch.from_numpy(g[f"w1_{k}"])
+    d = t("image").shape[2]
+    me = types.SimpleNamespace(cproj=torch.nn.Linear(d, d).cuda(), vproj=torch.nn.Linear(d, d).cuda())
+    with torch.no_grad():
+        me.cproj.weight.copy_(t("Wc")); me.cproj.bias.copy_(t("bc")); me.vproj.weight.copy_(t("Wv")); me.vproj.bias.copy_(t("bv"))
+    im = t("image").cuda().requires_grad_(True)
+    cp = t("caption").cuda().requires_grad_(True)
+    loss = leccr_b200.caption_vision_loss(me, cp, im, t("idx").cuda())
+    loss.backward()
+    want = float(g["w1_r0_loss"])
+    assert abs(loss.item() - want) <= 1e-3 * abs(want), (loss.item(), want)
+    for got, key in ((im.grad, "dimage"), (cp.grad, "dcaption"), (me.cproj.weight.grad, "dWc"), (me.vproj.weight.grad, "dWv")):
+        ref = torch.from_numpy(g[f"w1_r0_{key}"]).double()
+        assert (got.cpu().double() - ref).norm() <= 5e-3 * ref.norm(), (key, (got.cpu().double() - ref).norm().item(), ref.norm().item())

@@ -135,3 +135,21 @@ def test_dstl_loss_matches_reference(golden):
             assert abs(loss.item() - want) <= 2e-6 * abs(want) + 1e-9
             for got, ref in ((dim, g[f"{name}_r{rank}_dimage"]), (dtt, g[f"{name}_r{rank}_dtext_t"])):
                 assert np.abs(got.numpy() - ref).max() <= 1e-5 * np.abs(ref).max() + 1e-10
+
+
+def test_caption_vision_loss_matches_reference(golden):
+    """oracle.caption_vision_loss vs the reference's caption_vision_loss under gloo with 1 and 2 ranks
+    (oracle/make_golden_cv.py): loss, local input gradients and the projection-weight gradients of each rank."""
+    g = golden("caption_vision_loss.npz")
+    for name in ("w1", "w2"):
+        world = int(g[f"{name}_world"])
+        t = lambda k: torch.from_numpy(g[f"{name}_{k}"])
+        B = t("image").shape[0] // world
+        for rank in range(world):
+            loss, dim, dcp, dwc, dwv = oracle.caption_vision_loss_and_grads(t("caption"), t("image"), t("idx"), t("Wc"),
+                                                                            t("bc"), t("Wv"), t("bv"), rank, B)
+            want = float(g[f"{name}_r{rank}_loss"])
+            assert abs(loss.item() - want) <= 2e-6 * abs(want)
+            for got, key in ((dim, "dimage"), (dcp, "dcaption"), (dwc, "dWc"), (dwv, "dWv")):
+                ref = g[f"{name}_r{rank}_{key}"]
+                assert np.abs(got.numpy() - ref).max() <= 2e-5 * np.abs(ref).max() + 1e-9, key

@@ -71,6 +71,29 @@ e = [abs(dl.item() - w_l.item()) / abs(w_l.item()), ((im_l.grad.cpu().double() -
 dstl_ok = e[0] < 1e-3 and e[1] < 3e-3 and e[2] < 3e-3
 ok &= dstl_ok
 print(f"rank {rank}: dstl_loss {dl.item():.6f} rel {e[0]:.1e} dimage {e[1]:.1e} dtext_t {e[2]:.1e} {'PASS' if dstl_ok else 'FAIL'}", flush=True)
+# ---- caption_vision_loss: pooled drop-in on W ranks vs the oracle's token-level restatement on the gathered batch
+gc = torch.Generator().manual_seed(9)
+Nc, cn, vn, dc = 64 * world, 2, 5, 64
+c_img = torch.randn(Nc, vn, dc, generator=gc)
+c_cap = c_img.mean(1)[None] * 0.5 + torch.randn(cn, Nc, dc, generator=gc)
+c_idx = torch.randint(0, Nc // 2, (Nc,), generator=gc)
+Wc, bc = torch.randn(dc, dc, generator=gc) / dc ** 0.5, 0.1 * torch.randn(dc, generator=gc)
+Wv, bv = torch.randn(dc, dc, generator=gc) / dc ** 0.5, 0.1 * torch.randn(dc, generator=gc)
+me_c = types.SimpleNamespace(cproj=torch.nn.Linear(dc, dc).cuda(), vproj=torch.nn.Linear(dc, dc).cuda())
+with torch.no_grad():
+    me_c.cproj.weight.copy_(Wc); me_c.cproj.bias.copy_(bc); me_c.vproj.weight.copy_(Wv); me_c.vproj.bias.copy_(bv)
+slc = slice(rank * 64, (rank + 1) * 64)
+ci = c_img[slc].cuda().requires_grad_(True)
+cc = c_cap[:, slc].cuda().requires_grad_(True)
+cl = leccr_b200.caption_vision_loss(me_c, cc, ci, c_idx[slc].cuda())
+cl.backward()
+o_l, o_dim, o_dcp, o_dwc, o_dwv = oracle.caption_vision_loss_and_grads(c_cap, c_img, c_idx, Wc, bc, Wv, bv, rank, 64, dtype=torch.float64)
+rel = lambda a, b: ((a.cpu().double() - b).norm() / b.norm()).item()
+ec = [abs(cl.item() - o_l.item()) / abs(o_l.item()), rel(ci.grad, o_dim), rel(cc.grad, o_dcp), rel(me_c.cproj.weight.grad, o_dwc),
+      rel(me_c.vproj.weight.grad, o_dwv)]
+cv_ok = ec[0] < 1e-3 and max(ec[1:]) < 5e-3
+ok &= cv_ok
+print(f"rank {rank}: caption_vision_loss {cl.item():.6f} rel {ec[0]:.1e} dimage {ec[1]:.1e} dcaption {ec[2]:.1e} dWc {ec[3]:.1e} dWv {ec[4]:.1e} {'PASS' if cv_ok else 'FAIL'}", flush=True)
 # ---- the C-ABI NCCL entries (hosts without torch.distributed): communicator from a broadcast unique id,
 # all-gather of this rank's top-k lists, merge over a table of pointers into the gathered buffer
 import ctypes
