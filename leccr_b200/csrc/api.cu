@@ -645,6 +645,9 @@ static int topk_core(const leccr_topk_problem* probs, const leccr_topk_stream* s
     prof_mark("topk:gemm", stream);
   }
 
+  TopkFinalizeParams post[2];
+  int32_t* post_counts[2] = {nullptr, nullptr};
+  int n_post = 0;
   for (int p = 0; p < n_prob; ++p) {
     if (!(so[p].phases & LECCR_TOPK_FINALIZE)) continue;
     const leccr_topk_problem& q = probs[p];
@@ -687,17 +690,17 @@ static int topk_core(const leccr_topk_problem* probs, const leccr_topk_stream* s
     LAUNCH_CHECK("topk_finalize_kernel");
     prof_mark("topk:finalize", stream);
     if (q.gt_off != nullptr) {
-      const unsigned g2 = static_cast<unsigned>(std::min<int64_t>(q.n_rows, 2LL * num_sms()));
-      exact_rank_rows_kernel<<<g2, 256, 0, stream>>>(F);
-      LAUNCH_CHECK("exact_rank_rows_kernel");
-      prof_mark("topk:exact_rank", stream);
-      if (q.recall_counts != nullptr) {
-        const unsigned g3 = static_cast<unsigned>(std::min<int64_t>((q.n_rows + 255) / 256, 2LL * num_sms()));
-        recall_count_kernel<<<g3, 256, 0, stream>>>(q.rank, static_cast<int>(q.n_rows), q.recall_counts);
-        LAUNCH_CHECK("recall_count_kernel");
-        prof_mark("topk:recall_count", stream);
-      }
+      post[n_post] = F;
+      post_counts[n_post] = q.recall_counts;
+      ++n_post;
     }
+  }
+  if (n_post > 0) {  // exact fallback for flagged rows + Recall counts of every finalised problem: one launch
+    if (n_post == 1) memset(&post[1], 0, sizeof(post[1]));  // gt_off == nullptr: the second slice exits at once
+    dim3 g(static_cast<unsigned>(num_sms()), static_cast<unsigned>(n_post));
+    rank_post_kernel<<<g, 256, 0, stream>>>(post[0], post[1], post_counts[0], post_counts[1]);
+    LAUNCH_CHECK("rank_post_kernel");
+    prof_mark("topk:rank_post", stream);
   }
   return LECCR_OK;
 }

@@ -765,9 +765,7 @@ __global__ void __launch_bounds__(kFinalizeWarps * 32) topk_finalize_kernel(cons
 
 // Exact fallback for flagged rows: rank = min_g #{j : t_j > t_g} with every score an fp32 dot.
 // One block per flagged row (grid-stride over the list; normally the list is empty).
-__global__ void exact_rank_rows_kernel(const TopkFinalizeParams P) {
-  __shared__ float s_tg[16];
-  __shared__ int s_cnt[16];
+__device__ __forceinline__ void exact_rank_rows(const TopkFinalizeParams& P, float* s_tg, int* s_cnt) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int n_flagged = *P.flag_count;
   for (int fi = blockIdx.x; fi < n_flagged; fi += gridDim.x) {
@@ -806,6 +804,60 @@ __global__ void exact_rank_rows_kernel(const TopkFinalizeParams P) {
       for (int gi = 0; gi < ng; ++gi) best = min(best, s_cnt[gi]);
       P.rank[row] = best == 0x7fffffff ? kRankCap : best;
     }
+  }
+}
+
+__global__ void exact_rank_rows_kernel(const TopkFinalizeParams P) {
+  __shared__ float s_tg[16];
+  __shared__ int s_cnt[16];
+  exact_rank_rows(P, s_tg, s_cnt);
+}
+
+// What follows topk_finalize, for up to two problems in ONE launch (blockIdx.y = problem): the exact fallback for
+// the flagged rows (normally none), then #{rank < 1, 5, 10}.  Counting has to see the fallback's ranks: only
+// when rows WERE flagged the blocks of a problem meet at a grid barrier (flag_count[1], zeroed with the flag
+// count; every launch keeps its grid co-resident: at most 2 blocks of 256 threads per SM).
+__global__ void rank_post_kernel(const TopkFinalizeParams P0, const TopkFinalizeParams P1, int* __restrict__ counts0,
+                                 int* __restrict__ counts1) {
+  __shared__ float s_tg[16];
+  __shared__ int s_cnt[16];
+  const TopkFinalizeParams& P = blockIdx.y == 0 ? P0 : P1;
+  int* counts = blockIdx.y == 0 ? counts0 : counts1;
+  if (P.gt_off == nullptr) return;
+  const int n_flagged = *P.flag_count;
+  if (n_flagged > 0) {
+    exact_rank_rows(P, s_tg, s_cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      unsigned* bar = reinterpret_cast<unsigned*>(P.flag_count) + 1;
+      atomicAdd(bar, 1u);
+      unsigned seen;
+      long long spins = 0;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+        if (++spins > (1LL << 28)) __trap();
+      } while (seen < gridDim.x);
+    }
+    __syncthreads();
+  }
+  if (counts == nullptr) return;
+  int c1 = 0, c5 = 0, c10 = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_rows; i += gridDim.x * blockDim.x) {
+    const int r = P.rank[i];
+    c1 += r < 1;
+    c5 += r < 5;
+    c10 += r < 10;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+    c5 += __shfl_xor_sync(0xffffffffu, c5, o);
+    c10 += __shfl_xor_sync(0xffffffffu, c10, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (c1) atomicAdd(counts + 0, c1);
+    if (c5) atomicAdd(counts + 1, c5);
+    if (c10) atomicAdd(counts + 2, c10);
   }
 }
 

@@ -543,3 +543,29 @@ def test_caption_vision_loss_against_reference_golden(golden):
     for got, key in ((im.grad, "dimage"), (cp.grad, "dcaption"), (me.cproj.weight.grad, "dWc"), (me.vproj.weight.grad, "dWv")):
         ref = torch.from_numpy(g[f"w1_r0_{key}"]).double()
         assert (got.cpu().double() - ref).norm() <= 5e-3 * ref.norm(), (key, (got.cpu().double() - ref).norm().item(), ref.norm().item())
+
+
+def test_exact_rank_fallback_for_scores_tied_inside_the_16bit_tolerance():
+    """40 gallery columns whose fp32 scores differ by 1e-5 (far below the fp16-operand tolerance, far above fp32
+    rounding): the candidate list cannot order them, the rows are flagged and ranked by the exact fp32 fallback
+    (and counted after its grid barrier)."""
+    g = torch.Generator().manual_seed(8)
+    d, n_q = 256, 150
+    base = torch.nn.functional.normalize(torch.randn(n_q, d, generator=g), dim=-1)
+    filler = torch.nn.functional.normalize(torch.randn(600, d, generator=g), dim=-1)
+    copies = torch.cat([base[q:q + 1] * (1.0 - 1e-5 * j) for q in range(3) for j in range(40)], 0)   # queries 0..2
+    gallery = torch.cat([copies, filler], 0).contiguous()
+    gt_col = [20, 40 + 7, 80 + 0] + [120 + q for q in range(3, n_q)]          # ranks 20, 7, 0; others: a filler column
+    gt_off = torch.arange(n_q + 1, dtype=torch.int32, device="cuda")
+    gt_ids = torch.tensor(gt_col, dtype=torch.int32, device="cuda")
+    Q, G = ops.prep(base.cuda()), ops.prep(gallery.cuda())
+    res, = ops.sim_topk([(Q, G, (gt_off, gt_ids))], k=10)
+    S = (base.double() @ gallery.double().t())
+    want = torch.tensor([(S[q] > S[q, gt_col[q]]).sum().item() for q in range(n_q)])
+    got = res.rank.cpu().long()
+    assert got[0] == 20 and got[1] == 7 and got[2] == 0, got[:3]
+    small = want < 10
+    assert torch.equal(got[small], want[small])            # exact below the cap
+    assert (got[~small] >= 10).all()                        # lower bounds at or above it
+    c = res.recall_counts.cpu().tolist()
+    assert c == [int((want < 1).sum()), int((want < 5).sum()), int((want < 10).sum())]
