@@ -80,6 +80,11 @@ int leccr_profile_read(double* total_ms, int* launches);
 int leccr_prep(const float* src, int64_t n, int D, int64_t ld_src, int normalize, int fmt, int layout,
                void* dst16, int64_t ld_dst, float* rn_hi, float* rn_lo, float* stats,
                leccr_stream_t stream);
+/* leccr_prep for the two embedding sets of an evaluation in ONE launch (same D, format, layout, normalize). */
+int leccr_prep_pair(const float* src0, int64_t n0, int64_t ld_src0, void* dst16_0, int64_t ld_dst0, float* rn_hi0,
+                    float* rn_lo0, float* stats0, const float* src1, int64_t n1, int64_t ld_src1, void* dst16_1,
+                    int64_t ld_dst1, float* rn_hi1, float* rn_lo1, float* stats1, int D, int normalize, int fmt,
+                    int layout, leccr_stream_t stream);
 /* The cast prologue fused with its all-gather (replaces AllGather.forward, models/xvlm.py:53-59, for the
  * contrastive operands): casts this rank's n rows and stores them into EVERY rank's gathered operand
  * buffer at [dst_row0 + i][dst_col0 ...] through peer pointers (NVLink).  dst_ptrs_dev: device array of

@@ -60,6 +60,8 @@ _SIGNATURES = {
     "leccr_profile_enable": (None, [c_int]),
     "leccr_profile_read": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int)]),
     "leccr_prep": (c_int, [vp, i64, c_int, i64, c_int, c_int, c_int, vp, i64, vp, vp, vp, vp]),
+    "leccr_prep_pair": (c_int, [vp, i64, i64, vp, i64, vp, vp, vp, vp, i64, i64, vp, i64, vp, vp, vp, c_int, c_int, c_int,
+                                c_int, vp]),
     "leccr_prep_push": (c_int, [vp, i64, c_int, i64, c_int, c_int, vp, c_int, i64, i64, i64, vp]),
     "leccr_push_words": (c_int, [vp, i64, vp, c_int, i64, vp]),
     "leccr_sim_topk_stream_workspace": (sz, [i64, c_int]),

@@ -282,6 +282,36 @@ int leccr_prep(const float* src, int64_t n, int D, int64_t ld_src, int normalize
   return LECCR_OK;
 }
 
+int leccr_prep_pair(const float* src0, int64_t n0, int64_t ld_src0, void* dst16_0, int64_t ld_dst0, float* rn_hi0,
+                    float* rn_lo0, float* stats0, const float* src1, int64_t n1, int64_t ld_src1, void* dst16_1,
+                    int64_t ld_dst1, float* rn_hi1, float* rn_lo1, float* stats1, int D, int normalize, int fmt,
+                    int layout, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (src0 == nullptr || src1 == nullptr || dst16_0 == nullptr || dst16_1 == nullptr || n0 <= 0 || n1 <= 0 || D <= 0 ||
+      bad_fmt(fmt) || layout < 0 || layout > 2)
+    return LECCR_ERR_ARG;
+  const int64_t K = layout == 0 ? D : 3LL * D;
+  auto vec_ok = [&](const float* src, int64_t ld_src, void* dst, int64_t ld_dst) {
+    return ld_src >= D && ld_dst >= K && (D % 128 == 0) && D <= 1024 && (ld_src % 4 == 0) && (ld_dst % 4 == 0) &&
+           (reinterpret_cast<uintptr_t>(src) % 16 == 0) && (reinterpret_cast<uintptr_t>(dst) % 8 == 0);
+  };
+  if (!vec_ok(src0, ld_src0, dst16_0, ld_dst0) || !vec_ok(src1, ld_src1, dst16_1, ld_dst1)) {  // general path: two launches
+    int rc = leccr_prep(src0, n0, D, ld_src0, normalize, fmt, layout, dst16_0, ld_dst0, rn_hi0, rn_lo0, stats0, stream_);
+    if (rc != LECCR_OK) return rc;
+    return leccr_prep(src1, n1, D, ld_src1, normalize, fmt, layout, dst16_1, ld_dst1, rn_hi1, rn_lo1, stats1, stream_);
+  }
+  const int wpb = 8;
+  const int b0 = static_cast<int>((n0 + wpb - 1) / wpb), b1 = static_cast<int>((n1 + wpb - 1) / wpb);
+  PrepTensor t0 = {src0, ld_src0, static_cast<int>(n0), static_cast<uint16_t*>(dst16_0), ld_dst0, rn_hi0, rn_lo0, stats0};
+  PrepTensor t1 = {src1, ld_src1, static_cast<int>(n1), static_cast<uint16_t*>(dst16_1), ld_dst1, rn_hi1, rn_lo1, stats1};
+  if (fmt == LECCR_FMT_F16)
+    prep_rows_vec_pair_kernel<0><<<b0 + b1, wpb * 32, 0, stream>>>(t0, t1, b0, D, normalize, layout);
+  else
+    prep_rows_vec_pair_kernel<1><<<b0 + b1, wpb * 32, 0, stream>>>(t0, t1, b0, D, normalize, layout);
+  LAUNCH_CHECK("prep_rows_vec_pair_kernel");
+  return LECCR_OK;
+}
+
 int leccr_prep_push(const float* src, int64_t n, int D, int64_t ld_src, int normalize, int fmt,
                     void* const* dst_ptrs_dev, int world, int64_t dst_row0, int64_t dst_col0, int64_t ld_dst,
                     leccr_stream_t stream_) {
@@ -645,9 +675,10 @@ static int topk_core(const leccr_topk_problem* probs, const leccr_topk_stream* s
     prof_mark("topk:gemm", stream);
   }
 
-  TopkFinalizeParams post[2];
+  TopkFinalizeParams post[2], fin[2];
   int32_t* post_counts[2] = {nullptr, nullptr};
-  int n_post = 0;
+  int fin_slots[2] = {0, 0};
+  int n_post = 0, n_fin = 0;
   for (int p = 0; p < n_prob; ++p) {
     if (!(so[p].phases & LECCR_TOPK_FINALIZE)) continue;
     const leccr_topk_problem& q = probs[p];
@@ -681,19 +712,51 @@ static int topk_core(const leccr_topk_problem* probs, const leccr_topk_stream* s
     F.flag_count = flag[p];
     F.flag_list = flag[p] + 4;
     F.gt_score = q.gt_score;
-    const unsigned grid = static_cast<unsigned>((q.n_rows + kFinalizeWarps - 1) / kFinalizeWarps);
-    const int slots = F.n_chunks;  // one 32-entry slot per list
+    fin[n_fin] = F;
+    fin_slots[n_fin] = F.n_chunks;  // one 32-entry slot per list
+    ++n_fin;
+    if (q.gt_off != nullptr) {
+      post[n_post] = F;
+      post_counts[n_post] = q.recall_counts;
+      ++n_post;
+    }
+  }
+  if (n_fin == 2) {
+    // one launch for both problems; the pair kernel is instantiated for S0 >= S1
+    if (fin_slots[0] < fin_slots[1]) {
+      std::swap(fin[0], fin[1]);
+      std::swap(fin_slots[0], fin_slots[1]);
+    }
+    const int b0 = (fin[0].n_rows + kFinalizeWarps - 1) / kFinalizeWarps;
+    const int b1 = (fin[1].n_rows + kFinalizeWarps - 1) / kFinalizeWarps;
+    auto cls = [](int sl) { return sl <= 2 ? 0 : sl <= 4 ? 1 : sl <= 8 ? 2 : 3; };
+    const int c0 = cls(fin_slots[0]), c1 = cls(fin_slots[1]);
+#define LECCR_FIN_PAIR(A, B) topk_finalize_pair_kernel<A, B><<<b0 + b1, kFinalizeWarps * 32, 0, stream>>>(fin[0], fin[1], b0)
+    switch (c0 * 4 + c1) {
+      case 0: LECCR_FIN_PAIR(2, 2); break;
+      case 4: LECCR_FIN_PAIR(4, 2); break;
+      case 5: LECCR_FIN_PAIR(4, 4); break;
+      case 8: LECCR_FIN_PAIR(8, 2); break;
+      case 9: LECCR_FIN_PAIR(8, 4); break;
+      case 10: LECCR_FIN_PAIR(8, 8); break;
+      case 12: LECCR_FIN_PAIR(kMaxSlots, 2); break;
+      case 13: LECCR_FIN_PAIR(kMaxSlots, 4); break;
+      case 14: LECCR_FIN_PAIR(kMaxSlots, 8); break;
+      default: LECCR_FIN_PAIR(kMaxSlots, kMaxSlots); break;
+    }
+#undef LECCR_FIN_PAIR
+    LAUNCH_CHECK("topk_finalize_pair_kernel");
+    prof_mark("topk:finalize", stream);
+  } else if (n_fin == 1) {
+    const TopkFinalizeParams& F = fin[0];
+    const unsigned grid = static_cast<unsigned>((F.n_rows + kFinalizeWarps - 1) / kFinalizeWarps);
+    const int slots = fin_slots[0];
     if (slots <= 2) topk_finalize_kernel<2><<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
     else if (slots <= 4) topk_finalize_kernel<4><<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
     else if (slots <= 8) topk_finalize_kernel<8><<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
     else topk_finalize_kernel<kMaxSlots><<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
     LAUNCH_CHECK("topk_finalize_kernel");
     prof_mark("topk:finalize", stream);
-    if (q.gt_off != nullptr) {
-      post[n_post] = F;
-      post_counts[n_post] = q.recall_counts;
-      ++n_post;
-    }
   }
   if (n_post > 0) {  // exact fallback for flagged rows + Recall counts of every finalised problem: one launch
     if (n_post == 1) memset(&post[1], 0, sizeof(post[1]));  // gt_off == nullptr: the second slice exits at once

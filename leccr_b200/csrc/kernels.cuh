@@ -142,12 +142,11 @@ __global__ void prep_rows_kernel(const float* __restrict__ src, long long ld_src
 // Fast path of prep_rows for D % 128 == 0, D <= 1024, 16-byte aligned rows: one warp per row, each
 // lane holds D/128 float4 in registers (one pass over HBM even when normalising), 8-byte stores.
 template <int FMT>
-__global__ void prep_rows_vec_kernel(const float* __restrict__ src, long long ld_src, int n, int D,
-                                     int normalize, int layout, uint16_t* __restrict__ dst,
-                                     long long ld_dst, float* __restrict__ rn_hi,
-                                     float* __restrict__ rn_lo, float* __restrict__ stats) {
+__device__ __forceinline__ void prep_rows_vec_body(const float* __restrict__ src, long long ld_src, int n, int D,
+                                                   int normalize, int layout, uint16_t* __restrict__ dst,
+                                                   long long ld_dst, float* __restrict__ rn_hi,
+                                                   float* __restrict__ rn_lo, float* __restrict__ stats, int row) {
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) {
     publish_stats(stats, 0.f, 0.f, 0.f, false);
     return;
@@ -213,6 +212,35 @@ __global__ void prep_rows_vec_kernel(const float* __restrict__ src, long long ld
     if (rn_lo) rn_lo[row] = b;
   }
   publish_stats(stats, a, b, amax, anybad != 0);
+}
+
+template <int FMT>
+__global__ void prep_rows_vec_kernel(const float* __restrict__ src, long long ld_src, int n, int D,
+                                     int normalize, int layout, uint16_t* __restrict__ dst,
+                                     long long ld_dst, float* __restrict__ rn_hi,
+                                     float* __restrict__ rn_lo, float* __restrict__ stats) {
+  prep_rows_vec_body<FMT>(src, ld_src, n, D, normalize, layout, dst, ld_dst, rn_hi, rn_lo, stats,
+                          blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+}
+
+// Two tensors (the two embedding sets of an evaluation) in one launch: blocks [0, blocks0) cast the first.
+struct PrepTensor {
+  const float* src;
+  long long ld_src;
+  int n;
+  uint16_t* dst;
+  long long ld_dst;
+  float* rn_hi;
+  float* rn_lo;
+  float* stats;
+};
+template <int FMT>
+__global__ void prep_rows_vec_pair_kernel(const PrepTensor t0, const PrepTensor t1, int blocks0, int D, int normalize,
+                                          int layout) {
+  const bool second = static_cast<int>(blockIdx.x) >= blocks0;  // block-uniform
+  const PrepTensor& t = second ? t1 : t0;
+  const int row = (blockIdx.x - (second ? blocks0 : 0)) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  prep_rows_vec_body<FMT>(t.src, t.ld_src, t.n, D, normalize, layout, t.dst, t.ld_dst, t.rn_hi, t.rn_lo, t.stats, row);
 }
 
 // --------------------------------------------------------------------------------
@@ -577,11 +605,10 @@ __device__ __forceinline__ float warp_dot(const void* rows_x, long long ld_rows,
 // SLOTS = candidate slots per lane this instantiation handles (>= n_lists * list_cap / 32): the
 // selection loops are fully unrolled over it, so short merges do not pay for long ones.
 template <int SLOTS>
-__global__ void __launch_bounds__(kFinalizeWarps * 32) topk_finalize_kernel(const TopkFinalizeParams P) {
-  __shared__ float s_val[kFinalizeWarps][32];
-  __shared__ int s_idx[kFinalizeWarps][32];
+__device__ __forceinline__ void topk_finalize_body(const TopkFinalizeParams& P, int block, float (*s_val)[32],
+                                                   int (*s_idx)[32]) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int row = blockIdx.x * kFinalizeWarps + wib;
+  const int row = block * kFinalizeWarps + wib;
   if (row >= P.n_rows) return;
   const int KP = P.KP;
   const int sh = 0;                           // slots per list and lane, as a shift: lists arrive with <= 32 entries
@@ -761,6 +788,24 @@ __global__ void __launch_bounds__(kFinalizeWarps * 32) topk_finalize_kernel(cons
     P.rank[row] = rk_out;
     if (flagged) P.flag_list[atomicAdd(P.flag_count, 1)] = row;
   }
+}
+
+template <int SLOTS>
+__global__ void __launch_bounds__(kFinalizeWarps * 32) topk_finalize_kernel(const TopkFinalizeParams P) {
+  __shared__ float s_val[kFinalizeWarps][32];
+  __shared__ int s_idx[kFinalizeWarps][32];
+  topk_finalize_body<SLOTS>(P, blockIdx.x, s_val, s_idx);
+}
+
+// Both problems of a launch in one grid: blocks [0, blocks0) finalize problem 0 with S0 slots, the rest problem 1
+// with S1 (one launch instead of two, and the short one no longer runs a wave of its own).
+template <int S0, int S1>
+__global__ void __launch_bounds__(kFinalizeWarps * 32)
+topk_finalize_pair_kernel(const TopkFinalizeParams P0, const TopkFinalizeParams P1, int blocks0) {
+  __shared__ float s_val[kFinalizeWarps][32];
+  __shared__ int s_idx[kFinalizeWarps][32];
+  if (static_cast<int>(blockIdx.x) < blocks0) topk_finalize_body<S0>(P0, blockIdx.x, s_val, s_idx);
+  else topk_finalize_body<S1>(P1, blockIdx.x - blocks0, s_val, s_idx);
 }
 
 // Exact fallback for flagged rows: rank = min_g #{j : t_j > t_g} with every score an fp32 dot.

@@ -340,10 +340,10 @@ class FusedEvalPlan:
         st = torch.cuda.current_stream().cuda_stream
         lib, d, sp = self.lib, self.dim, self.state.data_ptr()
         self.state.zero_()
-        N.check(lib.leccr_prep(self.img.data_ptr(), self.n_img, d, d, 0, self.fmt, N.LAYOUT_HI, self.img16.data_ptr(), d,
-                               self.rn[0].data_ptr(), self.rn[1].data_ptr(), sp + 32, st), "leccr_prep")
-        N.check(lib.leccr_prep(self.txt.data_ptr(), self.n_txt, d, d, 0, self.fmt, N.LAYOUT_HI, self.txt16.data_ptr(), d,
-                               self.rn[2].data_ptr(), self.rn[3].data_ptr(), sp + 48, st), "leccr_prep")
+        N.check(lib.leccr_prep_pair(self.img.data_ptr(), self.n_img, d, self.img16.data_ptr(), d, self.rn[0].data_ptr(),
+                                    self.rn[1].data_ptr(), sp + 32, self.txt.data_ptr(), self.n_txt, d,
+                                    self.txt16.data_ptr(), d, self.rn[2].data_ptr(), self.rn[3].data_ptr(), sp + 48, d, 0,
+                                    self.fmt, N.LAYOUT_HI, st), "leccr_prep_pair")
         N.check(lib.leccr_sim_topk(self.probs, 2, d, self.fmt, self.k, self.tpc, self.ws.data_ptr(), self.ws.numel(), st),
                 "leccr_sim_topk")
 
