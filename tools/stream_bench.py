@@ -21,7 +21,7 @@ def h2d(): dsti.copy_(img_h, non_blocking=True); dst.copy_(txt_h, non_blocking=T
 print(f"pure H2D of 30.72 MB: {timed(h2d):.3f} ms")
 g = leccr_b200.FusedEvalPlan(5000, 25000, 256, gt=gt)
 print(f"graph plan e2e: {timed(lambda: g.run(img_h, txt_h)):.3f} ms")
-for W, a, b in [(3, 2, 3), ((0.4, 0.3, 0.2, 0.1), 2, 3), ((0.45, 0.35, 0.2), 2, 3), ((0.5, 0.3, 0.2), 2, 2), ((0.35, 0.3, 0.2, 0.15), 2, 3), ((4, 3, 2, 1), 1, 2), ((5,4,3,2,1,1), 1, 2)]:
+for W, a, b in [(3, 2, 3), ((0.36, 0.36, 0.28), 2, 3), ((0.4, 0.35, 0.25), 2, 3), ((0.38, 0.34, 0.28), 2, 2), (4, 2, 3), ((0.3, 0.3, 0.25, 0.15), 2, 3), (3, 2, 2)]:
     p = leccr_b200.StreamedEvalPlan(5000, 25000, 256, gt=gt, windows=W, img_subs=a, txt_subs=b)
     ev = p.run(img_h, txt_h)
     print(f"eager {timed(lambda: p.run(img_h, txt_h, graph=False)):.3f} ms; graph: streamed windows={[e-b for b,e in p.bounds]} img_subs={a} txt_subs={b}: {timed(lambda: p.run(img_h, txt_h)):.3f} ms  r1 {ev['txt_r1']:.2f}/{ev['img_r1']:.3f}", flush=True)
