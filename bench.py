@@ -23,7 +23,6 @@ collective; value = all ranks' queries / max-over-ranks device time.
 import argparse
 import json
 import os
-import subprocess
 import sys
 import time
 

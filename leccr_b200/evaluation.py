@@ -381,8 +381,6 @@ class StreamedEvalPlan:
 
     def __init__(self, n_img, n_txt, dim, txt2img=None, img2txt=None, k=10, precision="f16", gt=None,
                  windows=3, img_subs=2, txt_subs=3):
-        import ctypes
-
         self.dev = _device()
         lib = N.load()
         self.lib = lib
