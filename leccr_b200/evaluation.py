@@ -72,13 +72,41 @@ def _is_transpose_view(a: np.ndarray, b: np.ndarray) -> bool:
             and b.__array_interface__['data'][0] == a.__array_interface__['data'][0])
 
 
+# evaluation_coarse returns numpy matrices because the reference's main() expects them (:163), and itm_eval then
+# receives the same arrays back: the device copy is kept (a few entries, dropped when the array dies) so the
+# N x M matrix crosses PCIe once instead of twice.  The arrays are handed out read-only; a caller that makes one
+# writeable again gets the plain host path.
+_device_copies = {}
+
+
+def _remember_device_copy(arr: np.ndarray, dev_tensor: torch.Tensor):
+    import weakref
+
+    arr.flags.writeable = False
+    key = id(arr)
+    _device_copies[key] = (weakref.ref(arr, lambda _r, k=key: _device_copies.pop(k, None)), dev_tensor)
+    while len(_device_copies) > 8:
+        _device_copies.pop(next(iter(_device_copies)))
+
+
+def _device_copy_of(arr):
+    if not isinstance(arr, np.ndarray):
+        return None
+    hit = _device_copies.get(id(arr))
+    if hit is None or hit[0]() is not arr or arr.flags.writeable or hit[1].shape != arr.shape:
+        return None
+    return hit[1]
+
+
 @torch.no_grad()
 def itm_eval(scores_i2t, scores_t2i, txt2img, img2txt):
     """Drop-in for itm_eval: ranks every row on the GPU (one pass over the matrix per direction)."""
     dev = _device()
     n_img, n_txt = scores_i2t.shape
     gi, gt = _gt_lists(txt2img, img2txt, n_img, n_txt)
-    S = _to_device(scores_i2t, dev, torch.float32)
+    S = _device_copy_of(scores_i2t)
+    if S is None:
+        S = _to_device(scores_i2t, dev, torch.float32)
     r_i = ops.rank_rows(S, *ops.csr_from_lists(gi, dev))
     if _is_transpose_view(scores_i2t, scores_t2i) or scores_t2i is None:
         r_t = ops.rank_cols(S, *ops.csr_from_lists(gt, dev))  # the reference's t2i IS i2t.T (:152)
@@ -177,7 +205,9 @@ def evaluation_coarse(model, data_loader, tokenizer, device, config, distributed
         image_feat = image_feat.transpose(0, 1).contiguous()
         image_embeds.append(model.get_features(image_embeds=image_feat))
     image_embeds = torch.cat(image_embeds, dim=0)
-    i2t = score_matrix(image_embeds, text_embeds, _dist_scale(distributed)).cpu().numpy()
+    S = score_matrix(image_embeds, text_embeds, _dist_scale(distributed))
+    i2t = S.cpu().numpy()
+    _remember_device_copy(i2t, S)
     return i2t, i2t.T
 
 
@@ -200,8 +230,9 @@ def evaluation_coarse_video(model, data_loader, tokenizer, device, config, alpha
         caption_embeds.append(model.caption_proj1(caption_embed))
     image_embeds = torch.cat(image_embeds, dim=0)
     caption_embeds = torch.cat(caption_embeds, dim=1)
-    i2t = double_sim_matrix(image_embeds, text_embeds, caption_embeds, alpha, "norm",
-                            _dist_scale(distributed)).cpu().numpy()
+    S = double_sim_matrix(image_embeds, text_embeds, caption_embeds, alpha, "norm", _dist_scale(distributed))
+    i2t = S.cpu().numpy()
+    _remember_device_copy(i2t, S)
     return i2t, i2t.T
 
 

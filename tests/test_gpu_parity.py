@@ -189,6 +189,23 @@ def test_argument_errors_are_loud():
     rc = lib.leccr_sim_f32(a.t16.data_ptr() + 2, 64, a.t16.data_ptr(), 64, 16, 16, 64, 0, out.data_ptr(), 16, 1.0,
                            None, None)
     assert rc == -2  # LECCR_ERR_ALIGN
+    # the entries added later fail as loudly: status codes, never a silent fallback
+    S = torch.zeros(8, 8, device="cuda")
+    v, i = torch.empty(8, 17, device="cuda"), torch.empty(8, 17, dtype=torch.int32, device="cuda")
+    assert lib.leccr_topk_dense(S.data_ptr(), 8, 8, 8, 0, 17, v.data_ptr(), i.data_ptr(), None) == -1       # k > 16
+    assert lib.leccr_caploss_fwd(None, 0, None, 0, 2, 8, 24, 0, None, None, None, None, None, None, 0, None) == -1
+    assert lib.leccr_dstl_bwd(None, None, None, None, 0, None, 0, 8, 8, 0, 0, 8, None, None, None, None, 0, None) == -1
+    assert lib.leccr_peer_barrier(None, 2, 0, 1, None) == -1
+    assert lib.leccr_topk_merge_peers(None, None, 2, 10, 0, 4, None, 10, None, None, None) == -1
+    pr = (N.TopkProblem * 1)()
+    so = (N.TopkStream * 1)()
+    so[0].phases, so[0].sub_begin, so[0].sub_count, so[0].sub_total = N.TOPK_GEMM, 3, 2, 4                     # slots 3..4 of 4
+    assert lib.leccr_sim_topk_stream(pr, so, 1, 64, 0, 10, None) == -1
+    with pytest.raises(ValueError):
+        leccr_b200.fused_eval(rs.image, rs.text, rs.txt2img, rs.img2txt, fusion="max")
+    with pytest.raises(ValueError):
+        leccr_b200.caption_contrastive_loss(torch.zeros(2, 4, 8, device="cuda"), torch.zeros(5, 8, device="cuda"),
+                                            torch.tensor(0.07, device="cuda"))
 
 
 # ----------------------------------------------------------------------------- contrastive loss
@@ -569,3 +586,41 @@ def test_exact_rank_fallback_for_scores_tied_inside_the_16bit_tolerance():
     assert (got[~small] >= 10).all()                        # lower bounds at or above it
     c = res.recall_counts.cpu().tolist()
     assert c == [int((want < 1).sum()), int((want < 5).sum()), int((want < 10).sum())]
+
+
+# ----------------------------------------------------------------------------- evaluation_coarse drop-ins
+def _fake_loader(n_items, n_text, video):
+    from oracle import make_golden as mg
+
+    loader = mg._loader(n_items, 32, video=video)
+    loader.dataset.text = [str(t) for t in range(n_text)]
+    return loader
+
+
+def test_evaluation_coarse_dropins_with_the_fake_model_of_the_goldens(golden):
+    """Our evaluation_coarse / evaluation_coarse_video driven by the SAME fake model / loader / tokenizer objects
+    that drove the reference's functions when the goldens were made (oracle/make_golden.py): same matrices, same
+    transpose-view contract, and itm_eval on the returned arrays gives the reference's dict (re-using the device
+    copy of the matrix)."""
+    from oracle import make_golden as mg
+
+    g = golden("image_small.npz")
+    rs = synth.retrieval_set(40, 5, d=64, seed=11)
+    model = mg._ImageModel(rs.image.cuda(), rs.text.cuda())
+    i2t, t2i = leccr_b200.evaluation_coarse(model, _fake_loader(40, 200, False), mg._Tok(), "cuda", mg.CONFIG)
+    assert isinstance(i2t, np.ndarray) and i2t.dtype == np.float32 and i2t.shape == (40, 200)
+    assert t2i.shape == (200, 40) and np.shares_memory(i2t, t2i) and not t2i.flags["C_CONTIGUOUS"]   # the view of :152
+    assert np.abs(i2t - g["i2t"]).max() < X3_TOL
+    assert leccr_b200.evaluation._device_copy_of(i2t) is not None
+    txt2img = {t: t // 5 for t in range(200)}
+    img2txt = {i: list(range(5 * i, 5 * i + 5)) for i in range(40)}
+    assert_ev_equal(leccr_b200.itm_eval(i2t, t2i, txt2img, img2txt), ev_of(g, "ev_"))
+    assert_ev_equal(leccr_b200.itm_eval(i2t.copy(), t2i.copy(), txt2img, img2txt), ev_of(g, "ev_"))   # host path
+
+    gv = golden("video_small.npz")
+    rv = synth.retrieval_set(48, 1, d=64, seed=12, n_caption_queries=2)
+    vmodel = mg._VideoModel(rv.image.cuda(), rv.text.cuda(), rv.caption.cuda())
+    vi2t, vt2i = leccr_b200.evaluation_coarse_video(vmodel, _fake_loader(48, 48, True), mg._Tok(), "cuda", mg.CONFIG,
+                                                    alpha=0.9)
+    assert np.abs(vi2t - gv["i2t"]).max() < 2e-5 and np.abs(vt2i - gv["t2i"]).max() < 2e-5
+    assert_ev_equal(leccr_b200.itm_eval(vi2t, vt2i, rv.txt2img, rv.img2txt), ev_of(gv, "ev_"))
