@@ -95,17 +95,26 @@ class _GatherRows(torch.autograd.Function):
         return g[ctx.b * ctx.rank: ctx.b * (ctx.rank + 1)], None, None
 
 
+def gather_packed(image_embeds, caption_embeds, text_embeds_s, text_embeds_t, rank, world):
+    """The reference's four all-gathers (models/model_retrieval_caption.py:95-98) as ONE collective: every rank
+    sends rows [image | text_s | text_t | caption_0 .. caption_{n-1}]; returns (image_all [N, d], caption_all
+    [n, N, d], text_s_all, text_t_all) in rank order, with AllGather's backward (local slice) on all of them."""
+    n, B, D = caption_embeds.shape
+    packed = torch.cat([image_embeds, text_embeds_s, text_embeds_t, caption_embeds.transpose(0, 1).reshape(B, n * D)], 1)
+    allp = _GatherRows.apply(packed, rank, world)
+    image_all, ts_all, tt_all = allp[:, :D], allp[:, D:2 * D], allp[:, 2 * D:3 * D]
+    cap_all = allp[:, 3 * D:].reshape(world * B, n, D).transpose(0, 1)
+    return image_all, cap_all, ts_all, tt_all
+
+
 def dstl_loss(self, image_embeds, caption_embeds, text_embeds_s, text_embeds_t, idx, alpha=0.8):
     """Same contract as models/model_retrieval_caption.py:94-116; bind as a method of RetrievalModel."""
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
-    n, B, D = caption_embeds.shape
+    B = image_embeds.shape[0]
     if world > 1:
-        # one collective for the four tensors: rows [image | text_s | text_t | caption_0 .. caption_{n-1}]
-        packed = torch.cat([image_embeds, text_embeds_s, text_embeds_t, caption_embeds.transpose(0, 1).reshape(B, n * D)], 1)
-        allp = _GatherRows.apply(packed, rank, world)
-        image_all, ts_all, tt_all = allp[:, :D], allp[:, D:2 * D], allp[:, 2 * D:3 * D]
-        cap_all = allp[:, 3 * D:].reshape(world * B, n, D).transpose(0, 1)
+        image_all, cap_all, ts_all, tt_all = gather_packed(image_embeds, caption_embeds, text_embeds_s, text_embeds_t,
+                                                           rank, world)
     else:
         image_all, ts_all, tt_all, cap_all = image_embeds, text_embeds_s, text_embeds_t, caption_embeds
     return dstl_loss_gathered(image_all, cap_all, ts_all, tt_all, alpha, rank * B, B)

@@ -180,3 +180,50 @@ def test_install_rebinds_the_reference_names():
     assert list(inspect.signature(leccr_b200.dstl_loss).parameters) == ["self", "image_embeds", "caption_embeds", "text_embeds_s", "text_embeds_t", "idx", "alpha"]
     assert list(inspect.signature(leccr_b200.itm_eval).parameters) == ["scores_i2t", "scores_t2i", "txt2img", "img2txt"]
     assert list(inspect.signature(script.evaluation_coarse).parameters) == ["model", "data_loader", "tokenizer", "device", "config"]
+
+
+def _packed_gather_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from leccr_b200.dstl_loss import gather_packed
+
+    g = torch.Generator().manual_seed(3)
+    n, B, D = 3, 5, 8
+    image = torch.randn(world * B, D, generator=g)
+    ts = torch.randn(world * B, D, generator=g)
+    tt = torch.randn(world * B, D, generator=g)
+    cap = torch.randn(n, world * B, D, generator=g)
+    sl = slice(rank * B, (rank + 1) * B)
+    loc = [image[sl].clone().requires_grad_(True), cap[:, sl].clone().requires_grad_(True),
+           ts[sl].clone().requires_grad_(True), tt[sl].clone().requires_grad_(True)]
+    im_all, cap_all, ts_all, tt_all = gather_packed(loc[0], loc[1], loc[2], loc[3], rank, world)
+    fwd_ok = bool(torch.equal(im_all, image) and torch.equal(cap_all, cap) and torch.equal(ts_all, ts)
+                  and torch.equal(tt_all, tt))
+    # backward: every gathered element weighted by a distinct number; each rank must get its own slice back
+    w = [torch.arange(t.numel(), dtype=torch.float32).view_as(t) + 1000 * k for k, t in enumerate((image, cap, ts, tt))]
+    (im_all * w[0]).sum().add((cap_all * w[1]).sum()).add((ts_all * w[2]).sum()).add((tt_all * w[3]).sum()).backward()
+    bwd_ok = bool(torch.equal(loc[0].grad, w[0][sl]) and torch.equal(loc[1].grad, w[1][:, sl])
+                  and torch.equal(loc[2].grad, w[2][sl]) and torch.equal(loc[3].grad, w[3][sl]))
+    q.put((rank, fwd_ok, bwd_ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dstl_packed_gather_two_ranks_gloo():
+    """dstl_loss issues the reference's four all-gathers (models/model_retrieval_caption.py:95-98) as one collective:
+    same gathered tensors in rank order, and AllGather's backward (own slice, no reduction) on each of them."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_packed_gather_worker, args=(r, 2, 29613, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    for rank, fwd_ok, bwd_ok in res:
+        assert fwd_ok and bwd_ok, (rank, fwd_ok, bwd_ok)
