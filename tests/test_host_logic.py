@@ -227,3 +227,48 @@ def test_dstl_packed_gather_two_ranks_gloo():
         p.join(timeout=60)
     for rank, fwd_ok, bwd_ok in res:
         assert fwd_ok and bwd_ok, (rank, fwd_ok, bwd_ok)
+
+
+def _project_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from leccr_b200.contrastive import _project
+
+    g = torch.Generator().manual_seed(4)
+    lin = torch.nn.Linear(6, 6)
+    with torch.no_grad():
+        lin.weight.copy_(torch.randn(6, 6, generator=g))
+        lin.bias.copy_(torch.randn(6, generator=g))
+    x_all = torch.randn(world * 4, 3, 6, generator=g)
+    x = x_all[rank * 4:(rank + 1) * 4].clone().requires_grad_(True)
+    _project(lin, x, world).pow(2).sum().backward()
+    # what the reference's module holds after projecting ALL gathered rows: the full parameter gradient
+    ref = torch.nn.Linear(6, 6)
+    ref.load_state_dict(lin.state_dict())
+    xr = x_all.clone().requires_grad_(True)
+    ref(xr).pow(2).sum().backward()
+    ok = bool(torch.allclose(lin.weight.grad, ref.weight.grad, rtol=1e-5, atol=1e-6)
+              and torch.allclose(lin.bias.grad, ref.bias.grad, rtol=1e-5, atol=1e-6)
+              and torch.allclose(x.grad, xr.grad[rank * 4:(rank + 1) * 4], rtol=1e-5, atol=1e-6))
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_caption_vision_projection_gradients_two_ranks_gloo():
+    """caption_vision_loss projects before the gather; the parameter gradients of cproj / vproj must still be the
+    reference's (projection after the gather: every rank's module sees all rows), the input gradients local."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_project_worker, args=(r, 2, 29615, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
