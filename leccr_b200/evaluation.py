@@ -587,15 +587,18 @@ class StreamedEvalPlan:
         pinned = (not img_h.is_cuda) and (not txt_h.is_cuda) and img_h.is_pinned() and txt_h.is_pinned() \
             and img_h.is_contiguous() and txt_h.is_contiguous()
         key = (img_h.data_ptr(), txt_h.data_ptr())
-        if graph and pinned and getattr(self, "_graph_key", None) == key:
-            self._graph.replay()
+        graphs = self.__dict__.setdefault("_graphs", {})  # one graph per pair of pinned buffers (a few are kept)
+        if graph and pinned and key in graphs:
+            graphs[key][0].replay()
         elif graph and pinned:
             self._issue(img_h, txt_h)  # eager once: lazy initialisation must not happen under capture
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._issue(img_h, txt_h)
-            self._graph, self._graph_key, self._graph_src = g, key, (img_h, txt_h)
+            while len(graphs) >= 4:
+                graphs.pop(next(iter(graphs)))
+            graphs[key] = (g, img_h, txt_h)  # the buffers stay referenced: the graph holds their addresses
             g.replay()
         else:
             self._issue(img_h, txt_h)
