@@ -816,39 +816,42 @@ __device__ __forceinline__ void exact_rank_rows(const TopkFinalizeParams& P, flo
   for (int fi = blockIdx.x; fi < n_flagged; fi += gridDim.x) {
     const int row = P.flag_list[fi];
     const int g0 = P.gt_off[row];
-    const int ng = min(P.gt_off[row + 1] - g0, 16);
-    __syncthreads();
-    if (warp == 0) {
-      for (int gi = 0; gi < ng; ++gi) {
-        const float tg = warp_dot(P.rows_x, P.ld_rows, row, P.cols_x, P.ld_cols, P.gt_ids[g0 + gi],
-                                  P.D, P.x_dtype, lane);
-        if (lane == 0) {
-          s_tg[gi] = tg;
-          s_cnt[gi] = 0;
+    const int ng_all = P.gt_off[row + 1] - g0;
+    int best = 0x7fffffff;  // thread 0's running minimum over the ground-truth chunks
+    // any number of ground-truth entries per row (image_Retrieval_caption.py:274-278): chunks of kGtChunk
+    for (int gb = 0; gb < ng_all; gb += 16) {
+      const int ng = min(ng_all - gb, 16);
+      __syncthreads();
+      if (warp == 0) {
+        for (int gi = 0; gi < ng; ++gi) {
+          const float tg = warp_dot(P.rows_x, P.ld_rows, row, P.cols_x, P.ld_cols, P.gt_ids[g0 + gb + gi],
+                                    P.D, P.x_dtype, lane);
+          if (lane == 0) {
+            s_tg[gi] = tg;
+            s_cnt[gi] = 0;
+          }
         }
       }
-    }
-    __syncthreads();
-    int cnt[16];
+      __syncthreads();
+      int cnt[16];
 #pragma unroll
-    for (int gi = 0; gi < 16; ++gi) cnt[gi] = 0;
-    for (int j = warp; j < P.n_cols; j += nw) {
-      const float tj = warp_dot(P.rows_x, P.ld_rows, row, P.cols_x, P.ld_cols, j, P.D, P.x_dtype, lane);
+      for (int gi = 0; gi < 16; ++gi) cnt[gi] = 0;
+      for (int j = warp; j < P.n_cols; j += nw) {
+        const float tj = warp_dot(P.rows_x, P.ld_rows, row, P.cols_x, P.ld_cols, j, P.D, P.x_dtype, lane);
 #pragma unroll
-      for (int gi = 0; gi < 16; ++gi)
-        if (gi < ng && tj > s_tg[gi]) ++cnt[gi];
-    }
-    if (lane == 0) {
+        for (int gi = 0; gi < 16; ++gi)
+          if (gi < ng && tj > s_tg[gi]) ++cnt[gi];
+      }
+      if (lane == 0) {
 #pragma unroll
-      for (int gi = 0; gi < 16; ++gi)
-        if (gi < ng && cnt[gi]) atomicAdd(&s_cnt[gi], cnt[gi]);
+        for (int gi = 0; gi < 16; ++gi)
+          if (gi < ng && cnt[gi]) atomicAdd(&s_cnt[gi], cnt[gi]);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0)
+        for (int gi = 0; gi < ng; ++gi) best = min(best, s_cnt[gi]);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int best = 0x7fffffff;
-      for (int gi = 0; gi < ng; ++gi) best = min(best, s_cnt[gi]);
-      P.rank[row] = best == 0x7fffffff ? kRankCap : best;
-    }
+    if (threadIdx.x == 0) P.rank[row] = best == 0x7fffffff ? kRankCap : best;
   }
 }
 
@@ -913,46 +916,49 @@ __global__ void rank_post_kernel(const TopkFinalizeParams P0, const TopkFinalize
 //   rank_cols: for column c, rank = min_{g in gt(c)} #{r : S[r][c] > S[g][c]}      (t2i read
 //              from the same row-major matrix; the reference's t2i matrix is its transpose view)
 // --------------------------------------------------------------------------------
-constexpr int kMaxGt = 16;
+constexpr int kGtChunk = 16;  // ground-truth entries handled per sweep; longer lists take more sweeps
 
 __global__ void rank_rows_kernel(const float* __restrict__ S, long long ld, int R, int C,
                                  const int* __restrict__ gt_off, const int* __restrict__ gt_ids,
                                  int* __restrict__ rank) {
-  __shared__ float s_t[kMaxGt];
-  __shared__ int s_c[kMaxGt];
+  __shared__ float s_t[kGtChunk];
+  __shared__ int s_c[kGtChunk];
   const int row = blockIdx.x;
   if (row >= R) return;
   const float* s = S + static_cast<long long>(row) * ld;
   const int g0 = gt_off[row];
-  const int ng = min(gt_off[row + 1] - g0, kMaxGt);
-  if (threadIdx.x < ng) {
-    s_t[threadIdx.x] = s[gt_ids[g0 + threadIdx.x]];
-    s_c[threadIdx.x] = 0;
-  }
-  __syncthreads();
-  int cnt[kMaxGt];
-#pragma unroll
-  for (int g = 0; g < kMaxGt; ++g) cnt[g] = 0;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float v = __ldg(s + c);
-#pragma unroll
-    for (int g = 0; g < kMaxGt; ++g)
-      if (g < ng && v > s_t[g]) ++cnt[g];
-  }
-#pragma unroll
-  for (int g = 0; g < kMaxGt; ++g) {
-    if (g < ng) {
-      int v = cnt[g];
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_c[g], v);
+  const int ng_all = gt_off[row + 1] - g0;
+  int best = 0x7fffffff;  // thread 0's minimum over all ground-truth entries (:274-278 takes the min over every one)
+  for (int gb = 0; gb < ng_all; gb += kGtChunk) {
+    const int ng = min(ng_all - gb, kGtChunk);
+    __syncthreads();
+    if (threadIdx.x < ng) {
+      s_t[threadIdx.x] = s[gt_ids[g0 + gb + threadIdx.x]];
+      s_c[threadIdx.x] = 0;
     }
+    __syncthreads();
+    int cnt[kGtChunk];
+#pragma unroll
+    for (int g = 0; g < kGtChunk; ++g) cnt[g] = 0;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float v = __ldg(s + c);
+#pragma unroll
+      for (int g = 0; g < kGtChunk; ++g)
+        if (g < ng && v > s_t[g]) ++cnt[g];
+    }
+#pragma unroll
+    for (int g = 0; g < kGtChunk; ++g) {
+      if (g < ng) {
+        int v = cnt[g];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_c[g], v);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (int g = 0; g < ng; ++g) best = min(best, s_c[g]);
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int best = 0x7fffffff;
-    for (int g = 0; g < ng; ++g) best = min(best, s_c[g]);
-    rank[row] = best == 0x7fffffff ? C : best;
-  }
+  if (threadIdx.x == 0) rank[row] = best == 0x7fffffff ? C : best;
 }
 
 // One thread per column, rows split over blockIdx.y; partial counts combined with atomicAdd into
@@ -963,24 +969,27 @@ __global__ void rank_cols_count_kernel(const float* __restrict__ S, long long ld
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const int g0 = gt_off[c];
-  const int ng = min(gt_off[c + 1] - g0, kMaxGt);
-  float t[kMaxGt];
-  int cnt[kMaxGt];
-#pragma unroll
-  for (int g = 0; g < kMaxGt; ++g) {
-    cnt[g] = 0;
-    t[g] = (g < ng) ? __ldg(S + static_cast<long long>(gt_ids[g0 + g]) * ld + c) : CUDART_INF_F;
-  }
+  const int ng_all = gt_off[c + 1] - g0;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(R, r0 + rows_per_block);
-  for (int r = r0; r < r1; ++r) {
-    const float v = __ldg(S + static_cast<long long>(r) * ld + c);
+  for (int gb = 0; gb < ng_all; gb += kGtChunk) {  // one sweep per kGtChunk ground-truth entries (normally one)
+    const int ng = min(ng_all - gb, kGtChunk);
+    float t[kGtChunk];
+    int cnt[kGtChunk];
 #pragma unroll
-    for (int g = 0; g < kMaxGt; ++g) cnt[g] += (v > t[g]) ? 1 : 0;
+    for (int g = 0; g < kGtChunk; ++g) {
+      cnt[g] = 0;
+      t[g] = (g < ng) ? __ldg(S + static_cast<long long>(gt_ids[g0 + gb + g]) * ld + c) : CUDART_INF_F;
+    }
+    for (int r = r0; r < r1; ++r) {
+      const float v = __ldg(S + static_cast<long long>(r) * ld + c);
+#pragma unroll
+      for (int g = 0; g < kGtChunk; ++g) cnt[g] += (v > t[g]) ? 1 : 0;
+    }
+#pragma unroll
+    for (int g = 0; g < kGtChunk; ++g)
+      if (g < ng && cnt[g]) atomicAdd(cnt_nnz + g0 + gb + g, cnt[g]);
   }
-#pragma unroll
-  for (int g = 0; g < kMaxGt; ++g)
-    if (g < ng && cnt[g]) atomicAdd(cnt_nnz + g0 + g, cnt[g]);
 }
 
 __global__ void rank_cols_min_kernel(int C, int R, const int* __restrict__ gt_off,
@@ -988,7 +997,7 @@ __global__ void rank_cols_min_kernel(int C, int R, const int* __restrict__ gt_of
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   int best = 0x7fffffff;
-  const int g1 = min(gt_off[c + 1], gt_off[c] + kMaxGt);
+  const int g1 = gt_off[c + 1];
   for (int g = gt_off[c]; g < g1; ++g) best = min(best, cnt_nnz[g]);
   rank[c] = best == 0x7fffffff ? R : best;
 }

@@ -278,3 +278,28 @@ def topk(scores: np.ndarray, k: int):
     leaves unspecified at ties)."""
     order = np.lexsort((np.arange(scores.shape[1])[None, :].repeat(scores.shape[0], 0), -scores), axis=1)[:, :k]
     return np.take_along_axis(scores, order, 1), order
+
+
+# ----------------------------------------------------------------------------- large-gallery retrieval (cfg5)
+def gallery_eval(gallery: torch.Tensor, queries: torch.Tensor, gt: Sequence[int], k: int = 10):
+    """BASELINE.json configs[4]: every query ranks the whole gallery, one ground-truth gallery row per query.
+    The reference would run it as its text->image direction: score = gallery @ queries.T
+    (image_Retrieval_caption.py:151), t2i = its transpose (:152), then per query a full np.argsort and the
+    position of the ground truth (:288-290), Recall@1/5/10 (:293-295).  16-bit inputs are scored in fp32, as
+    `.float()` embeddings would be.  Returns (recall dict img_r1/5/10, top-k values, top-k gallery rows)."""
+    t2i = (gallery.float() @ queries.float().t()).t().cpu().numpy()
+    ranks = np.zeros(t2i.shape[0])
+    top = np.zeros((t2i.shape[0], k), dtype=np.int64)
+    for index, score in enumerate(t2i):
+        inds = np.argsort(score)[::-1]
+        ranks[index] = np.where(inds == int(gt[index]))[0][0]
+        top[index] = inds[:k]
+    ev = {f"img_r{c}": 100.0 * len(np.where(ranks < c)[0]) / len(ranks) for c in (1, 5, 10)}
+    return ev, np.take_along_axis(t2i, top, 1), top
+
+
+# ----------------------------------------------------------------------------- get_features (SURVEY section 8f rank 3)
+def get_features(tokens: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """models/xvlm.py:241-256 for one modality with the default 'cls' pooling:
+    F.normalize(proj(embeds[:, 0, :]), dim=-1)."""
+    return F.normalize(F.linear(tokens[:, 0, :], weight, bias), dim=-1)

@@ -624,3 +624,46 @@ def test_evaluation_coarse_dropins_with_the_fake_model_of_the_goldens(golden):
                                                     alpha=0.9)
     assert np.abs(vi2t - gv["i2t"]).max() < 2e-5 and np.abs(vt2i - gv["t2i"]).max() < 2e-5
     assert_ev_equal(leccr_b200.itm_eval(vi2t, vt2i, rv.txt2img, rv.img2txt), ev_of(gv, "ev_"))
+
+
+# ----------------------------------------------------------------------------- ground-truth lists of any length
+def test_more_than_16_ground_truth_entries_per_row(golden):
+    """20 ground-truth texts per image (MSR-VTT's layout, run_video.sh): the reference takes the minimum rank over
+    EVERY entry of img2txt[index] (image_Retrieval_caption.py:274-278); golden made by the reference's itm_eval."""
+    g = golden("gt20_small.npz")
+    i2t = g["i2t"]
+    n, m = i2t.shape
+    txt2img = {t: t // 20 for t in range(m)}
+    img2txt = {i: list(range(20 * i, 20 * i + 20)) for i in range(n)}
+    want = ev_of(g, "ev_")
+    assert_ev_equal(leccr_b200.itm_eval(i2t, i2t.T, txt2img, img2txt), want)                         # rank_rows + rank_cols
+    assert_ev_equal(leccr_b200.itm_eval(i2t, np.ascontiguousarray(i2t.T), txt2img, img2txt), want)  # rank_rows twice
+    assert_ev_equal(leccr_b200.fused_eval(g["image"], g["text"], txt2img, img2txt, return_topk=False), want)
+    assert_ev_equal(leccr_b200.fused_eval(g["image"], g["text"], txt2img, img2txt, return_topk=False,
+                                          caption_embeds=np.zeros((1, n, 64), np.float32), alpha=1.0, fusion="raw"), want)
+    # columns with 20 ground-truth rows each: rank the columns of the contiguous t2i matrix
+    S = torch.from_numpy(np.ascontiguousarray(i2t.T)).cuda()
+    gi = ops.csr_from_lists([img2txt[i] for i in range(n)], "cuda")
+    want_r = oracle.ranks_by_count(i2t, [img2txt[i] for i in range(n)])
+    assert np.array_equal(ops.rank_cols(S, *gi).cpu().numpy(), want_r)
+    assert np.array_equal(ops.rank_rows(torch.from_numpy(i2t).cuda(), *gi).cpu().numpy(), want_r)
+
+
+def test_exact_rank_fallback_with_a_long_ground_truth_list():
+    """The exact fp32 fallback (rows whose ground truth ties inside the 16-bit tolerance) walks the whole
+    ground-truth list: the best entry sits at position 18 of 20."""
+    g = torch.Generator().manual_seed(8)
+    d, n_q = 256, 64
+    base = torch.nn.functional.normalize(torch.randn(n_q, d, generator=g), dim=-1)
+    filler = torch.nn.functional.normalize(torch.randn(600, d, generator=g), dim=-1)
+    copies = torch.cat([base[0:1] * (1.0 - 1e-5 * j) for j in range(40)], 0)    # query 0: 40 near-ties
+    gallery = torch.cat([copies, filler], 0).contiguous()
+    lists = [[100 + j for j in range(17)] + [3] + [200, 201]] + [[40 + q] for q in range(1, n_q)]
+    gt = ops.csr_from_lists(lists, "cuda")
+    res, = ops.sim_topk([(ops.prep(base.cuda()), ops.prep(gallery.cuda()), gt)], k=10)
+    S = (base.double() @ gallery.double().t()).numpy()
+    want = oracle.ranks_by_count(S, lists)
+    assert want[0] == 3
+    got = res.rank.cpu().numpy()
+    small = want < 10
+    assert np.array_equal(got[small], want[small]) and (got[~small] >= 10).all()

@@ -153,3 +153,37 @@ def test_caption_vision_loss_matches_reference(golden):
             for got, key in ((dim, "dimage"), (dcp, "dcaption"), (dwc, "dWc"), (dwv, "dWv")):
                 ref = g[f"{name}_r{rank}_{key}"]
                 assert np.abs(got.numpy() - ref).max() <= 2e-5 * np.abs(ref).max() + 1e-9, key
+
+
+def test_gt20_small_every_ground_truth_entry_counts(golden):
+    """20 ground-truth texts per image (the MSR-VTT layout): rank = min over ALL of them (:274-278)."""
+    g = golden("gt20_small.npz")
+    n, m = g["i2t"].shape
+    assert m == 20 * n
+    txt2img = {t: t // 20 for t in range(m)}
+    img2txt = {i: list(range(20 * i, 20 * i + 20)) for i in range(n)}
+    want = ev_of(g, "ev_")
+    assert_ev_equal(oracle.itm_eval(g["i2t"], g["i2t"].T, txt2img, img2txt), want)
+    assert_ev_equal(oracle.itm_eval_by_count(g["i2t"], g["i2t"].T, txt2img, img2txt), want)
+    # a reader that stopped after 16 entries would differ on this set (the fixture is only useful if so)
+    cut = oracle.itm_eval_by_count(g["i2t"], g["i2t"].T, txt2img, {i: v[:16] for i, v in img2txt.items()})
+    assert any(float(cut[k]) != want[k] for k in ("txt_r1", "txt_r5", "txt_r10"))
+
+
+def test_gallery_small(golden):
+    """cfg5 in small: the oracle's gallery_eval against the reference's matmul + itm_eval + argsort."""
+    g = golden("gallery_small.npz")
+    gal = torch.from_numpy(g["gallery_bf16_bits"]).view(torch.bfloat16)
+    qry = torch.from_numpy(g["query_bf16_bits"]).view(torch.bfloat16)
+    ev, val, idx = oracle.gallery_eval(gal, qry, g["gt"], k=10)
+    for c in (1, 5, 10):
+        assert ev[f"img_r{c}"] == float(g[f"ev_img_r{c}"])
+    np.testing.assert_allclose(val, g["top10_val"], rtol=0, atol=1e-6)
+    assert (idx == g["top10"]).mean() > 0.999   # argsort order at exact ties is unspecified
+
+
+def test_get_features(golden):
+    g = golden("get_features.npz")
+    for tok, W, b, feat in (("img_tok", "vW", "vb", "feat_i"), ("txt_tok", "tW", "tb", "feat_t")):
+        got = oracle.get_features(torch.from_numpy(g[tok]), torch.from_numpy(g[W]), torch.from_numpy(g[b]))
+        np.testing.assert_allclose(got.numpy(), g[feat], rtol=0, atol=1e-6)
