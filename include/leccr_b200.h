@@ -157,6 +157,8 @@ int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
 #define LECCR_TOPK_INIT 1     /* first call of a problem: reset its workspace */
 #define LECCR_TOPK_GEMM 2     /* similarity + candidate lists for the columns given */
 #define LECCR_TOPK_FINALIZE 4 /* merge all slots: top-k, exact ranks, Recall counts */
+#define LECCR_TOPK_LONG 8     /* set on EVERY call of a problem whose windows are long (> 8192 columns per slot,
+                                 e.g. the gallery windows of a 1M-row search): filter-epilogue list shape */
 typedef struct leccr_topk_stream {
   int32_t phases;
   int32_t sub_begin, sub_count, sub_total;
@@ -228,6 +230,8 @@ int leccr_double_sim_fuse(float* S, const float* Cn, int n_cap, int64_t numel, f
  *
  * leccr_peer_barrier: stream-ordered barrier across the ranks.  flag_ptrs_dev[p] -> rank p's block of
  *   `world` uint32 words (zero-initialised once); `epoch` must grow by one per barrier on every rank.
+ *   The wait is bounded by wall time: LECCR_PEER_TIMEOUT_S seconds (default 600, 0 = for ever), then the
+ *   kernel reports the missing peer and traps.
  *   Orders all earlier peer stores of this stream before all later work of the peers' streams.
  * leccr_topk_merge_peers: the exchange step of the row-partitioned gallery (replaces nothing in the
  *   reference, which ranks on one CPU; north_star layout).  Rank p published its per-query local top-k
@@ -236,6 +240,11 @@ int leccr_double_sim_fuse(float* S, const float* Cn, int n_cap, int64_t numel, f
  *   ONE kernel: out [q_count][k_out], global column = local + col_offset_host[p].
  * ------------------------------------------------------------------------------------------ */
 int leccr_peer_barrier(uint32_t* const* flag_ptrs_dev, int world, int rank, uint32_t epoch, leccr_stream_t stream);
+/* leccr_memcpy_peer_async: stream-ordered copy between device pointers, either of which may be a peer-mapped
+ * address (copy engines over NVLink, no SMs): the gallery windows a rank uploaded are pushed to the ranks
+ * that share its gallery part while the tensor cores rank the windows that have arrived (the reference moves
+ * every feature through the host: image_Retrieval_caption.py:163). */
+int leccr_memcpy_peer_async(void* dst, const void* src, size_t bytes, leccr_stream_t stream);
 int leccr_topk_merge_peers(const float* const* val_ptrs_dev, const int32_t* const* idx_ptrs_dev, int world, int k_in,
                            int64_t q_begin, int64_t q_count, const int64_t* col_offset_host, int k_out,
                            float* out_val, int32_t* out_idx, leccr_stream_t stream);

@@ -50,7 +50,7 @@ class TopkStream(ctypes.Structure):
     ]
 
 
-TOPK_INIT, TOPK_GEMM, TOPK_FINALIZE = 1, 2, 4
+TOPK_INIT, TOPK_GEMM, TOPK_FINALIZE, TOPK_LONG = 1, 2, 4, 8
 
 _SIGNATURES = {
     "leccr_strerror": (ctypes.c_char_p, [c_int]),
@@ -89,6 +89,7 @@ _SIGNATURES = {
     "leccr_dstl_bwd_workspace": (sz, [i64, i64, c_int]),
     "leccr_dstl_bwd": (c_int, [vp, vp, vp, vp, i64, vp, i64, i64, c_int, c_int, i64, i64, vp, vp, vp, vp, sz, vp]),
     "leccr_peer_barrier": (c_int, [vp, c_int, c_int, ctypes.c_uint32, vp]),
+    "leccr_memcpy_peer_async": (c_int, [vp, vp, sz, vp]),
     "leccr_topk_merge_peers": (c_int, [vp, vp, c_int, c_int, i64, i64, ctypes.POINTER(i64), c_int, vp, vp, vp]),
     "leccr_stats16": (c_int, [vp, c_int, i64, c_int, i64, vp, vp, vp, vp]),
     "leccr_transpose16": (c_int, [vp, i64, c_int, i64, vp, i64, vp]),
@@ -125,7 +126,7 @@ def load():
     if _lib is not None:
         return _lib
     path = lib_path()
-    if not os.path.exists(path):
+    if _build.is_stale():  # missing, or built from other sources than the ones in the tree
         _build.build()
     lib = ctypes.CDLL(path)
     for name, (res, args) in _SIGNATURES.items():

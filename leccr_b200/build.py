@@ -26,33 +26,65 @@ def nvcc_path():
     raise RuntimeError("nvcc not found; leccr_b200 needs the CUDA toolkit to build its sm_100a library")
 
 
+HASH = LIB + ".srchash"
+
+
+def source_hash():
+    """Content hash of everything the library is compiled from (mtimes do not survive a snapshot copy)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for d in DEPS:
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def is_stale():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(HASH):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(d) > t for d in DEPS)
+    with open(HASH) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
-    """Compile the library if it is missing or older than its sources. Returns the .so path."""
+    """Compile the library if it is missing or was built from other sources. Returns the .so path.
+    Safe under torchrun: one process builds (file lock), into a temporary file that is renamed into place."""
     if not force and not is_stale():
         return LIB
+    import fcntl
+
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [
-        nvcc_path(),
-        "-gencode", "arch=compute_100a,code=sm_100a",
-        "-O3", "-lineinfo", "-std=c++17",
-        "-shared", "-Xcompiler", "-fPIC",
-        "-o", LIB, SRC, "-ldl",
-    ]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        sys.stderr.write(res.stderr)
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():  # another rank built it while we waited
+                return LIB
+            tmp = f"{LIB}.{os.getpid()}.tmp"
+            cmd = [
+                nvcc_path(),
+                "-gencode", "arch=compute_100a,code=sm_100a",
+                "-O3", "-lineinfo", "-std=c++17",
+                "-shared", "-Xcompiler", "-fPIC",
+                "-o", tmp, SRC, "-ldl",
+            ]
+            if verbose:
+                cmd.insert(1, "-Xptxas")
+                cmd.insert(2, "-v")
+            digest = source_hash()
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            if verbose:
+                sys.stderr.write(res.stderr)
+            os.replace(tmp, LIB)
+            with open(HASH + ".tmp", "w") as f:
+                f.write(digest + "\n")
+            os.replace(HASH + ".tmp", HASH)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <atomic>
 #include <mutex>
 
 #include "epilogues.cuh"
@@ -178,12 +179,16 @@ int launch_gemm(const SimLaunch& L, const typename Epi::Params& EP, cudaStream_t
   auto kern = sim_gemm_kernel<Epi, kStages, kBK, kARes>;
   constexpr size_t smem = sim_gemm_smem_bytes<Epi, kStages, kBK, kARes>();
   static_assert(smem <= 232448, "exceeds the 227 KB shared memory limit of sm_100");
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  });
-  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(sim_gemm_kernel)");
+  // function attributes are per device: one flag per device ordinal (a process may drive several GPUs)
+  static std::atomic<int> attr_set[64];
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || attr_set[dev].load(std::memory_order_acquire) == 0) {
+    const cudaError_t attr_err =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(sim_gemm_kernel)");
+    if (dev >= 0 && dev < 64) attr_set[dev].store(1, std::memory_order_release);
+  }
   if (L.n_items <= 0) return LECCR_OK;
   const int grid = std::min(L.n_items, num_sms());
   if (g_profile) {
@@ -531,6 +536,24 @@ static int topk_plan(const leccr_topk_problem* probs, int n_prob, int tiles_per_
       // (More chunks than load balance needs do not pay: later chunks inherit a threshold from the
       // earlier ones, but a stale one, and the total number of list inserts per row grows.)
       chunks = std::max<int64_t>(1, std::min<int64_t>(chunks, std::min<int64_t>(kMaxTopkChunks, col_tiles)));
+      if (n_prob == 1 && col_tiles >= 256) {
+        // Long rows, one problem: the items are equally long and the grid is persistent, so what matters is that
+        // the last wave is full (782 row blocks x 1 chunk = 5.3 waves of 148 would idle 12 % of the machine).
+        // Take the smallest chunk count >= the balance rule's whose waves are >= 97 % full, else the fullest.
+        const int64_t sms = num_sms();
+        int64_t best_c = chunks;
+        double best_eff = 0.0;
+        for (int64_t c = chunks; c <= std::min<int64_t>(kMaxTopkChunks, col_tiles); ++c) {
+          const int64_t items = row_blocks * c;
+          const double eff = static_cast<double>(items) / static_cast<double>((items + sms - 1) / sms * sms);
+          if (eff > best_eff + 1e-9) {
+            best_eff = eff;
+            best_c = c;
+          }
+          if (eff >= 0.97) break;
+        }
+        chunks = best_c;
+      }
       tpc = static_cast<int>((col_tiles + chunks - 1) / chunks);
     }
     plans[p] = plan_problem(probs[p].n_cols, 0, probs[p].n_rows, tpc);
@@ -816,7 +839,8 @@ int leccr_sim_topk_stream(const leccr_topk_problem* probs, const leccr_topk_stre
   Plan plans[2];
   for (int p = 0; p < n_prob; ++p) {
     const leccr_topk_stream& o = streams[p];
-    if ((o.phases & ~(LECCR_TOPK_INIT | LECCR_TOPK_GEMM | LECCR_TOPK_FINALIZE)) != 0 || o.phases == 0 ||
+    if ((o.phases & ~(LECCR_TOPK_INIT | LECCR_TOPK_GEMM | LECCR_TOPK_FINALIZE | LECCR_TOPK_LONG)) != 0 ||
+        (o.phases & ~LECCR_TOPK_LONG) == 0 || ((o.phases ^ streams[0].phases) & LECCR_TOPK_LONG) != 0 ||
         o.sub_total < 1 || o.sub_total > kMaxTopkChunks || o.sub_begin < 0 || o.sub_count < 1 ||
         o.sub_begin + o.sub_count > o.sub_total || o.col_begin < 0 || o.col_begin > 0x7fffffffLL)
       return LECCR_ERR_ARG;
@@ -828,8 +852,10 @@ int leccr_sim_topk_stream(const leccr_topk_problem* probs, const leccr_topk_stre
   int rc = leccr_check_device();
   if (rc != LECCR_OK) return rc;
   // A streamed problem's lists keep one shape from INIT to FINALIZE: the two-warpgroup dense shape, which
-  // requires every window's column chunks to be short (<= 32 tiles): choose sub_count accordingly.
-  const bool two = topk_two_wgs_allowed();
+  // requires every window's column chunks to be short (<= 32 tiles): choose sub_count accordingly -- or, when
+  // every call of the problem carries LECCR_TOPK_LONG (gallery windows of a large-gallery search), the filter
+  // shape of the one-shot path's long chunks.
+  const bool two = topk_two_wgs_allowed() && !(streams[0].phases & LECCR_TOPK_LONG);
   if (two) {
     for (int p = 0; p < n_prob; ++p)
       if ((streams[p].phases & LECCR_TOPK_GEMM) && plans[p].tiles_per_chunk > 32) return LECCR_ERR_ARG;
@@ -1094,8 +1120,22 @@ int leccr_double_sim_fuse(float* S, const float* Cn, int n_cap, int64_t numel, f
 int leccr_peer_barrier(uint32_t* const* flag_ptrs_dev, int world, int rank, uint32_t epoch, leccr_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (flag_ptrs_dev == nullptr || world < 1 || world > 32 || rank < 0 || rank >= world) return LECCR_ERR_ARG;
-  peer_barrier_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<unsigned* const*>(flag_ptrs_dev), world, rank, epoch);
+  // LECCR_PEER_TIMEOUT_S: seconds a rank waits for its peers before it gives up (default 600; 0 = for ever)
+  static long long timeout_s = -1;
+  if (timeout_s < 0) {
+    const char* e = getenv("LECCR_PEER_TIMEOUT_S");
+    timeout_s = (e != nullptr && atoll(e) >= 0) ? atoll(e) : 600;
+  }
+  peer_barrier_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<unsigned* const*>(flag_ptrs_dev), world, rank, epoch,
+                                            static_cast<unsigned long long>(timeout_s) * 1000000000ull);
   LAUNCH_CHECK("peer_barrier_kernel");
+  return LECCR_OK;
+}
+
+int leccr_memcpy_peer_async(void* dst, const void* src, size_t bytes, leccr_stream_t stream_) {
+  if (dst == nullptr || src == nullptr) return LECCR_ERR_ARG;
+  if (bytes == 0) return LECCR_OK;
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream_)));
   return LECCR_OK;
 }
 
@@ -1116,12 +1156,10 @@ int leccr_topk_merge_peers(const float* const* val_ptrs_dev, const int32_t* cons
   }
   const int warps = 2;
   const size_t smem = static_cast<size_t>(warps) * world * 32 * k_in * 8;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(topk_merge_peers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
-  }
   if (smem > 200 * 1024) return LECCR_ERR_ARG;
+  // function attributes are per device: set it on every call that needs it (cheap) rather than once per process
+  if (smem > 48 * 1024)
+    CUDA_TRY(cudaFuncSetAttribute(topk_merge_peers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const unsigned grid = static_cast<unsigned>((q_count + warps * 32 - 1) / (warps * 32));
   topk_merge_peers_kernel<<<grid, warps * 32, smem, stream>>>(val_ptrs_dev, reinterpret_cast<const int* const*>(idx_ptrs_dev),
                                                             world, k_in, q_begin, q_count, offs, k_out, out_val, out_idx);

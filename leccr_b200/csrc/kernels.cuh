@@ -1092,9 +1092,17 @@ __global__ void fuse_scores_kernel(float* __restrict__ S, const float* __restric
 // Barrier over peer-visible flag words.  flags[p] -> rank p's block of `world` uint32 (slot r is written by
 // rank r only).  Thread p publishes `epoch` into peer p's slot [rank] (release, system scope: everything
 // this stream did before -- including peer stores of earlier kernels -- is visible to whoever acquires it)
-// and waits until peer p's epoch has arrived in the own block.  Epochs only grow.  Bounded spin: a lost
-// peer traps instead of hanging the box.
-__global__ void peer_barrier_kernel(unsigned* const* __restrict__ flags, int world, int rank, unsigned epoch) {
+// and waits until peer p's epoch has arrived in the own block.  Epochs only grow.  The wait is bounded by
+// WALL TIME (timeout_ns, %globaltimer; 0 = wait for ever, as NCCL would): ranks of a training job may be
+// minutes apart (a rank-local checkpoint write, image_Retrieval_caption.py:478-499, has no dist.barrier after
+// it), so the default is minutes, not seconds; only a peer that is really gone traps.
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__global__ void peer_barrier_kernel(unsigned* const* __restrict__ flags, int world, int rank, unsigned epoch,
+                                    unsigned long long timeout_ns) {
   const int p = threadIdx.x;
   if (p >= world) return;
   __threadfence_system();
@@ -1102,12 +1110,16 @@ __global__ void peer_barrier_kernel(unsigned* const* __restrict__ flags, int wor
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
   const unsigned* mine = flags[rank] + p;
   unsigned seen = 0;
-  long long spins = 0;
+  unsigned spins = 0;
+  const unsigned long long t0 = global_ns();
   for (;;) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
     if (static_cast<int>(seen - epoch) >= 0) break;
-    if (++spins > (1LL << 26)) __trap();  // seconds
-    __nanosleep(64);
+    if ((++spins & 1023u) == 0 && timeout_ns != 0 && global_ns() - t0 > timeout_ns) {
+      printf("leccr: peer barrier timed out (rank %d waiting for rank %d, epoch %u, seen %u)\n", rank, p, epoch, seen);
+      __trap();
+    }
+    __nanosleep(spins < 4096u ? 64 : 1000);
   }
 }
 

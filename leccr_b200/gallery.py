@@ -1,0 +1,296 @@
+"""Large-gallery search (BASELINE.json configs[4]): per-query top-k of Q queries
+against a G-row gallery of 16-bit embeddings, on the ranks of one NVLink node.
+
+The reference has no such entry: it materialises `image_embeds @ text_embeds.t()` and argsorts every row on
+rank 0's CPU (image_Retrieval_caption.py:151,268), which cannot be done for 1M x 100k (400 GB of scores).
+This is the additive, sharded form of `fused_eval`'s top-k half.
+
+Layout (north_star): the QUERY set is sharded over S = world / P groups of ranks, the GALLERY is row-partitioned
+into P parts inside each group.  Rank r = (shard r // P, part r % P) ranks its query shard against its gallery
+part with the fused tensor-core pass (the Q x G scores never reach HBM), finalize writes the local [Qs, k]
+lists straight into a peer-mapped buffer, ONE cross-rank barrier, and `leccr_topk_merge_peers` pulls the P
+partial lists of this rank's slice of the shard over NVLink while merging them.  P = 1 is pure query sharding
+(no exchange); world = 1 is the single-GPU search.
+
+Two entries:
+  search()                       inputs resident in HBM (load_device / the buffers .gal16, .qry16)
+  search_host(gallery, queries)  pinned HOST arrays: the gallery part crosses PCIe in windows on a copy stream
+                                 while the tensor cores rank the windows that have arrived
+                                 (leccr_sim_topk_stream with LECCR_TOPK_LONG), results come back to the host.
+With `exchange_gallery=True` (default when P < world) every gallery row crosses PCIe ONCE per node: the ranks
+that hold the same gallery part each upload 1/S of every window and push it to the others through peer
+pointers (copy engines over NVLink), so the host link carries G / world rows per rank instead of G / P.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _native as N
+from . import peer
+from .sharding import shard_range
+
+
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def _pick_windows(row_blocks: int, part_rows: int, sms: int = 148):
+    """(windows, slots per window) of the host path: windows * slots <= 8 list slots per query row; prefer the
+    split whose work items fill whole waves of the persistent grid, then the one with more (smaller) windows
+    (less un-overlapped H2D in front of the first pass)."""
+    best = None
+    for w in (8, 4, 2, 1):
+        if part_rows // w < 32768 and w > 1:
+            continue  # windows this small are launch- and threshold-warm-up-bound
+        for s in range(1, 8 // w + 1):
+            items = row_blocks * s
+            eff = items / (-(-items // sms) * sms)
+            score = (int(min(eff, 0.95) / 0.05 + 1e-9), w, -s)  # 5 % buckets: 0.96 and 0.99 are the same
+            if best is None or score > best[0]:
+                best = (score, w, s)
+    return best[1], best[2]
+
+
+class GallerySearchPlan:
+    """Static buffers + the launch sequence of one search shape.
+
+        plan = GallerySearchPlan(n_gallery, n_query, dim)            # collective when world > 1
+        plan.load_device(gallery_part_16bit, query_shard_16bit)      # rows plan.gallery_rows / plan.query_rows
+        val, idx, (q0, q1) = plan.search()                           # this rank's merged query slice, global columns
+        val_h, idx_h, (q0, q1) = plan.search_host(gallery_host, queries_host)   # pinned [G, D] / [Q, D] arrays
+    """
+
+    def __init__(self, n_gallery, n_query, dim, k=10, dtype=torch.bfloat16, gallery_parts=None, windows=None,
+                 exchange_gallery=None):
+        if not torch.cuda.is_available():
+            raise N.LeccrError("leccr_b200 has no CPU path: a CUDA device (B200) is required")
+        if dtype not in (torch.bfloat16, torch.float16):
+            raise N.LeccrError("the gallery is stored in a 16-bit format (bf16 / fp16)")
+        if dim % 8 != 0:
+            raise N.LeccrError("embedding dimension must be a multiple of 8 (TMA 16-byte rows)")
+        self.lib = lib = N.load()
+        N.check(lib.leccr_check_device(), "leccr_check_device")
+        self.dev = dev = torch.device("cuda", torch.cuda.current_device())
+        self.rank, self.world = _world()
+        P = gallery_parts if gallery_parts is not None else (2 if self.world % 2 == 0 else 1)
+        if P < 1 or self.world % P != 0 or P > 8:
+            raise N.LeccrError("gallery_parts must divide the number of ranks")
+        self.P, self.S = P, self.world // P
+        self.shard, self.part = self.rank // P, self.rank % P
+        self.G, self.Q, self.D, self.k = n_gallery, n_query, dim, k
+        self.fmt = N.FMT_BF16 if dtype == torch.bfloat16 else N.FMT_F16
+        self.dtype = dtype
+        self.query_rows = shard_range(n_query, self.shard, self.S)
+        self.gallery_rows = shard_range(n_gallery, self.part, P)
+        qb, qe = self.query_rows
+        gb, ge = self.gallery_rows
+        self.Qs, self.Gp = qe - qb, ge - gb
+        if self.Qs <= 0 or self.Gp <= 0:
+            raise N.LeccrError("fewer queries / gallery rows than ranks")
+        self.qry16 = torch.empty((self.Qs, dim), dtype=dtype, device=dev)
+        # gallery part: private, or -- host path with exchange -- one peer-mapped copy per rank that the S ranks
+        # holding the same part fill together (each uploads 1/S of every window and pushes it to its mates)
+        if exchange_gallery is None:
+            exchange_gallery = self.S > 1
+        self.xchg = self.endb = None
+        self.gal16 = None
+        if exchange_gallery and self.S > 1 and peer.available(dev):
+            gp_max = -(-n_gallery // P)
+            self.xchg = peer.get_buffer(("gallery_part", n_gallery, P, dim), gp_max * dim * 2, dev, slots=1)
+            if self.xchg is not None:
+                self.xchg_base = self.xchg.slot_offset(0)
+                self.gal16 = self.xchg.local(self.xchg_base, (self.Gp, dim), dtype)
+                self.mates = [self.part + P * s for s in range(self.S)]
+                if P == 1:  # no merge barrier at the end of a search: a mate must not refill a window still being ranked
+                    self.endb = peer.get_buffer(("gallery_end",), 256, dev, slots=1)
+        if self.gal16 is None:
+            self.gal16 = torch.empty((self.Gp, dim), dtype=dtype, device=dev)
+        f32, i32 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.int32, device=dev)
+        # local lists: a private pair when there is nothing to merge, else the two slots of a peer-mapped buffer
+        self.pb = None
+        if P > 1:
+            if not peer.available(dev):
+                raise N.LeccrError("a partitioned gallery needs the NCCL process group of one NVLink node")
+            qs_max = -(-n_query // self.S)
+            self.pb = peer.get_buffer(("gallery_search", n_query, self.S, k), qs_max * k * 8, dev)
+            if self.pb is None:
+                raise N.LeccrError("peer-mapped memory is not available on this system")
+            self.local = []
+            for slot in range(2):
+                off = self.pb.slot_offset(slot)
+                self.local.append((self.pb.local(off, (self.Qs, k), torch.float32),
+                                   self.pb.local(off + self.Qs * k * 4, (self.Qs, k), torch.int32), off))
+            self.group = [self.shard * P + i for i in range(P)]
+            self.part_offsets = (ctypes.c_int64 * P)(*[shard_range(n_gallery, i, P)[0] for i in range(P)])
+            mb, me = shard_range(self.Qs, self.part, P)
+            self.merge_rows = (mb, me)
+            self.out_val = torch.empty((me - mb, k), **f32)
+            self.out_idx = torch.empty((me - mb, k), **i32)
+            self._tabs = {}
+        else:
+            self.local = [(torch.empty((self.Qs, k), **f32), torch.empty((self.Qs, k), **i32), 0)]
+            self.merge_rows = (0, self.Qs)
+            self.out_val, self.out_idx = self.local[0][0], self.local[0][1]
+        self.calls = 0
+        # ---- one-shot problem (device-resident inputs)
+        self.probs = []
+        for (lv, li, _off) in self.local:
+            pr = (N.TopkProblem * 1)()
+            self._fill(pr[0], self.gal16.data_ptr(), self.Gp, lv, li)
+            self.probs.append(pr)
+        self.ws = torch.empty(lib.leccr_sim_topk_workspace(self.probs[0], 1, 0), dtype=torch.uint8, device=dev)
+        # ---- windowed problems (host inputs)
+        row_blocks = (self.Qs + 127) // 128
+        if windows is None:
+            W, subs = _pick_windows(row_blocks, self.Gp)
+        else:
+            W, subs = int(windows), max(1, 8 // int(windows))
+            if W < 1 or W > 8:
+                raise N.LeccrError("1 to 8 gallery windows")
+        self.subs = subs
+        step = -(-self.Gp // W)
+        step = (step + 255) // 256 * 256
+        self.bounds = [(b, min(self.Gp, b + step)) for b in range(0, self.Gp, step)]
+        W = len(self.bounds)
+        self.ws_stream = torch.empty(lib.leccr_sim_topk_stream_workspace(self.Qs, W * subs), dtype=torch.uint8, device=dev)
+        self.stream_calls = []
+        esz = 2
+        for (lv, li, _off) in self.local:
+            calls = []
+            for w, (b, e) in enumerate(self.bounds):
+                pr = (N.TopkProblem * 1)()
+                so = (N.TopkStream * 1)()
+                self._fill(pr[0], self.gal16.data_ptr() + b * dim * esz, e - b, lv, li)
+                o = so[0]
+                o.phases = N.TOPK_LONG | N.TOPK_GEMM | (N.TOPK_INIT if w == 0 else 0) | (N.TOPK_FINALIZE if w == W - 1 else 0)
+                o.sub_begin, o.sub_count, o.sub_total = w * subs, subs, W * subs
+                o.col_begin = b
+                o.n_cols_total = self.Gp
+                o.workspace, o.workspace_bytes = self.ws_stream.data_ptr(), self.ws_stream.numel()
+                calls.append((pr, so))
+            self.stream_calls.append(calls)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ev_q = torch.cuda.Event()
+        self.ev_win = [torch.cuda.Event() for _ in self.bounds]
+        mb, me = self.merge_rows
+        self.host_val = torch.empty((me - mb, k), dtype=torch.float32).pin_memory()
+        self.host_idx = torch.empty((me - mb, k), dtype=torch.int32).pin_memory()
+        self.launches_per_search = 2 + (2 if P > 1 else 0)  # tensor-core pass, finalize (, barrier, merge)
+
+    # -------------------------------------------------------------------------------------------------
+    def _fill(self, p, cols_ptr, n_cols, lv, li):
+        p.rows16, p.cols16 = self.qry16.data_ptr(), cols_ptr
+        p.ld_rows16 = p.ld_cols16 = self.D
+        p.n_rows, p.n_cols = self.Qs, n_cols
+        p.topk_val, p.topk_idx = lv.data_ptr(), li.data_ptr()
+
+    def load_device(self, gallery_part, query_shard):
+        """Device-resident inputs: rows `gallery_rows` of the gallery and `query_rows` of the queries."""
+        self.gal16.copy_(gallery_part)
+        self.qry16.copy_(query_shard)
+
+    # -------------------------------------------------------------------------------------------------
+    def _merge(self, slot, host_path=False):
+        """Exchange step of a partitioned gallery: barrier, then pull + merge this rank's slice of the shard."""
+        if self.P == 1:
+            if host_path and self.endb is not None:
+                self.endb.barrier()
+            return
+        pb = self.pb
+        pb.barrier()
+        off = self.local[slot][2]
+        tabs = self._tabs.get(slot)
+        if tabs is None:
+            tabs = (torch.tensor([pb.ptrs[r] + off for r in self.group], dtype=torch.int64, device=self.dev),
+                    torch.tensor([pb.ptrs[r] + off + self.Qs * self.k * 4 for r in self.group], dtype=torch.int64,
+                                 device=self.dev))
+            self._tabs[slot] = tabs
+        mb, me = self.merge_rows
+        N.check(self.lib.leccr_topk_merge_peers(N.ptr(tabs[0]), N.ptr(tabs[1]), self.P, self.k, mb, me - mb,
+                                                self.part_offsets, self.k, N.ptr(self.out_val), N.ptr(self.out_idx),
+                                                N.stream_ptr()), "leccr_topk_merge_peers")
+
+    def _result_rows(self):
+        qb = self.query_rows[0]
+        return qb + self.merge_rows[0], qb + self.merge_rows[1]
+
+    @torch.no_grad()
+    def search(self):
+        """Inputs resident in HBM.  Returns (val [n, k], idx int32 [n, k] global gallery rows, (q0, q1)): the
+        merged lists of queries [q0, q1) -- this rank's slice; the slices of all ranks tile the query set."""
+        slot = self.calls % len(self.local)
+        self.calls += 1
+        N.check(self.lib.leccr_sim_topk(self.probs[slot], 1, self.D, self.fmt, self.k, 0, self.ws.data_ptr(),
+                                        self.ws.numel(), N.stream_ptr()), "leccr_sim_topk")
+        self._merge(slot)
+        return self.out_val, self.out_idx, self._result_rows()
+
+    def _issue_host(self, gallery_host, queries_host):
+        cur = torch.cuda.current_stream()
+        cs = self.copy_stream
+        slot = self.calls % len(self.local)
+        self.calls += 1
+        qb, qe = self.query_rows
+        gb, _ge = self.gallery_rows
+        cs.wait_stream(cur)  # the previous search has consumed the staging buffers
+        with torch.cuda.stream(cs):
+            self.qry16.copy_(queries_host[qb:qe], non_blocking=True)
+            self.ev_q.record(cs)
+            for w, (b, e) in enumerate(self.bounds):
+                if self.xchg is None:
+                    self.gal16[b:e].copy_(gallery_host[gb + b: gb + e], non_blocking=True)
+                else:
+                    # my 1/S of the window over PCIe, then pushed to the mates' copies by the copy engines (NVLink)
+                    sb, se = shard_range(e - b, self.shard, self.S)
+                    sb, se = b + sb, b + se
+                    self.gal16[sb:se].copy_(gallery_host[gb + sb: gb + se], non_blocking=True)
+                    nbytes = (se - sb) * self.D * 2
+                    src = self.gal16.data_ptr() + sb * self.D * 2
+                    for r in self.mates:
+                        if r == self.rank:
+                            continue
+                        dst = self.xchg.ptrs[r] + self.xchg_base + sb * self.D * 2
+                        _memcpy_async(dst, src, nbytes, cs.cuda_stream)
+                    self.xchg.barrier()  # on the copy stream: everybody's pushes of this window have landed
+                self.ev_win[w].record(cs)
+        st = cur.cuda_stream
+        cur.wait_event(self.ev_q)
+        for w, (pr, so) in enumerate(self.stream_calls[slot]):
+            cur.wait_event(self.ev_win[w])
+            N.check(self.lib.leccr_sim_topk_stream(pr, so, 1, self.D, self.fmt, self.k, st), "leccr_sim_topk_stream")
+        self._merge(slot, host_path=True)
+        self.host_val.copy_(self.out_val, non_blocking=True)
+        self.host_idx.copy_(self.out_idx, non_blocking=True)
+
+    @torch.no_grad()
+    def search_host(self, gallery_host, queries_host):
+        """HOST inputs: the whole [G, D] gallery and [Q, D] query arrays in (ideally pinned) host memory, 16-bit.
+        Each rank uploads only what it needs; returns pinned host tensors (val, idx, (q0, q1)) of its slice."""
+        g = torch.as_tensor(gallery_host)
+        q = torch.as_tensor(queries_host)
+        if g.shape != (self.G, self.D) or q.shape != (self.Q, self.D) or g.dtype != self.dtype or q.dtype != self.dtype:
+            raise N.LeccrError("search_host needs the [G, D] gallery and [Q, D] queries in the planned 16-bit dtype")
+        if g.is_cuda or q.is_cuda:
+            raise N.LeccrError("search_host takes host arrays; use load_device + search for device-resident inputs")
+        self._issue_host(g, q)
+        torch.cuda.current_stream().synchronize()
+        return self.host_val, self.host_idx, self._result_rows()
+
+    @property
+    def h2d_bytes(self):
+        """Bytes this rank moves host -> device per search_host call."""
+        g_rows = self.Gp if self.xchg is None else sum(
+            shard_range(e - b, self.shard, self.S)[1] - shard_range(e - b, self.shard, self.S)[0] for b, e in self.bounds)
+        return (g_rows + self.Qs) * self.D * 2
+
+    @property
+    def d2h_bytes(self):
+        return self.host_val.numel() * 8
+
+
+def _memcpy_async(dst: int, src: int, nbytes: int, stream: int):
+    """Copy between device pointers, one of them peer-mapped: a copy-engine transfer over NVLink, no SMs."""
+    N.check(N.load().leccr_memcpy_peer_async(dst, src, nbytes, stream), "leccr_memcpy_peer_async")

@@ -37,17 +37,18 @@ def available(device) -> bool:
 
 
 class PeerBuffer:
-    """A peer-mapped allocation of `nbytes` payload bytes x 2 slots + a block of barrier flags, identical
-    on every rank of the default group.  Collective: every rank must construct it at the same time."""
+    """A peer-mapped allocation of `nbytes` payload bytes x `slots` slots (2: used alternately) + a block of
+    barrier flags, identical on every rank of the default group.  Collective: every rank must construct it
+    at the same time."""
 
     FLAG_BYTES = 256
 
-    def __init__(self, nbytes: int, device):
+    def __init__(self, nbytes: int, device, slots: int = 2):
         import torch.distributed._symmetric_memory as symm_mem
 
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.slot_bytes = (nbytes + 255) // 256 * 256
-        total = self.FLAG_BYTES + 2 * self.slot_bytes
+        total = self.FLAG_BYTES + slots * self.slot_bytes
         group = dist.group.WORLD
         import warnings
 
@@ -101,13 +102,13 @@ class PeerBuffer:
                                             N.stream_ptr()), "leccr_peer_barrier")
 
 
-def get_buffer(key, nbytes: int, device):
+def get_buffer(key, nbytes: int, device, slots: int = 2):
     """Cached PeerBuffer per use (key); None when peer memory cannot be set up (NCCL is used instead)."""
     global _warned
     if key in _cache:
         return _cache[key]
     try:
-        pb = PeerBuffer(nbytes, device)
+        pb = PeerBuffer(nbytes, device, slots)
     except Exception as e:  # allocation / rendezvous unsupported on this system
         if not _warned:
             import warnings

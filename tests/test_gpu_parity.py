@@ -667,3 +667,30 @@ def test_exact_rank_fallback_with_a_long_ground_truth_list():
     got = res.rank.cpu().numpy()
     small = want < 10
     assert np.array_equal(got[small], want[small]) and (got[~small] >= 10).all()
+
+
+# ----------------------------------------------------------------------------- large-gallery search plan (cfg5 shape)
+def test_gallery_search_plan_device_and_host_paths_against_oracle():
+    """GallerySearchPlan on one GPU: the one-shot pass (inputs in HBM) and the windowed host path (gallery in
+    two windows, LECCR_TOPK_LONG streams) give bit-identical lists; top-10 and Recall@1/5/10 equal the oracle's
+    (fp32 matmul + per-row np.argsort, image_Retrieval_caption.py:151,288-295) on the same bf16 inputs."""
+    G, Q = 70_000, 384
+    gal, qry, gt = synth.cfg5_gallery(G, Q, seed=11)
+    plan = leccr_b200.GallerySearchPlan(G, Q, 256, k=10)
+    assert len(plan.bounds) == 2 and plan.P == 1 and plan.query_rows == (0, Q)
+    plan.load_device(gal.cuda(), qry.cuda())
+    val, idx, rows = plan.search()
+    val, idx = val.cpu().clone(), idx.cpu().clone()
+    assert rows == (0, Q)
+    hv, hi, hrows = plan.search_host(gal.pin_memory(), qry.pin_memory())
+    assert hrows == rows and torch.equal(hi, idx) and torch.equal(hv, val)
+    ev, want_val, want_idx = oracle.gallery_eval(gal, qry, gt.tolist(), k=10)
+    s = (qry.float() @ gal.float().t()).numpy()
+    got_true = np.take_along_axis(s, idx.numpy().astype(np.int64), 1)
+    assert np.abs(np.sort(got_true, 1)[:, ::-1] - want_val).max() < 1e-4   # same set up to ties inside the tolerance
+    assert (idx.numpy() == want_idx).all(axis=1).mean() > 0.99
+    for c in (1, 5, 10):
+        mine = 100.0 * float((idx[:, :c].long() == gt[:, None]).any(dim=1).float().mean())
+        assert mine == ev[f"img_r{c}"], (c, mine, ev)
+    with pytest.raises(N.LeccrError):
+        plan.search_host(gal.float(), qry.float())   # the plan's dtype is binding: no silent conversion

@@ -3,6 +3,7 @@ concatenated batch, and the AllGather drop-in.  Development / gpu-box tool."""
 import os, sys, types
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
+os.environ.setdefault("LECCR_PEER_TIMEOUT_S", "60")
 import leccr_b200
 from leccr_b200 import synth
 from oracle import oracle
@@ -126,6 +127,27 @@ nccl_ok = bool(torch.equal(oi.long(), full.idx.long())) and bool(torch.equal(ov,
 _N.check(_lib.leccr_comm_destroy(comm), "leccr_comm_destroy")
 ok &= nccl_ok
 print(f"rank {rank}: C-ABI NCCL all-gather + merge == single pass {nccl_ok}", flush=True)
+# ---- GallerySearchPlan: query shards x gallery parts with the peer merge (P = 2), and pure query sharding with the
+# gallery pushed between ranks on the host path (P = 1); both against a single pass over the whole gallery
+G5, Q5 = 160_000, 1024
+gal5, qry5, _gt5 = synth.cfg5_gallery(G5, Q5, device="cuda", seed=21)
+full5, = _ops.sim_topk([(_ops.prep(qry5, want_stats=False), _ops.prep(gal5, want_stats=False), None)], k=10)
+gal5_h, qry5_h = gal5.cpu().pin_memory(), qry5.cpu().pin_memory()
+plan_ok = True
+for parts in ((2, 1) if world % 2 == 0 else (1,)):
+    plan = leccr_b200.GallerySearchPlan(G5, Q5, 256, k=10, gallery_parts=parts)
+    gb5, ge5 = plan.gallery_rows
+    qb5, qe5 = plan.query_rows
+    plan.load_device(gal5[gb5:ge5], qry5[qb5:qe5])
+    for rep in range(3):  # both slots of the double-buffered lists
+        v5, i5, (r0, r1) = plan.search()
+        plan_ok &= bool(torch.equal(i5, full5.idx[r0:r1])) and bool(torch.equal(v5, full5.val[r0:r1]))
+    for rep in range(3):
+        hv5, hi5, (h0, h1) = plan.search_host(gal5_h, qry5_h)
+        plan_ok &= (h0, h1) == (r0, r1) and bool(torch.equal(hi5.cuda(), full5.idx[r0:r1])) and bool(torch.equal(hv5.cuda(), full5.val[r0:r1]))
+    print(f"rank {rank}: GallerySearchPlan parts={parts} shards={plan.S} windows={len(plan.bounds)} exchange={plan.xchg is not None} "
+          f"h2d {plan.h2d_bytes} B: {'PASS' if plan_ok else 'FAIL'}", flush=True)
+ok &= plan_ok
 # timing of the training step (fwd + bwd) on this rank, max over ranks
 def step():
     me.temp.grad = None
