@@ -145,7 +145,7 @@ def run_reference(args, rank):
         return
     threads = os.cpu_count() or 1
     gal, qry, gt = cpu_data()
-    n_q = 24
+    n_q = 64
     for _ in range(min(args.warmup, 1)):
         cpu_search_sample(gal, qry, gt, 4, threads)
     total_t, total_q = 0.0, 0
@@ -324,7 +324,7 @@ def run_ours(args, rank, world, local_rank):
         threads = os.cpu_count() or 1
         g32, q32, gtl = cpu_data()
         cpu_search_sample(g32, q32, gtl, 4, threads)
-        n_q = 96
+        n_q = 512
         dt, q = cpu_search_sample(g32, q32, gtl, n_q, threads)
         line["cpu_baseline"] = {
             "value": q / dt, "unit": "queries/s", "cores": threads, "kind": "port",
