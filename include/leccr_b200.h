@@ -224,6 +224,20 @@ int leccr_double_sim_fuse(float* S, const float* Cn, int n_cap, int64_t numel, f
                           float w1, float w2, int mode, leccr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * leccr_normalize_fwd / leccr_normalize_bwd: row-wise L2 normalisation as a training op.
+ * Replaces: the F.normalize(..., dim=-1) of XVLMBase.get_features, models/xvlm.py:245-256 and
+ * models/xvlm_video.py:264-277 (the projection in front of it stays torch's Linear).
+ *   x   : [n][ld_x] fp32 projected features;  y: [n][ld_y] fp32 = x / max(||x||, 1e-12)
+ *   inv : [n] out, 1 / max(||x||, 1e-12), NEGATED for rows whose norm was clamped (saved for the backward)
+ *   y16 : optional [n][ld_y16] 16-bit copy of y in `fmt` (the similarity stage's operand, same pass)
+ *   backward: dx = inv * (g - y (y . g)); clamped rows: dx = g * inv (torch's clamp_min semantics)
+ * ------------------------------------------------------------------------------------------ */
+int leccr_normalize_fwd(const float* x, int64_t n, int D, int64_t ld_x, float* y, int64_t ld_y, float* inv,
+                        void* y16, int64_t ld_y16, int fmt, leccr_stream_t stream);
+int leccr_normalize_bwd(const float* y, int64_t ld_y, const float* inv, const float* g, int64_t ld_g, int64_t n, int D,
+                        float* dx, int64_t ld_dx, leccr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Cross-rank exchange over peer memory (one node, NVLink / NVSwitch).  The pointer
  * tables are device arrays of `world` device pointers into peer-mapped (symmetric) buffers, own rank
  * included; the Python shim obtains them from torch.distributed._symmetric_memory.
@@ -263,6 +277,13 @@ int leccr_topk_merge_peers(const float* const* val_ptrs_dev, const int32_t* cons
  *                labels part; flag_ptrs_dev / epoch as in leccr_peer_barrier; local_slot = this rank's slot,
  *                local_slot_bytes the bytes to copy into both16 (rows, + labels when idx != NULL).
  *                The caller alternates two slots.  5 launches: push, barrier, copy, tensor-core pass, finalize.
+ *   stat_ptrs_dev != NULL (world > 1): STRIP forward.  Every row's log-sum-exp, positives and E_softmax[z]
+ *                depend on that row alone (:279-290 are row-wise), so the rank runs the tensor-core pass for ITS
+ *                B rows of both orientations only (1 / world of the work) and the per-row statistics are
+ *                exchanged: stat_ptrs_dev[p] -> rank p's peer-mapped statistics slot, float lse2[2][n] |
+ *                float rcnt[2][n] | double partial[world][4]; local_stat_slot = this rank's.  A second barrier
+ *                (epoch + 1: the caller advances its epoch by TWO per call) orders the exchange.  7 launches:
+ *                push, barrier, copy, tensor-core pass, finalize + push, barrier, reduce.
  *   both16 : out, private [n][2D] 16-bit gathered operands [image | text] (saved for the backward)
  *   idx_all: out, [n] int64 (when idx != NULL);  out/lse2/rcnt as in leccr_infonce_fwd
  *   backward: dA, dB [row_count][D] fp32, dtemp scalar = grad_out * out[1] (may be NULL);
@@ -273,7 +294,8 @@ size_t leccr_itc_fwd_workspace(int64_t n, int tiles_per_chunk);
 int leccr_itc_forward(const float* image_feat, int64_t ld_img, const float* text_feat, int64_t ld_txt,
                       const int64_t* idx, int64_t B, int D, int fmt, int rank, int world,
                       void* const* rows_ptrs_dev, void* const* idx_ptrs_dev, uint32_t* const* flag_ptrs_dev,
-                      uint32_t epoch, const void* local_slot, size_t local_slot_bytes, void* both16,
+                      uint32_t epoch, const void* local_slot, size_t local_slot_bytes, void* const* stat_ptrs_dev,
+                      const void* local_stat_slot, void* both16,
                       int64_t* idx_all, const float* temp, float* out, float* lse2, float* rcnt,
                       void* workspace, size_t workspace_bytes, leccr_stream_t stream);
 size_t leccr_itc_bwd_workspace(int64_t n, int64_t row_count, int D);

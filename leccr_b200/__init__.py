@@ -16,6 +16,7 @@ from .allgather import AllGather, allgather  # noqa: E402,F401
 from .caption_loss import caption_contrastive_loss, get_caption_contrastive_loss  # noqa: E402,F401
 from .contrastive import caption_vision_loss, contrastive_loss, get_contrastive_loss  # noqa: E402,F401
 from .dstl_loss import dstl_loss, dstl_loss_gathered  # noqa: E402,F401
+from .features import get_features, get_features_video, normalize_rows  # noqa: E402,F401
 from .gallery import GallerySearchPlan  # noqa: E402,F401
-from .evaluation import (FusedEvalPlan, StreamedEvalPlan, double_sim_matrix, evaluation_coarse, evaluation_coarse_video, fused_eval,  # noqa: E402,F401
+from .evaluation import (FeatureGallery, FusedEvalPlan, StreamedEvalPlan, double_sim_matrix, evaluation_coarse, evaluation_coarse_video, fused_eval,  # noqa: E402,F401
                          fused_eval_sharded, itm_eval, prepare_gt, score_matrix, topk_gallery_sharded)

@@ -69,7 +69,7 @@ _SIGNATURES = {
                                       c_int, vp]),
     "leccr_itc_fwd_workspace": (sz, [i64, c_int]),
     "leccr_itc_forward": (c_int, [vp, i64, vp, i64, vp, i64, c_int, c_int, c_int, c_int, vp, vp, vp, ctypes.c_uint32,
-                                  vp, sz, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+                                  vp, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "leccr_itc_bwd_workspace": (sz, [i64, i64, c_int]),
     "leccr_itc_backward": (c_int, [vp, vp, i64, c_int, c_int, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, c_int, vp, sz,
                                    vp]),
@@ -89,6 +89,8 @@ _SIGNATURES = {
     "leccr_dstl_bwd_workspace": (sz, [i64, i64, c_int]),
     "leccr_dstl_bwd": (c_int, [vp, vp, vp, vp, i64, vp, i64, i64, c_int, c_int, i64, i64, vp, vp, vp, vp, sz, vp]),
     "leccr_peer_barrier": (c_int, [vp, c_int, c_int, ctypes.c_uint32, vp]),
+    "leccr_normalize_fwd": (c_int, [vp, i64, c_int, i64, vp, i64, vp, vp, i64, c_int, vp]),
+    "leccr_normalize_bwd": (c_int, [vp, i64, vp, vp, i64, i64, c_int, vp, i64, vp]),
     "leccr_memcpy_peer_async": (c_int, [vp, vp, sz, vp]),
     "leccr_topk_merge_peers": (c_int, [vp, vp, c_int, c_int, i64, i64, ctypes.POINTER(i64), c_int, vp, vp, vp]),
     "leccr_stats16": (c_int, [vp, c_int, i64, c_int, i64, vp, vp, vp, vp]),
@@ -151,6 +153,11 @@ def ptr(t):
 
 
 def stream_ptr():
+    """Raw cudaStream_t of torch's current stream on the current device (the per-call host cost matters: the
+    training losses are host-issue-bound)."""
     import torch
 
-    return torch.cuda.current_stream().cuda_stream
+    try:
+        return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+    except AttributeError:  # older / newer torch without the private accessor
+        return torch.cuda.current_stream().cuda_stream

@@ -11,6 +11,8 @@ instead of three collectives), elsewhere one all-gather of the [image | text] ha
 forward emits per-row log-sum-exp statistics and d loss / d temp, and the backward recomputes the logits
 of the local row strips only.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -20,6 +22,9 @@ from . import peer
 from .allgather import gather_into
 
 PRECISION = "f16"  # tensor-core operand format for fp32 inputs: "f16" (default) or "bf16"
+# world > 1 with peer memory: every rank runs the tensor-core pass for ITS rows only and the per-row statistics
+# are exchanged (leccr_itc_forward, strip forward); False = every rank runs the whole N x N forward redundantly
+STRIP_FORWARD = os.environ.get("LECCR_ITC_STRIPS", "1") != "0"
 
 
 def _world():
@@ -56,18 +61,17 @@ class _SymmetricInfoNCE(torch.autograd.Function):
         B, D = image_feat.shape
         n = B * world
         dev = image_feat.device
-        img = image_feat.detach()
-        txt = text_feat.detach()
+        img, txt = image_feat, text_feat  # autograd.Function.forward runs without grad mode: no detach needed
         if img.dtype != torch.float32 or img.stride(1) != 1:
             img = img.float().contiguous()
         if txt.dtype != torch.float32 or txt.stride(1) != 1:
             txt = txt.float().contiguous()
         ix = None
         if idx is not None:
-            ix = idx.detach().view(-1)
+            ix = idx if idx.dim() == 1 else idx.view(-1)
             if ix.dtype != torch.int64 or not ix.is_contiguous():
                 ix = ix.long().contiguous()
-        temp_dev = temp.detach().reshape(())
+        temp_dev = temp if temp.dim() == 0 else temp.reshape(())
         if temp_dev.dtype != torch.float32:
             temp_dev = temp_dev.float()
         # everything the backward needs lives in ONE allocation: [both16 | idx_all | out(4) | lse2 | rcnt]
@@ -93,20 +97,24 @@ class _SymmetricInfoNCE(torch.autograd.Function):
                                           N.stream_ptr()), "leccr_infonce_fwd")
         else:
             ws = _workspace("fwd", lib.leccr_itc_fwd_workspace(n, 0), dev)
-            rows_tab = idx_tab = flag_tab = None
-            epoch, l_slot = 0, None
+            rows_tab = idx_tab = flag_tab = stat_tab = None
+            epoch, l_slot, l_stat = 0, None, None
             if slot is not None:
-                rows_tab, idx_tab, flag_tab, epoch, l_slot = slot
+                rows_tab, idx_tab, flag_tab, epoch, l_slot, stat_tab, l_stat = slot
+                if not STRIP_FORWARD:
+                    stat_tab = l_stat = None
             l_bytes = (o_idx + n * 8) if ix is not None else n * 2 * D * 2
             N.check(lib.leccr_itc_forward(N.ptr(img), img.stride(0), N.ptr(txt), txt.stride(0), N.ptr(ix), B, D, fmt,
                                           rank, world, N.ptr(rows_tab), N.ptr(idx_tab), N.ptr(flag_tab), epoch,
-                                          l_slot, l_bytes, base, base + o_idx, N.ptr(temp_dev), base + o_out,
+                                          l_slot, l_bytes, N.ptr(stat_tab), l_stat, base, base + o_idx,
+                                          N.ptr(temp_dev), base + o_out,
                                           base + o_lse, base + o_rc, N.ptr(ws), ws.numel(), N.stream_ptr()),
                     "leccr_itc_forward")
         ctx.save_for_backward(saved, temp_dev)
         ctx.meta = (rank, B, D, n, fmt, idx is not None, (o_idx, o_out, o_lse, o_rc), bool(one_dir))
-        # out = [loss, dloss/dtemp, loss_i2t, loss_t2i, ...]: the one-directional loss is the i2t half
-        return saved[o_out:o_out + 16].view(torch.float32)[2 if one_dir else 0].clone()
+        # out = [loss, dloss/dtemp, loss_i2t, loss_t2i, ...]: the one-directional loss is the i2t half.  The result
+        # is a 0-d view of the saved block (no copy kernel); modifying it in place trips autograd's version check.
+        return saved[o_out + (8 if one_dir else 0): o_out + (12 if one_dir else 4)].view(torch.float32)[0]
 
     @staticmethod
     def backward(ctx, grad_out):

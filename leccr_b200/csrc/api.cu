@@ -231,7 +231,7 @@ const char* leccr_strerror(int code) {
   }
 }
 const char* leccr_last_cuda_error(void) { return g_cuda_err; }
-int leccr_abi_version(void) { return 1; }
+int leccr_abi_version(void) { return 2; }
 
 void leccr_profile_enable(int on) {
   g_profile = on != 0;
@@ -953,6 +953,87 @@ static int infonce_fwd_impl(const void* a16, const void* b16, int64_t ld16, cons
   return LECCR_OK;
 }
 
+// Strip forward of a distributed step: tensor-core pass over this rank's rows only, statistics exchanged
+// through the peer-mapped slots (see infonce_finalize_local_kernel).  Workspace as leccr_infonce_fwd_workspace.
+static Plan infonce_strip_plan(int64_t n, int64_t row_begin, int64_t row_count) {
+  const int64_t col_tiles = (n + BN - 1) / BN;
+  const int64_t row_blocks = (row_begin + row_count + BM - 1) / BM - row_begin / BM;
+  // one launch carries both orientations: spread 2 * row_blocks * chunks items over the SMs
+  int64_t chunks = std::max<int64_t>(1, num_sms() / std::max<int64_t>(1, 2 * row_blocks));
+  chunks = std::min<int64_t>(chunks, col_tiles);
+  const int tpc = static_cast<int>((col_tiles + chunks - 1) / chunks);
+  return plan_problem(n, row_begin, row_count, tpc);
+}
+// row_blocks * chunks <= max(num_sms / 2, row_blocks of the whole matrix) for every strip of an n-row problem
+static size_t strip_part_bytes(int64_t n) {
+  const int64_t rb_chunks = std::max<int64_t>(num_sms() / 2 + 1, (n + BM - 1) / BM + 1);
+  return align256(static_cast<size_t>(rb_chunks) * BM * EpiLse::kWGs * 5 * 4);
+}
+static double* strip_scratch(int64_t n, void* workspace) {
+  return reinterpret_cast<double*>(static_cast<uint8_t*>(workspace) + 2 * strip_part_bytes(n));
+}
+
+static int infonce_fwd_strips(const void* a16, const void* b16, int64_t ld16, const int64_t* idx, int64_t n, int D,
+                              int fmt, const float* temp, float* out, float* lse2, float* rcnt, int64_t row_begin,
+                              int64_t row_count, float* const* stat_ptrs_dev, const float* local_stat, int world,
+                              int rank, uint32_t* const* flag_ptrs_dev, uint32_t epoch, void* workspace,
+                              size_t workspace_bytes, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (workspace == nullptr || workspace_bytes < 2 * strip_part_bytes(n) + 256) return LECCR_ERR_WORKSPACE;
+  const Plan pl = infonce_strip_plan(n, row_begin, row_count);
+  SimLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.n_prob = 2;
+  L.fmt = fmt;
+  L.k_chunks = (D + BK - 1) / BK;
+  const int items = pl.row_blocks * pl.n_chunks;
+  int rc = fill_problem(L.prob[0], a16, ld16, b16, ld16, n, n, D, fmt, pl, 0);
+  if (rc != LECCR_OK) return rc;
+  rc = fill_problem(L.prob[1], b16, ld16, a16, ld16, n, n, D, fmt, pl, items);
+  if (rc != LECCR_OK) return rc;
+  L.n_items = 2 * items;
+  const int n_sub = pl.n_chunks * EpiLse::kWGs;
+  // partial planes hold the strip's row blocks only; the kernels address rows absolutely, so the plane
+  // pointers are biased by the strip's first row
+  const size_t part_bytes = strip_part_bytes(n);
+  const long long bias = static_cast<long long>(pl.row_block_begin) * BM * n_sub * 5;
+  float* part0 = static_cast<float*>(workspace) - bias;
+  float* part1 = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + part_bytes) - bias;
+  double* scratch = strip_scratch(n, workspace);
+  EpiLse::Params EP;
+  memset(&EP, 0, sizeof(EP));
+  EP.temp = temp;
+  for (int p = 0; p < 2; ++p) {
+    EP.idx_rows[p] = reinterpret_cast<const long long*>(idx);
+    EP.idx_cols[p] = reinterpret_cast<const long long*>(idx);
+    EP.n_sub[p] = n_sub;
+  }
+  EP.part[0] = part0;
+  EP.part[1] = part1;
+  rc = launch_gemm<EpiLse>(L, EP, stream);
+  if (rc != LECCR_OK) return rc;
+  FinalizeLocalParams F;
+  memset(&F, 0, sizeof(F));
+  F.part[0] = part0;
+  F.part[1] = part1;
+  F.nch[0] = F.nch[1] = n_sub;
+  F.n = static_cast<int>(n);
+  F.row_begin = static_cast<int>(row_begin);
+  F.row_count = static_cast<int>(row_count);
+  F.stat_ptrs = stat_ptrs_dev;
+  F.world = world;
+  F.rank = rank;
+  F.scratch = scratch;
+  infonce_finalize_local_kernel<<<static_cast<unsigned>((2 * row_count + 255) / 256), 256, 0, stream>>>(F);
+  LAUNCH_CHECK("infonce_finalize_local_kernel");
+  rc = leccr_peer_barrier(flag_ptrs_dev, world, rank, epoch, stream_);
+  if (rc != LECCR_OK) return rc;
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(32, (2 * n + 255) / 256));
+  infonce_reduce_kernel<<<blocks, 256, 0, stream>>>(local_stat, static_cast<int>(n), world, temp, out, lse2, rcnt);
+  LAUNCH_CHECK("infonce_reduce_kernel");
+  return LECCR_OK;
+}
+
 static int64_t round_up8(int64_t x) { return (x + 7) & ~static_cast<int64_t>(7); }
 
 // split-K factor of the gradient products: fill the machine, at least 2 K-chunks per split
@@ -1132,6 +1213,33 @@ int leccr_peer_barrier(uint32_t* const* flag_ptrs_dev, int world, int rank, uint
   return LECCR_OK;
 }
 
+int leccr_normalize_fwd(const float* x, int64_t n, int D, int64_t ld_x, float* y, int64_t ld_y, float* inv,
+                        void* y16, int64_t ld_y16, int fmt, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (x == nullptr || y == nullptr || n <= 0 || D <= 0 || ld_x < D || ld_y < D || (y16 != nullptr && (bad_fmt(fmt) || ld_y16 < D)))
+    return LECCR_ERR_ARG;
+  const int wpb = 8;
+  const unsigned grid = static_cast<unsigned>((n + wpb - 1) / wpb);
+  if (fmt == LECCR_FMT_BF16)
+    normalize_rows_kernel<1><<<grid, wpb * 32, 0, stream>>>(x, ld_x, (int)n, D, y, ld_y, inv, static_cast<uint16_t*>(y16), ld_y16);
+  else
+    normalize_rows_kernel<0><<<grid, wpb * 32, 0, stream>>>(x, ld_x, (int)n, D, y, ld_y, inv, static_cast<uint16_t*>(y16), ld_y16);
+  LAUNCH_CHECK("normalize_rows_kernel");
+  return LECCR_OK;
+}
+
+int leccr_normalize_bwd(const float* y, int64_t ld_y, const float* inv, const float* g, int64_t ld_g, int64_t n, int D,
+                        float* dx, int64_t ld_dx, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (y == nullptr || inv == nullptr || g == nullptr || dx == nullptr || n <= 0 || D <= 0 || ld_y < D || ld_g < D || ld_dx < D)
+    return LECCR_ERR_ARG;
+  const int wpb = 8;
+  normalize_rows_bwd_kernel<<<static_cast<unsigned>((n + wpb - 1) / wpb), wpb * 32, 0, stream>>>(y, ld_y, inv, g, ld_g, (int)n, D,
+                                                                                              dx, ld_dx);
+  LAUNCH_CHECK("normalize_rows_bwd_kernel");
+  return LECCR_OK;
+}
+
 int leccr_memcpy_peer_async(void* dst, const void* src, size_t bytes, leccr_stream_t stream_) {
   if (dst == nullptr || src == nullptr) return LECCR_ERR_ARG;
   if (bytes == 0) return LECCR_OK;
@@ -1170,22 +1278,26 @@ int leccr_topk_merge_peers(const float* const* val_ptrs_dev, const int32_t* cons
 // ------------------------------------------------------------------------------------ one-call contrastive step
 // The Python shim's per-launch overhead (tens of microseconds per torch / ctypes call) dominated the
 // training step; these two entries issue the whole forward / backward launch sequence from C++.
-size_t leccr_itc_fwd_workspace(int64_t n, int tiles_per_chunk) { return leccr_infonce_fwd_workspace(n, tiles_per_chunk); }
+size_t leccr_itc_fwd_workspace(int64_t n, int tiles_per_chunk) {
+  if (n <= 0) return 0;
+  return std::max(leccr_infonce_fwd_workspace(n, tiles_per_chunk), 2 * strip_part_bytes(n) + 256);
+}
 
 int leccr_itc_forward(const float* image_feat, int64_t ld_img, const float* text_feat, int64_t ld_txt,
                       const int64_t* idx, int64_t B, int D, int fmt, int rank, int world,
                       void* const* rows_ptrs_dev, void* const* idx_ptrs_dev, uint32_t* const* flag_ptrs_dev,
-                      uint32_t epoch, const void* local_slot, size_t local_slot_bytes, void* both16,
-                      int64_t* idx_all, const float* temp, float* out, float* lse2, float* rcnt,
-                      void* workspace, size_t workspace_bytes, leccr_stream_t stream_) {
+                      uint32_t epoch, const void* local_slot, size_t local_slot_bytes, void* const* stat_ptrs_dev,
+                      const void* local_stat_slot, void* both16, int64_t* idx_all, const float* temp, float* out,
+                      float* lse2, float* rcnt, void* workspace, size_t workspace_bytes, leccr_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (image_feat == nullptr || text_feat == nullptr || both16 == nullptr || B <= 0 || D <= 0 || (D & 7) != 0 ||
       bad_fmt(fmt) || world < 1 || rank < 0 || rank >= world || (idx != nullptr && idx_all == nullptr) ||
       ld_img < D || ld_txt < D)
     return LECCR_ERR_ARG;
   const int64_t n = B * world;
-  if (workspace == nullptr || workspace_bytes < leccr_infonce_fwd_workspace(n, 0)) return LECCR_ERR_WORKSPACE;
-  double* scratch = infonce_fwd_scratch(n, 0, workspace);
+  if (workspace == nullptr || workspace_bytes < leccr_itc_fwd_workspace(n, 0)) return LECCR_ERR_WORKSPACE;
+  const bool strips = world > 1 && stat_ptrs_dev != nullptr && local_stat_slot != nullptr;
+  double* scratch = strips ? strip_scratch(n, workspace) : infonce_fwd_scratch(n, 0, workspace);
   uint16_t* both = static_cast<uint16_t*>(both16);
   // ONE launch casts both operands (and pushes idx): into every rank's peer-mapped slot (world > 1, NVLink
   // stores) or straight into the private buffers (world == 1, a "world" of this rank's own two pointers)
@@ -1225,6 +1337,11 @@ int leccr_itc_forward(const float* image_feat, int64_t ld_img, const float* text
   // private copy (one memcpy: the slot and the private buffer share the layout [rows | idx]): the peer-mapped
   // slot is reused two calls later, the backward runs after that
   CUDA_TRY(cudaMemcpyAsync(both, local_slot, local_slot_bytes, cudaMemcpyDeviceToDevice, stream));
+  if (strips)  // this rank's row strips + statistics exchange
+    return infonce_fwd_strips(both, both + D, 2 * D, idx != nullptr ? idx_all : nullptr, n, D, fmt, temp, out, lse2,
+                              rcnt, static_cast<int64_t>(rank) * B, B, reinterpret_cast<float* const*>(stat_ptrs_dev),
+                              static_cast<const float*>(local_stat_slot), world, rank, flag_ptrs_dev, epoch + 1u,
+                              workspace, workspace_bytes, stream_);
   return infonce_fwd_impl(both, both + D, 2 * D, idx != nullptr ? idx_all : nullptr, n, D, fmt, temp, out, lse2, rcnt,
                           0, workspace, workspace_bytes, true, stream_);
 }

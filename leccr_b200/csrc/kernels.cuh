@@ -244,6 +244,54 @@ __global__ void prep_rows_vec_pair_kernel(const PrepTensor t0, const PrepTensor 
 }
 
 // --------------------------------------------------------------------------------
+// normalize_rows: y = x / max(||x||_2, 1e-12) per row == F.normalize(x, dim=-1), the last step of
+// XVLMBase.get_features (models/xvlm.py:245-256, models/xvlm_video.py:264-277), as a training op: fp32 result
+// (what the reference hands to its losses), 1 / max(||x||, eps) kept for the backward, and -- optionally, in the
+// same pass -- the 16-bit tensor-core operand of y, so the similarity stage needs no second cast.
+// One warp per row.  Backward: dx = inv * (g - y (y . g)) where ||x|| > eps, g * inv below (clamp_min passes no
+// gradient to the norm).
+// --------------------------------------------------------------------------------
+template <int FMT>
+__global__ void normalize_rows_kernel(const float* __restrict__ x, long long ld_x, int n, int D, float* __restrict__ y,
+                                      long long ld_y, float* __restrict__ inv_out, uint16_t* __restrict__ y16,
+                                      long long ld_y16) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float* xr = x + static_cast<long long>(row) * ld_x;
+  float ss = 0.f;
+  for (int d = lane; d < D; d += 32) ss = fmaf(xr[d], xr[d], ss);
+  const float nrm = sqrtf(warp_sum(ss));
+  const float inv = 1.f / fmaxf(nrm, 1e-12f);
+  if (lane == 0 && inv_out != nullptr) inv_out[row] = nrm > 1e-12f ? inv : -inv;  // sign bit marks a clamped row
+  float* yr = y + static_cast<long long>(row) * ld_y;
+  for (int d = lane; d < D; d += 32) {
+    const float v = xr[d] * inv;
+    yr[d] = v;
+    if (y16 != nullptr) y16[static_cast<long long>(row) * ld_y16 + d] = f32_to_16<FMT>(v);
+  }
+}
+
+__global__ void normalize_rows_bwd_kernel(const float* __restrict__ y, long long ld_y, const float* __restrict__ inv_in,
+                                          const float* __restrict__ g, long long ld_g, int n, int D,
+                                          float* __restrict__ dx, long long ld_dx) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float* yr = y + static_cast<long long>(row) * ld_y;
+  const float* gr = g + static_cast<long long>(row) * ld_g;
+  const float iv = inv_in[row];
+  const bool clamped = iv < 0.f;
+  const float inv = fabsf(iv);
+  float dot = 0.f;
+  if (!clamped)
+    for (int d = lane; d < D; d += 32) dot = fmaf(yr[d], gr[d], dot);
+  dot = warp_sum(dot);
+  float* o = dx + static_cast<long long>(row) * ld_dx;
+  for (int d = lane; d < D; d += 32) o[d] = inv * (gr[d] - yr[d] * dot);
+}
+
+// --------------------------------------------------------------------------------
 // prep_push: the cast prologue fused with its all-gather.  Every rank casts ITS rows of the fp32
 // features to the 16-bit operand format and stores them straight into EVERY rank's gathered operand
 // buffer (peer pointers over NVLink, own pointer included) at its row offset -- the exchange of
@@ -516,6 +564,110 @@ __global__ void infonce_finalize_kernel(const FinalizeLseParams P) {
     P.out[3] = static_cast<float>(l1);
     P.out[4] = static_cast<float>(-d0 / temp);  // d loss_i2t / d temp, d loss_t2i / d temp (one-directional losses)
     P.out[5] = static_cast<float>(-d1 / temp);
+  }
+}
+
+// --------------------------------------------------------------------------------
+// Strip forward (world > 1): a rank runs the tensor-core pass for ITS rows only -- rows [row_begin, +row_count)
+// of both orientations, all n columns -- because a row's log-sum-exp, positives and E_softmax[z] depend on that
+// row alone (models/xvlm.py:279-290 are row-wise).  What the backward and the scalar loss need from the other
+// ranks is only the per-row statistics: infonce_finalize_local merges this rank's chunk partials and stores
+// lse2 / rcnt of its rows into EVERY rank's statistics slot through peer pointers, plus this rank's four partial
+// sums; after one barrier infonce_reduce adds the partial sums of all ranks in rank order (same bits on every
+// rank) and copies the statistics into the private buffers the backward reads.
+// Statistics slot layout: float lse2[2][n] | float rcnt[2][n] | double partial[world][4].
+// --------------------------------------------------------------------------------
+struct FinalizeLocalParams {
+  const float* part[2];
+  int nch[2];
+  int n, row_begin, row_count;
+  float* const* stat_ptrs;  // [world] device pointers to every rank's slot (own rank included)
+  int world, rank;
+  double* scratch;          // local: 4 partial sums + ticket, zeroed before the launch
+};
+
+__global__ void infonce_finalize_local_kernel(const FinalizeLocalParams P) {
+  __shared__ double red[4][8];
+  __shared__ bool is_last;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = gid >= P.row_count ? 1 : 0;
+  const int lr = p ? gid - P.row_count : gid;
+  if (lr < P.row_count) {
+    const int r = P.row_begin + lr;
+    const float* q = P.part[p] + static_cast<long long>(r) * P.nch[p] * 5;
+    float m = -CUDART_INF_F;
+    for (int c = 0; c < P.nch[p]; ++c) m = fmaxf(m, q[5 * c]);
+    float l = 0.f, w = 0.f, pz = 0.f, cnt = 0.f;
+    for (int c = 0; c < P.nch[p]; ++c) {
+      const float s = exp2f(q[5 * c] - m);
+      l = fmaf(q[5 * c + 1], s, l);
+      w = fmaf(q[5 * c + 2], s, w);
+      pz += q[5 * c + 3];
+      cnt += q[5 * c + 4];
+    }
+    const float lse2 = m + log2f(l);
+    const float rc = cnt > 0.f ? 1.f / cnt : 0.f;
+    const long long o = static_cast<long long>(p) * P.n + r;
+    for (int w2 = 0; w2 < P.world; ++w2) {
+      float* st = P.stat_ptrs[w2];
+      st[o] = lse2;
+      st[2LL * P.n + o] = rc;
+    }
+    acc[p] = 0.6931471805599453 * (static_cast<double>(lse2) - static_cast<double>(pz) * rc);
+    acc[2 + p] = 0.6931471805599453 * (static_cast<double>(w) / l - static_cast<double>(pz) * rc);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = 0; k < 4; ++k) {
+    double v = acc[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[k][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = blockDim.x >> 5;
+    for (int k = 0; k < 4; ++k) {
+      double t = 0.0;
+      for (int w = 0; w < nw; ++w) t += red[k][w];
+      atomicAdd(P.scratch + k, t);
+    }
+    __threadfence();
+    const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(P.scratch + 4), 1u);
+    is_last = ticket == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x < 4) {
+    __threadfence();
+    const double v = *(reinterpret_cast<volatile double*>(P.scratch) + threadIdx.x);
+    for (int w2 = 0; w2 < P.world; ++w2) {
+      double* part = reinterpret_cast<double*>(P.stat_ptrs[w2] + 4LL * P.n);
+      part[4 * P.rank + threadIdx.x] = v;
+    }
+  }
+}
+
+// After the barrier: scalars from the partial sums of all ranks (fixed order), statistics -> private buffers.
+__global__ void infonce_reduce_kernel(const float* __restrict__ stat, int n, int world, const float* __restrict__ temp,
+                                      float* __restrict__ out, float* __restrict__ lse2, float* __restrict__ rcnt) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nt = gridDim.x * blockDim.x;
+  for (int i = tid; i < 2 * n; i += nt) {
+    lse2[i] = stat[i];
+    rcnt[i] = stat[2LL * n + i];
+  }
+  if (tid == 0) {
+    const double* part = reinterpret_cast<const double*>(stat + 4LL * n);
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int w = 0; w < world; ++w)
+      for (int k = 0; k < 4; ++k) s[k] += part[4 * w + k];
+    const double l0 = s[0] / n, l1 = s[1] / n, d0 = s[2] / n, d1 = s[3] / n;
+    const double t = static_cast<double>(*temp);
+    out[0] = static_cast<float>(0.5 * (l0 + l1));
+    out[1] = static_cast<float>(-0.5 * (d0 + d1) / t);
+    out[2] = static_cast<float>(l0);
+    out[3] = static_cast<float>(l1);
+    out[4] = static_cast<float>(-d0 / t);
+    out[5] = static_cast<float>(-d1 / t);
   }
 }
 

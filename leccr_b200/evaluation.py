@@ -166,16 +166,73 @@ def _dist_scale(distributed: bool) -> float:
     return 1.0
 
 
-def _collect_text(model, texts, tokenizer, device, config):
-    embeds = []
+class FeatureGallery:
+    """An embedding set that arrives batch by batch, written straight into a preallocated tensor-core operand.
+
+    The reference appends every batch's features to a Python list and `torch.cat`s them at the end
+    (image_Retrieval_caption.py:112-118,144-148; video_Retrieval_caption_double_sim.py:124-131,158-162): two
+    copies of the set and one allocation per batch.  Here the cast prologue (leccr_prep) writes each batch at its
+    row offset of ONE 16-bit buffer in the layout the similarity pass consumes (split-precision [hi|lo|hi] /
+    [hi|hi|lo] for the fp32-faithful matrices the drop-ins return), so nothing is kept in fp32 and nothing is
+    concatenated.  `capacity` is the number of rows when known (len(dataset)); otherwise the buffer doubles."""
+
+    def __init__(self, dim, precision="f16x3", role="rows", capacity=0, device=None):
+        self.dev = device or _device()
+        self.D = dim
+        self.fmt = ops.fmt_of(precision)
+        self.layout = N.LAYOUT_HI if not precision.endswith("x3") else (N.LAYOUT_X3_ROWS if role == "rows" else N.LAYOUT_X3_COLS)
+        self.K = dim if self.layout == N.LAYOUT_HI else 3 * dim
+        self.dt16 = torch.float16 if self.fmt == N.FMT_F16 else torch.bfloat16
+        self.n = 0
+        self.buf = torch.empty((max(int(capacity), 0), self.K), dtype=self.dt16, device=self.dev)
+
+    def append(self, feats: torch.Tensor):
+        """feats: [b, D] fp32 CUDA rows (e.g. model.get_features(...) of one batch)."""
+        if feats.dim() != 2 or feats.shape[1] != self.D:
+            raise N.LeccrError(f"FeatureGallery expects [b, {self.D}] rows")
+        if not feats.is_cuda:
+            raise N.LeccrError("leccr_b200 has no CPU path: features must be CUDA tensors")
+        b = feats.shape[0]
+        if b == 0:
+            return
+        if feats.dtype != torch.float32 or feats.stride(1) != 1:
+            feats = feats.float().contiguous()
+        if self.n + b > self.buf.shape[0]:
+            grown = torch.empty((max(2 * self.buf.shape[0], self.n + b, 1024), self.K), dtype=self.dt16, device=self.dev)
+            grown[:self.n].copy_(self.buf[:self.n])
+            self.buf = grown
+        dst = self.buf[self.n:self.n + b]
+        N.check(N.load().leccr_prep(N.ptr(feats), b, self.D, feats.stride(0), 0, self.fmt, self.layout, N.ptr(dst), self.K,
+                                    None, None, None, N.stream_ptr()), "leccr_prep")
+        self.n += b
+
+    def operand(self) -> ops.Operand:
+        t16 = self.buf[:self.n]
+        return ops.Operand(t16, self.fmt, self.layout, self.n, self.D, None, None, None, t16)
+
+
+def _len_or_zero(x):
+    try:
+        return len(x)
+    except TypeError:
+        return 0
+
+
+def _collect_text(model, texts, tokenizer, device, config, precision="f16x3"):
+    """Text side of evaluation_coarse (image_Retrieval_caption.py:99-118): encoder + get_features per batch as in
+    the reference, each batch written into the preallocated column operand."""
     bs = config['batch_size_test_text']
+    gal = None
     for i in range(0, len(texts), bs):
         chunk = texts[i: min(len(texts), i + bs)]
         tok = tokenizer(chunk, padding='max_length', truncation=True, max_length=config['max_tokens'],
                         return_tensors="pt").to(device)
         feat = model.get_text_embeds(tok.input_ids, tok.attention_mask)
-        embeds.append(model.get_features(text_embeds=feat))
-    return torch.cat(embeds, dim=0)
+        f = model.get_features(text_embeds=feat)
+        if gal is None:
+            gal = FeatureGallery(f.shape[1], precision, "cols", len(texts), f.device)
+        gal.append(f)
+    return gal
 
 
 def _caption_inputs(model, generated_captions, tokenizer, device, config, clip_tokenizer):
@@ -194,8 +251,8 @@ def evaluation_coarse(model, data_loader, tokenizer, device, config, distributed
     """Drop-in for the image evaluation_coarse: encoders run as in the reference (they are out of scope),
     the similarity stage (:147-163) runs on the tensor cores.  Returns (i2t, t2i) numpy, t2i a view of i2t.T."""
     model.eval()
-    text_embeds = _collect_text(model, data_loader.dataset.text, tokenizer, device, config)
-    image_embeds = []
+    texts = _collect_text(model, data_loader.dataset.text, tokenizer, device, config)
+    images = None
     for image, generated_captions, img_id in data_loader:
         image = image.to(device)
         image_feat, _ = model.get_vision_embeds(image)
@@ -203,9 +260,11 @@ def evaluation_coarse(model, data_loader, tokenizer, device, config, distributed
         image_feat, _, _ = model.interaction_with_caption(image_embeds=image_feat, caption_embeds=caption_embed,
                                                           key_padding_mask=kpm)
         image_feat = image_feat.transpose(0, 1).contiguous()
-        image_embeds.append(model.get_features(image_embeds=image_feat))
-    image_embeds = torch.cat(image_embeds, dim=0)
-    S = score_matrix(image_embeds, text_embeds, _dist_scale(distributed))
+        f = model.get_features(image_embeds=image_feat)
+        if images is None:
+            images = FeatureGallery(f.shape[1], "f16x3", "rows", _len_or_zero(data_loader.dataset), f.device)
+        images.append(f)
+    S = ops.sim_matrix(images.operand(), texts.operand(), _dist_scale(distributed))
     i2t = S.cpu().numpy()
     _remember_device_copy(i2t, S)
     return i2t, i2t.T
@@ -216,8 +275,8 @@ def evaluation_coarse_video(model, data_loader, tokenizer, device, config, alpha
                             clip_tokenizer=None):
     """Drop-in for the video evaluation_coarse with the double_sim fusion (:164-190)."""
     model.eval()
-    text_embeds = _collect_text(model, data_loader.dataset.text, tokenizer, device, config)
-    image_embeds, caption_embeds = [], []
+    texts = _collect_text(model, data_loader.dataset.text, tokenizer, device, config)
+    videos, captions = None, None
     for video, mask_video, generated_captions, img_id in data_loader:
         video = video.to(device)
         mask_video = mask_video.to(device)
@@ -226,11 +285,24 @@ def evaluation_coarse_video(model, data_loader, tokenizer, device, config, alpha
         image_feat, caption_embed, _ = model.interaction_with_caption(
             image_embeds=image_feat, caption_embeds=caption_embed, key_padding_mask=kpm, video_mask=image_atts)
         image_feat = image_feat.transpose(0, 1).contiguous()
-        image_embeds.append(model.get_features(image_embeds=image_feat, vis_mask=mask_video.unsqueeze(-1)))
-        caption_embeds.append(model.caption_proj1(caption_embed))
-    image_embeds = torch.cat(image_embeds, dim=0)
-    caption_embeds = torch.cat(caption_embeds, dim=1)
-    S = double_sim_matrix(image_embeds, text_embeds, caption_embeds, alpha, "norm", _dist_scale(distributed))
+        f = model.get_features(image_embeds=image_feat, vis_mask=mask_video.unsqueeze(-1))
+        cap = model.caption_proj1(caption_embed)          # [n, bsz, d], not normalised (:157)
+        if videos is None:
+            total = _len_or_zero(data_loader.dataset)
+            videos = FeatureGallery(f.shape[1], "f16x3", "rows", total, f.device)
+            captions = [FeatureGallery(cap.shape[2], "f16x3", "rows", total, f.device) for _ in range(cap.shape[0])]
+        videos.append(f)
+        for q, g in enumerate(captions):
+            g.append(cap[q])
+    t_op = texts.operand()
+    S = ops.sim_matrix(videos.operand(), t_op)
+    Cn = torch.empty((len(captions),) + tuple(S.shape), dtype=torch.float32, device=S.device)
+    for q, g in enumerate(captions):
+        ops.sim_matrix(g.operand(), t_op, out=Cn[q])
+    ops.double_sim_fuse(S, Cn, alpha, N.FUSE_NORM)
+    scale = _dist_scale(distributed)
+    if scale != 1.0:
+        S.mul_(scale)
     i2t = S.cpu().numpy()
     _remember_device_copy(i2t, S)
     return i2t, i2t.T

@@ -15,6 +15,7 @@ from . import caption_loss as _cl
 from . import contrastive as _ct
 from .dstl_loss import dstl_loss as _dstl_loss  # (same shadowing: the package attribute is the function)
 from . import evaluation as _ev
+from . import features as _ft
 
 
 def _patch_xvlm(mod, base_name):
@@ -23,6 +24,8 @@ def _patch_xvlm(mod, base_name):
     base = getattr(mod, base_name, None)
     if base is not None:
         base.get_contrastive_loss = _ct.get_contrastive_loss
+        # models/xvlm.py:241 / models/xvlm_video.py:260: same name, the video variant pools with a frame mask
+        base.get_features = _ft.get_features_video if base_name == "XVLMBase_video" else _ft.get_features
 
 
 def install(modules=("models.xvlm", "models.xvlm_video")):

@@ -122,20 +122,26 @@ def get_buffer(key, nbytes: int, device, slots: int = 2):
 
 def itc_slot(B: int, D: int, fmt: int, device):
     """Peer-mapped slot for one contrastive exchange (leccr_itc_forward): returns
-    (rows_table, idx_table, flag_table, epoch, local_slot_ptr) or None when peer exchange is not available.
-    Slot layout = the private buffer's: [n][2D] 16-bit rows (padded to 256 bytes) then [n] int64 labels.
-    Collective on first use per shape; alternates two slots."""
+    (rows_table, idx_table, flag_table, epoch, local_slot_ptr, stat_table, local_stat_ptr) or None when peer
+    exchange is not available.  Slot layout = the private buffer's: [n][2D] 16-bit rows (padded to 256 bytes),
+    [n] int64 labels (padded), then the statistics of the strip forward: float lse2[2][n] | float rcnt[2][n] |
+    double partial[world][4].  Collective on first use per shape; alternates two slots; a call takes TWO barrier
+    epochs (rows exchange, statistics exchange)."""
     if not available(device):
         return None
     world = dist.get_world_size()
     n = B * world
     rows_bytes = (n * 2 * D * 2 + 255) // 256 * 256
-    pb = get_buffer(("itc", B, D, fmt), rows_bytes + n * 8, device)
+    idx_bytes = (n * 8 + 255) // 256 * 256
+    stat_bytes = 16 * n + 32 * world
+    pb = get_buffer(("itc", B, D, fmt), rows_bytes + idx_bytes + stat_bytes, device)
     if pb is None:
         return None
     off = pb.slot_offset(pb.next_slot())
-    pb.epoch += 1
-    return pb.table(off), pb.table(off + rows_bytes), pb.flag_table, pb.epoch, pb.buf.data_ptr() + off
+    pb.epoch += 2
+    stat_off = off + rows_bytes + idx_bytes
+    return (pb.table(off), pb.table(off + rows_bytes), pb.flag_table, pb.epoch - 1, pb.buf.data_ptr() + off,
+            pb.table(stat_off), pb.buf.data_ptr() + stat_off)
 
 
 def merge_topk_peers(val, idx, shard_offset: int, k: int, all_queries: bool = True, offsets=None, ranks=None):

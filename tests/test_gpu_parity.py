@@ -694,3 +694,86 @@ def test_gallery_search_plan_device_and_host_paths_against_oracle():
         assert 100.0 * hits / Q == ev[f"img_r{c}"], (c, hits, ev)
     with pytest.raises(N.LeccrError):
         plan.search_host(gal.float(), qry.float())   # the plan's dtype is binding: no silent conversion
+
+
+# ----------------------------------------------------------------------------- get_features
+def test_get_features_drop_in_against_the_reference_golden(golden):
+    """XVLMBase.get_features (models/xvlm.py:241-256) through the drop-in: features and the gradients autograd
+    sends back to the tokens and the projection weights equal the reference's own run (tests/golden/get_features.npz)."""
+    g = golden("get_features.npz")
+    W, D = g["vW"].shape[1], g["vW"].shape[0]
+    vproj, tproj = torch.nn.Linear(W, D).cuda(), torch.nn.Linear(W, D).cuda()
+    with torch.no_grad():
+        vproj.weight.copy_(torch.from_numpy(g["vW"])); vproj.bias.copy_(torch.from_numpy(g["vb"]))
+        tproj.weight.copy_(torch.from_numpy(g["tW"])); tproj.bias.copy_(torch.from_numpy(g["tb"]))
+    me = types.SimpleNamespace(vision_proj=vproj, text_proj=tproj)
+    img_tok = torch.from_numpy(g["img_tok"]).cuda().requires_grad_(True)
+    txt_tok = torch.from_numpy(g["txt_tok"]).cuda().requires_grad_(True)
+    fi, ft = leccr_b200.get_features(me, img_tok, txt_tok)
+    np.testing.assert_allclose(fi.detach().cpu().numpy(), g["feat_i"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(ft.detach().cpu().numpy(), g["feat_t"], rtol=0, atol=2e-6)
+    ((fi * torch.from_numpy(g["up_i"]).cuda()).sum() + (ft * torch.from_numpy(g["up_t"]).cuda()).sum()).backward()
+    for got, want in ((img_tok.grad, "d_img_tok"), (txt_tok.grad, "d_txt_tok"), (vproj.weight.grad, "d_vW"),
+                      (tproj.weight.grad, "d_tW")):
+        w = torch.from_numpy(g[want])
+        assert (got.cpu() - w).norm() <= 1e-5 * w.norm(), want
+    # single-modality forms and the oracle's restatement
+    only_t = leccr_b200.get_features(me, text_embeds=txt_tok)
+    want_t = oracle.get_features(txt_tok.detach().cpu(), tproj.weight.detach().cpu(), tproj.bias.detach().cpu())
+    assert (only_t.detach().cpu() - want_t).abs().max() < 2e-6
+    mean_i = leccr_b200.get_features(me, image_embeds=img_tok, vis_pooling='mean')
+    want_m = torch.nn.functional.normalize(vproj(img_tok.mean(1)), dim=-1)
+    assert (mean_i - want_m).abs().max() < 2e-6
+    mask = (torch.rand(img_tok.shape[0], img_tok.shape[1], 1, device="cuda") > 0.3).float()
+    mask[:, 0] = 1.0
+    vid = leccr_b200.get_features_video(me, image_embeds=img_tok, vis_mask=mask)
+    want_v = torch.nn.functional.normalize(vproj((img_tok * mask).sum(1) / mask.sum(1)), dim=-1)
+    assert (vid - want_v).abs().max() < 2e-6
+
+
+def test_normalize_rows_and_the_fused_cast_against_torch():
+    """leccr_normalize_fwd / bwd vs F.normalize and its autograd (incl. a zero row: clamp_min semantics), and the
+    normalise fused into the cast prologue (leccr_prep normalize=1) vs F.normalize rounded to the operand format."""
+    gsd = torch.Generator().manual_seed(3)
+    x = (torch.randn(777, 256, generator=gsd) * torch.rand(777, 1, generator=gsd) * 5).cuda()
+    x[5] = 0.0
+    up = torch.randn(777, 256, generator=gsd).cuda()
+    xa = x.clone().requires_grad_(True)
+    ya = leccr_b200.normalize_rows(xa)
+    (ya * up).sum().backward()
+    xb = x.clone().requires_grad_(True)
+    yb = torch.nn.functional.normalize(xb, dim=-1)
+    (yb * up).sum().backward()
+    assert (ya - yb).abs().max() < 1e-6
+    assert torch.isfinite(xa.grad).all()
+    keep = torch.ones(777, dtype=torch.bool, device="cuda")
+    keep[5] = False
+    assert (xa.grad[keep] - xb.grad[keep]).norm() <= 1e-5 * xb.grad[keep].norm()
+    assert (xa.grad[5] - xb.grad[5]).norm() <= 1e-5 * xb.grad[5].norm()   # 1e12 * upstream on the clamped row
+    for fmt, dt in ((N.FMT_F16, torch.float16), (N.FMT_BF16, torch.bfloat16)):
+        got = ops.prep(x, fmt, normalize=True, want_stats=False).t16
+        want = yb.detach().to(dt)
+        # one rounding of a value that may differ by 1 ulp of fp32 before it: at most one 16-bit ulp apart
+        ulp = 2.0 ** (-10 if dt == torch.float16 else -7)
+        assert (got.float() - want.float()).abs().max() <= ulp * want.float().abs().max()
+        assert (got == want).float().mean() > 0.99
+
+
+def test_feature_gallery_equals_the_cast_of_the_concatenation():
+    """FeatureGallery (image_Retrieval_caption.py:112-118,144-148): batches written at their row
+    offset of one preallocated operand == leccr_prep of torch.cat(batches), bit for bit, with a known capacity and
+    with a buffer that has to grow; ragged batch sizes."""
+    gsd = torch.Generator().manual_seed(17)
+    batches = [torch.nn.functional.normalize(torch.randn(b, 64, generator=gsd), dim=-1).cuda() for b in (32, 32, 7, 1, 50)]
+    whole = torch.cat(batches)
+    for precision, role, layout in (("f16x3", "rows", N.LAYOUT_X3_ROWS), ("f16x3", "cols", N.LAYOUT_X3_COLS),
+                                    ("bf16", "rows", N.LAYOUT_HI)):
+        want = ops.prep(whole, ops.fmt_of(precision), layout, want_stats=False).t16
+        for cap in (whole.shape[0], 0):
+            gal = leccr_b200.FeatureGallery(64, precision, role, cap)
+            for bt in batches:
+                gal.append(bt)
+            op = gal.operand()
+            assert op.n == whole.shape[0] and torch.equal(op.t16, want)
+    with pytest.raises(N.LeccrError):
+        leccr_b200.FeatureGallery(64).append(torch.zeros(3, 32, device="cuda"))

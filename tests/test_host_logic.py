@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), name
     assert sorted(N.EXPORTS) == names, "ctypes signatures and header disagree"
-    assert lib.leccr_abi_version() == 1
+    assert lib.leccr_abi_version() == 2
     assert b"sm_100" in lib.leccr_strerror(-3)
 
 
