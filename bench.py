@@ -428,7 +428,51 @@ def contrastive_leg(torch, dist, leccr_b200, synth, dev, rank, world, peak, max_
         wall_us = (time.perf_counter() - t0) / reps * 1e6
         us, wall_us = max_over_ranks([e0.elapsed_time(e1) / reps * 1e3, wall_us])
         flops = 2.0 * n * n * DIM + 2.0 * 2.0 * B * n * DIM   # fwd 2 N^2 D + local grads 2 * (2 B N D); no recompute
+        # the same step captured once in a CUDA graph and replayed (what a training loop under torch.cuda.graphs
+        # pays): device-bound time, the eager figure above is bound by the host issuing ~12 launches through autograd
+        graph_us = None
+        cap_ok, g = True, None
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                a2 = a.detach().clone().requires_grad_(True)
+                b2 = b.detach().clone().requires_grad_(True)
+                me2 = types.SimpleNamespace(embed_dim=DIM, temp=torch.nn.Parameter(torch.tensor(cb.temp, device=dev)))
+
+                def step2():
+                    leccr_b200.get_contrastive_loss(me2, a2, b2, idx).backward()
+
+                for _ in range(3):
+                    a2.grad = b2.grad = me2.temp.grad = None
+                    step2()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            a2.grad = b2.grad = me2.temp.grad = None
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step2()
+        except Exception as ex:  # capture is optional evidence, never fatal
+            cap_ok = False
+            sys.stderr.write(f"contrastive graph capture failed: {type(ex).__name__}: {str(ex)[:200]}\n")
+        if all_ok(cap_ok):  # every rank replays the same number of barriers, or nobody replays
+            for _ in range(3):
+                g.replay()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            graph_us = max_over_ranks([e0.elapsed_time(e1) / reps * 1e3])[0]
+            ga = max_over_ranks([((a2.grad - a.grad).norm() / a.grad.norm()).item()])[0]
+            chk[name]["graph_replay_dA_rel_vs_eager"] = ga
+            chk["ok"] = chk["ok"] and ga < 1e-5
         out[name] = {"per_rank_batch": B, "global_batch": n, "us_per_step": us, "wall_us_per_step": wall_us,
+                     "graph_replay_us_per_step": graph_us,
+                     "graph_replay_frac_of_peak": None if graph_us is None else flops / graph_us / 1e6 / peak,
                      "algorithmic_gflop_per_rank": flops / 1e9, "tflops_per_rank": flops / us / 1e6,
                      "frac_of_peak": flops / us / 1e6 / peak,
                      "includes": "cast + exchange (peer-memory push + barrier), forward, backward of the local rows, "

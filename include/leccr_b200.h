@@ -243,7 +243,9 @@ int leccr_normalize_bwd(const float* y, int64_t ld_y, const float* inv, const fl
  * included; the Python shim obtains them from torch.distributed._symmetric_memory.
  *
  * leccr_peer_barrier: stream-ordered barrier across the ranks.  flag_ptrs_dev[p] -> rank p's block of
- *   `world` uint32 words (zero-initialised once); `epoch` must grow by one per barrier on every rank.
+ *   64 uint32 words (zero-initialised once: `world` flags, word 48 an epoch counter); `epoch` must grow by one
+ *   per barrier on every rank, or be 0 on every call: the kernel then takes the next epoch from the counter
+ *   word itself, the launch has no per-call argument and can be captured in a CUDA graph.
  *   The wait is bounded by wall time: LECCR_PEER_TIMEOUT_S seconds (default 600, 0 = for ever), then the
  *   kernel reports the missing peer and traps.
  *   Orders all earlier peer stores of this stream before all later work of the peers' streams.
@@ -282,7 +284,8 @@ int leccr_topk_merge_peers(const float* const* val_ptrs_dev, const int32_t* cons
  *                B rows of both orientations only (1 / world of the work) and the per-row statistics are
  *                exchanged: stat_ptrs_dev[p] -> rank p's peer-mapped statistics slot, float lse2[2][n] |
  *                float rcnt[2][n] | double partial[world][4]; local_stat_slot = this rank's.  A second barrier
- *                (epoch + 1: the caller advances its epoch by TWO per call) orders the exchange.  7 launches:
+ *                (epoch + 1, or 0 again in counter mode: the caller advances its epoch by TWO per call) orders the
+ *                exchange.  7 launches:
  *                push, barrier, copy, tensor-core pass, finalize + push, barrier, reduce.
  *   both16 : out, private [n][2D] 16-bit gathered operands [image | text] (saved for the backward)
  *   idx_all: out, [n] int64 (when idx != NULL);  out/lse2/rcnt as in leccr_infonce_fwd

@@ -1340,7 +1340,7 @@ int leccr_itc_forward(const float* image_feat, int64_t ld_img, const float* text
   if (strips)  // this rank's row strips + statistics exchange
     return infonce_fwd_strips(both, both + D, 2 * D, idx != nullptr ? idx_all : nullptr, n, D, fmt, temp, out, lse2,
                               rcnt, static_cast<int64_t>(rank) * B, B, reinterpret_cast<float* const*>(stat_ptrs_dev),
-                              static_cast<const float*>(local_stat_slot), world, rank, flag_ptrs_dev, epoch + 1u,
+                              static_cast<const float*>(local_stat_slot), world, rank, flag_ptrs_dev, epoch == 0u ? 0u : epoch + 1u,
                               workspace, workspace_bytes, stream_);
   return infonce_fwd_impl(both, both + D, 2 * D, idx != nullptr ? idx_all : nullptr, n, D, fmt, temp, out, lse2, rcnt,
                           0, workspace, workspace_bytes, true, stream_);

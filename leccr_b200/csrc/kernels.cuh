@@ -1253,9 +1253,23 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// epoch == 0: the epoch comes from a device-resident counter (word kBarrierCounterWord of the rank's own flag
+// block, advanced by the kernel), so the launch has no per-call argument and a training step that contains
+// barriers can be captured in a CUDA graph and replayed.
+constexpr int kBarrierCounterWord = 48;
 __global__ void peer_barrier_kernel(unsigned* const* __restrict__ flags, int world, int rank, unsigned epoch,
                                     unsigned long long timeout_ns) {
+  __shared__ unsigned s_epoch;
   const int p = threadIdx.x;
+  if (epoch == 0u) {
+    if (p == 0) {
+      unsigned* counter = flags[rank] + kBarrierCounterWord;
+      s_epoch = *counter + 1u;
+      *counter = s_epoch;
+    }
+    __syncthreads();
+    epoch = s_epoch;
+  }
   if (p >= world) return;
   __threadfence_system();
   unsigned* theirs = flags[p] + rank;

@@ -97,9 +97,10 @@ class PeerBuffer:
         return self.buf[byte_offset: byte_offset + nbytes].view(dtype).view(shape)
 
     def barrier(self):
-        self.epoch += 1
-        N.check(N.load().leccr_peer_barrier(N.ptr(self.flag_table), self.world, self.rank, self.epoch,
-                                            N.stream_ptr()), "leccr_peer_barrier")
+        """Epoch 0 = the kernel advances a device-resident epoch counter: no per-call argument, so sequences
+        containing barriers can be captured in CUDA graphs (every rank replays the same number of barriers)."""
+        N.check(N.load().leccr_peer_barrier(N.ptr(self.flag_table), self.world, self.rank, 0, N.stream_ptr()),
+                "leccr_peer_barrier")
 
 
 def get_buffer(key, nbytes: int, device, slots: int = 2):
@@ -125,8 +126,8 @@ def itc_slot(B: int, D: int, fmt: int, device):
     (rows_table, idx_table, flag_table, epoch, local_slot_ptr, stat_table, local_stat_ptr) or None when peer
     exchange is not available.  Slot layout = the private buffer's: [n][2D] 16-bit rows (padded to 256 bytes),
     [n] int64 labels (padded), then the statistics of the strip forward: float lse2[2][n] | float rcnt[2][n] |
-    double partial[world][4].  Collective on first use per shape; alternates two slots; a call takes TWO barrier
-    epochs (rows exchange, statistics exchange)."""
+    double partial[world][4].  Collective on first use per shape; alternates two slots; epoch 0 = the barrier
+    kernels keep their own epoch counter (graph-capturable)."""
     if not available(device):
         return None
     world = dist.get_world_size()
@@ -138,9 +139,8 @@ def itc_slot(B: int, D: int, fmt: int, device):
     if pb is None:
         return None
     off = pb.slot_offset(pb.next_slot())
-    pb.epoch += 2
     stat_off = off + rows_bytes + idx_bytes
-    return (pb.table(off), pb.table(off + rows_bytes), pb.flag_table, pb.epoch - 1, pb.buf.data_ptr() + off,
+    return (pb.table(off), pb.table(off + rows_bytes), pb.flag_table, 0, pb.buf.data_ptr() + off,
             pb.table(stat_off), pb.buf.data_ptr() + stat_off)
 
 
