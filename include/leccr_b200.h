@@ -224,6 +224,31 @@ int leccr_double_sim_fuse(float* S, const float* Cn, int n_cap, int64_t numel, f
                           float w1, float w2, int mode, leccr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * leccr_double_sim_topk: the double_sim evaluation fused into the tensor-core epilogue -- no N x M matrix.
+ * Replaces: video_Retrieval_caption_double_sim.py:170-179 (S = V T^T, C = max_n caption_n T^T,
+ * alpha * norm_score(S) + (1 - alpha) * norm_score(C), both directions; norm_score :87-91) followed by itm_eval
+ * (:194-247), and the raw variant image_Retrieval_caption.py:239-246 (mode RAW).
+ *   vc16 : [G * n_vid][K] 16-bit, the videos and their caption queries INTERLEAVED: row G i = video i, rows
+ *          G i + 1 .. G i + n_cap = caption_1..n (i), rows above repeat the last caption.  G in {2, 4, 8} > n_cap.
+ *          Split-precision layout LECCR_LAYOUT_X3_COLS (K = 3 D) for fp32-faithful scores, or HI (K = D).
+ *   t16  : [n_txt][K] texts, layout LECCR_LAYOUT_X3_ROWS (or HI).  Both contiguous (ld = K).
+ *   w1, w2 : alpha, 1 - alpha.   txt_gt: [n_txt] ground-truth video of every text (txt2img), or NULL: no ranks.
+ *   vid_gt_off / vid_gt_ids : CSR of img2txt; it must be the inverse map of txt_gt (every dataset of the
+ *          reference builds them together, dataset/retrieval_dataset_video.py:201-219).
+ *   topk_*_vc : [G * n_vid][k] per-VC-row lists (row G i = video i's top-k texts) or NULL (orientation A skipped);
+ *   topk_*_txt: [n_txt][k] per-text top-k videos or NULL.   rank_vid [n_vid], rank_txt [n_txt]: number of scores
+ *   strictly above the row's best ground-truth score;  recall_counts [6]: #{rank < 1, 5, 10} i2t then t2i.
+ * Pass 1 (tensor cores, nothing stored): min / max of S and max_n C_n, scores at the ground truth.  Pass 2
+ * (recompute): fuse with the reference's fp32 operation order, count, top-k lists.
+ * ------------------------------------------------------------------------------------------ */
+size_t leccr_double_sim_topk_workspace(int64_t n_vid, int64_t n_txt, int G);
+int leccr_double_sim_topk(const void* vc16, const void* t16, int64_t n_vid, int64_t n_txt, int K, int fmt, int G,
+                          int n_cap, float w1, float w2, int mode, const int32_t* txt_gt, const int32_t* vid_gt_off,
+                          const int32_t* vid_gt_ids, int k, float* topk_val_vc, int32_t* topk_idx_vc,
+                          float* topk_val_txt, int32_t* topk_idx_txt, int32_t* rank_vid, int32_t* rank_txt,
+                          int32_t* recall_counts, void* workspace, size_t workspace_bytes, leccr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * leccr_normalize_fwd / leccr_normalize_bwd: row-wise L2 normalisation as a training op.
  * Replaces: the F.normalize(..., dim=-1) of XVLMBase.get_features, models/xvlm.py:245-256 and
  * models/xvlm_video.py:264-277 (the projection in front of it stays torch's Linear).

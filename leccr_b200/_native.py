@@ -89,6 +89,9 @@ _SIGNATURES = {
     "leccr_dstl_bwd_workspace": (sz, [i64, i64, c_int]),
     "leccr_dstl_bwd": (c_int, [vp, vp, vp, vp, i64, vp, i64, i64, c_int, c_int, i64, i64, vp, vp, vp, vp, sz, vp]),
     "leccr_peer_barrier": (c_int, [vp, c_int, c_int, ctypes.c_uint32, vp]),
+    "leccr_double_sim_topk_workspace": (sz, [i64, i64, c_int]),
+    "leccr_double_sim_topk": (c_int, [vp, vp, i64, i64, c_int, c_int, c_int, c_int, c_float, c_float, c_int, vp, vp, vp,
+                                      c_int, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "leccr_normalize_fwd": (c_int, [vp, i64, c_int, i64, vp, i64, vp, vp, i64, c_int, vp]),
     "leccr_normalize_bwd": (c_int, [vp, i64, vp, vp, i64, i64, c_int, vp, i64, vp]),
     "leccr_memcpy_peer_async": (c_int, [vp, vp, sz, vp]),

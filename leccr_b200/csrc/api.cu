@@ -863,6 +863,204 @@ int leccr_sim_topk_stream(const leccr_topk_problem* probs, const leccr_topk_stre
   return topk_core(probs, streams, plans, n_prob, D, fmt, k, two ? 1 : 0, stream);
 }
 
+// ------------------------------------------------------------------------------------ double_sim, fused
+// Two tensor-core passes over the interleaved video/caption operand (EpiDsStats, EpiDsTopK); no N x M buffer.
+// Problem order of the plans: [0] orientation A (rows VC, columns texts), [1] orientation B.
+static int ds_plan(int64_t n_vid, int64_t n_txt, int G, Plan* plans) {
+  leccr_topk_problem pr[2];
+  memset(pr, 0, sizeof(pr));
+  pr[0].n_rows = G * n_vid;
+  pr[0].n_cols = n_txt;
+  pr[1].n_rows = n_txt;
+  pr[1].n_cols = G * n_vid;
+  return topk_plan(pr, 2, 0, plans);
+}
+
+size_t leccr_double_sim_topk_workspace(int64_t n_vid, int64_t n_txt, int G) {
+  if (n_vid <= 0 || n_txt <= 0 || (G != 2 && G != 4 && G != 8)) return 0;
+  Plan plans[2];
+  if (ds_plan(n_vid, n_txt, G, plans) != LECCR_OK) return 0;
+  return topk_ws_bytes(G * n_vid, plans[0].n_chunks, true) + topk_ws_bytes(n_txt, plans[1].n_chunks, true) +
+         align256(static_cast<size_t>(n_txt) * 4) * 3 + align256(static_cast<size_t>(n_vid) * 4) + 256;
+}
+
+extern "C++" {
+template <int G>
+static int ds_launch(const void* vc16, const void* t16, int64_t n_vid, int64_t n_txt, int K, int fmt, int n_cap,
+                     float w1, float w2, int mode, const int32_t* txt_gt, const int32_t* vid_gt_off,
+                     const int32_t* vid_gt_ids, int k, float* topk_val_vc, int32_t* topk_idx_vc, float* topk_val_txt,
+                     int32_t* topk_idx_txt, int32_t* rank_vid, int32_t* rank_txt, int32_t* recall_counts,
+                     void* workspace, cudaStream_t stream) {
+  Plan plans[2];
+  int rc = ds_plan(n_vid, n_txt, G, plans);
+  if (rc != LECCR_OK) return rc;
+  const int64_t n_vc = G * n_vid;
+  const bool ranks = txt_gt != nullptr;
+  const bool lists_a = topk_val_vc != nullptr && topk_idx_vc != nullptr;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  uint8_t* ws_list[2] = {ws, ws + topk_ws_bytes(n_vc, plans[0].n_chunks, true)};
+  ws = ws_list[1] + topk_ws_bytes(n_txt, plans[1].n_chunks, true);
+  float* gt_s = reinterpret_cast<float*>(ws);
+  ws += align256(static_cast<size_t>(n_txt) * 4);
+  float* gt_c = reinterpret_cast<float*>(ws);
+  ws += align256(static_cast<size_t>(n_txt) * 4);
+  float* txt_best = reinterpret_cast<float*>(ws);
+  ws += align256(static_cast<size_t>(n_txt) * 4);
+  float* vid_best = reinterpret_cast<float*>(ws);
+  ws += align256(static_cast<size_t>(n_vid) * 4);
+  unsigned* mm = reinterpret_cast<unsigned*>(ws);
+  mm_init_kernel<<<1, 32, 0, stream>>>(mm);
+  LAUNCH_CHECK("mm_init_kernel");
+  // ---- pass 1 (orientation B): min / max of S and max_n C_n, (S, max C) at every text's ground-truth video
+  if (mode == LECCR_FUSE_NORM || ranks) {
+    SimLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.n_prob = 1;
+    L.fmt = fmt;
+    L.k_chunks = (K + BK - 1) / BK;
+    const int64_t tiles = ((n_txt + BM - 1) / BM) * ((n_vc + BN - 1) / BN);
+    const Plan pl = plan_problem(n_vc, 0, n_txt, auto_tiles_per_chunk(tiles, 1));
+    rc = fill_problem(L.prob[0], t16, K, vc16, K, n_txt, n_vc, K, fmt, pl, 0);
+    if (rc != LECCR_OK) return rc;
+    L.n_items = pl.row_blocks * pl.n_chunks;
+    typename EpiDsStats<G>::Params EP;
+    memset(&EP, 0, sizeof(EP));
+    EP.n_cap = n_cap;
+    EP.n_groups = static_cast<int>(n_vid);
+    EP.gt_group = txt_gt;
+    EP.gt_s = gt_s;
+    EP.gt_c = gt_c;
+    EP.mm = mm;
+    rc = launch_gemm<EpiDsStats<G>>(L, EP, stream);
+    if (rc != LECCR_OK) return rc;
+  }
+  if (ranks) {
+    const unsigned g = static_cast<unsigned>((n_txt + n_vid + 255) / 256);
+    ds_gt_scores_kernel<<<g, 256, 0, stream>>>(gt_s, gt_c, (int)n_txt, vid_gt_off, vid_gt_ids, (int)n_vid, mm, w1, w2, mode,
+                                               txt_best, vid_best);
+    LAUNCH_CHECK("ds_gt_scores_kernel");
+    CUDA_TRY(cudaMemsetAsync(rank_vid, 0, static_cast<size_t>(n_vid) * 4, stream));
+    CUDA_TRY(cudaMemsetAsync(rank_txt, 0, static_cast<size_t>(n_txt) * 4, stream));
+    CUDA_TRY(cudaMemsetAsync(recall_counts, 0, 6 * 4, stream));
+  }
+  // ---- pass 2: orientation B (ranks of both directions, per-text lists) and, for per-video lists, orientation A
+  SimLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.fmt = fmt;
+  L.k_chunks = (K + kBK2 - 1) / kBK2;
+  typename EpiDsTopK<G>::Params EP;
+  memset(&EP, 0, sizeof(EP));
+  EP.dense = 1;
+  EP.trig = TopK2D::TRIG;
+  const void* rows16[2] = {vc16, t16};
+  const void* cols16[2] = {t16, vc16};
+  const int64_t nr[2] = {n_vc, n_txt}, nc[2] = {n_txt, n_vc};
+  float* cand_val[2] = {nullptr, nullptr};
+  int* cand_idx[2] = {nullptr, nullptr};
+  int* cand_cnt[2] = {nullptr, nullptr};
+  int item_base = 0, g = 0;
+  for (int p = lists_a ? 0 : 1; p < 2; ++p, ++g) {
+    uint8_t* w = ws_list[p];
+    const size_t lists = static_cast<size_t>(nr[p]) * plans[p].n_chunks * 4;
+    cand_val[p] = reinterpret_cast<float*>(w);
+    w += align256(lists * 32 * 4);
+    cand_idx[p] = reinterpret_cast<int*>(w);
+    w += align256(lists * 32 * 4);
+    cand_cnt[p] = reinterpret_cast<int*>(w);
+    w += align256(lists * 4);
+    w += align256(static_cast<size_t>(nr[p]) * 4 + 16);  // (flag list of the exact-rank fallback: unused here)
+    unsigned* row_thr = reinterpret_cast<unsigned*>(w);
+    CUDA_TRY(cudaMemsetAsync(row_thr, 0, static_cast<size_t>(nr[p]) * 12, stream));
+    rc = fill_problem(L.prob[g], rows16[p], K, cols16[p], K, nr[p], nc[p], K, fmt, plans[p], item_base, kBK2);
+    if (rc != LECCR_OK) return rc;
+    item_base += plans[p].row_blocks * plans[p].n_chunks;
+    EP.row_thr[g] = row_thr;
+    EP.row_h8[g] = row_thr + nr[p];
+    EP.out_val[g] = cand_val[p];
+    EP.out_idx[g] = cand_idx[p];
+    EP.out_cnt[g] = cand_cnt[p];
+    EP.n_sub[g] = plans[p].n_chunks * 2;
+  }
+  L.n_prob = g;
+  L.n_items = item_base;
+  EP.b_problem = g - 1;
+  EP.n_cap = n_cap;
+  EP.n_groups = static_cast<int>(n_vid);
+  EP.mm = mm;
+  EP.w1 = w1;
+  EP.w2 = w2;
+  EP.mode = mode;
+  EP.txt_best = ranks ? txt_best : nullptr;
+  EP.vid_best = ranks ? vid_best : nullptr;
+  EP.rank_txt = ranks ? rank_txt : nullptr;
+  EP.rank_vid = ranks ? rank_vid : nullptr;
+  rc = launch_gemm<EpiDsTopK<G>, kBK2>(L, EP, stream);
+  if (rc != LECCR_OK) return rc;
+  // ---- top-k lists out of the candidate lists (no exact re-scoring: the scores ARE the fp32-faithful fused ones)
+  float* tv[2] = {topk_val_vc, topk_val_txt};
+  int32_t* ti[2] = {topk_idx_vc, topk_idx_txt};
+  for (int p = 0; p < 2; ++p) {
+    if (tv[p] == nullptr || ti[p] == nullptr || cand_val[p] == nullptr) continue;
+    TopkFinalizeParams F;
+    memset(&F, 0, sizeof(F));
+    F.cand_val = cand_val[p];
+    F.cand_idx = cand_idx[p];
+    F.cand_cnt = cand_cnt[p];
+    F.n_rows = static_cast<int>(nr[p]);
+    F.n_cols = static_cast<int>(p == 0 ? n_txt : n_vid);
+    F.n_chunks = plans[p].n_chunks * 2;
+    F.list_cap = TopK2D::C;
+    F.KP = LECCR_TOPK_KP;
+    F.k = k;
+    F.topk_val = tv[p];
+    F.topk_idx = ti[p];
+    const unsigned grid = static_cast<unsigned>((F.n_rows + kFinalizeWarps - 1) / kFinalizeWarps);
+    const int slots = F.n_chunks;
+    if (slots <= 2) topk_finalize_kernel<2><<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
+    else if (slots <= 4) topk_finalize_kernel<4><<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
+    else if (slots <= 8) topk_finalize_kernel<8><<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
+    else topk_finalize_kernel<kMaxSlots><<<grid, kFinalizeWarps * 32, 0, stream>>>(F);
+    LAUNCH_CHECK("topk_finalize_kernel");
+  }
+  if (ranks) {
+    const unsigned g0 = static_cast<unsigned>(std::min<int64_t>((n_vid + 255) / 256, 2LL * num_sms()));
+    recall_count_kernel<<<g0, 256, 0, stream>>>(rank_vid, (int)n_vid, recall_counts);
+    LAUNCH_CHECK("recall_count_kernel");
+    const unsigned g1 = static_cast<unsigned>(std::min<int64_t>((n_txt + 255) / 256, 2LL * num_sms()));
+    recall_count_kernel<<<g1, 256, 0, stream>>>(rank_txt, (int)n_txt, recall_counts + 3);
+    LAUNCH_CHECK("recall_count_kernel");
+  }
+  return LECCR_OK;
+}
+}  // extern "C++"
+
+int leccr_double_sim_topk(const void* vc16, const void* t16, int64_t n_vid, int64_t n_txt, int K, int fmt, int G,
+                          int n_cap, float w1, float w2, int mode, const int32_t* txt_gt, const int32_t* vid_gt_off,
+                          const int32_t* vid_gt_ids, int k, float* topk_val_vc, int32_t* topk_idx_vc,
+                          float* topk_val_txt, int32_t* topk_idx_txt, int32_t* rank_vid, int32_t* rank_txt,
+                          int32_t* recall_counts, void* workspace, size_t workspace_bytes, leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (vc16 == nullptr || t16 == nullptr || n_vid <= 0 || n_txt <= 0 || K <= 0 || (K & 7) != 0 || bad_fmt(fmt) ||
+      (G != 2 && G != 4 && G != 8) || n_cap < 1 || n_cap >= G || (mode != LECCR_FUSE_NORM && mode != LECCR_FUSE_RAW) ||
+      k < 1 || k > LECCR_TOPK_KP)
+    return LECCR_ERR_ARG;
+  if (txt_gt != nullptr && (vid_gt_off == nullptr || vid_gt_ids == nullptr || rank_vid == nullptr || rank_txt == nullptr ||
+                            recall_counts == nullptr))
+    return LECCR_ERR_ARG;
+  int rc = leccr_check_device();
+  if (rc != LECCR_OK) return rc;
+  const size_t need = leccr_double_sim_topk_workspace(n_vid, n_txt, G);
+  if (need == 0) return LECCR_ERR_ARG;
+  if (workspace == nullptr || workspace_bytes < need) return LECCR_ERR_WORKSPACE;
+#define LECCR_DS(GG)                                                                                                  \
+  ds_launch<GG>(vc16, t16, n_vid, n_txt, K, fmt, n_cap, w1, w2, mode, txt_gt, vid_gt_off, vid_gt_ids, k, topk_val_vc, \
+                topk_idx_vc, topk_val_txt, topk_idx_txt, rank_vid, rank_txt, recall_counts, workspace, stream)
+  if (G == 2) return LECCR_DS(2);
+  if (G == 4) return LECCR_DS(4);
+  return LECCR_DS(8);
+#undef LECCR_DS
+}
+
 // ------------------------------------------------------------------------------------ InfoNCE
 static Plan infonce_plan(int64_t n, int tiles_per_chunk) {
   const int64_t tiles = 2 * ((n + BM - 1) / BM) * ((n + BN - 1) / BN);

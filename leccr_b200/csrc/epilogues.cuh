@@ -341,6 +341,33 @@ struct EpiTopK {
     return pack_state(keep_thr, j);
   }
 
+  // The unfiltered treatment of one chunk of 32 values (dense mode; also the consumer of the fused double_sim
+  // scores, EpiDsTopK): every value is offered to the list, four at a time, with a (warp-uniform) check for a
+  // shrink round every 16.  Invariant: cnt <= DTRIG before every 16 values.
+  __device__ static void dense_chunk(State& st, const float (&v)[32], int col, unsigned* my_h8, unsigned* shared_thr) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float thr = st.thr;
+      uint32_t cur = st.vb + st.cnt * ES;  // list cursor as an address: one predicated add per element
+#pragma unroll
+      for (int e = 0; e < 16; e += 4)
+        cur = append4_if_gt(v[16 * h + e], v[16 * h + e + 1], v[16 * h + e + 2], v[16 * h + e + 3], thr, cur,
+                            col + 16 * h + e);
+      const int cnt = static_cast<int>(cur - st.vb) / ES;
+      st.dc[4] += cnt - st.cnt;
+      st.cnt = cnt;
+      if (__any_sync(0xffffffffu, cnt > DTRIG)) {
+        ++st.dc[3];
+        if (cnt > JOIN) {
+          const unsigned long long r = quad_shrink(st.thr, cnt, st.vb, st.ib, my_h8);
+          st.thr = __uint_as_float(static_cast<unsigned>(r >> 32));
+          st.cnt = static_cast<int>(r & 0xffffffffu);
+          if (shared_thr != nullptr) atomicMax(shared_thr, f32_key(st.thr));
+        }
+      }
+    }
+  }
+
   // Called before the wait for the accumulator: the (L2) read of the row's shared threshold overlaps it.
   // A threshold proven valid by ANY column chunk of this row is valid for every chunk; stale reads are fine.
   __device__ static void prefetch(State& st, const Params& P, const ItemCtx& c) {
@@ -387,27 +414,7 @@ struct EpiTopK {
       }
       const int col = lcol + cb;  // stored indices are global
       if (dense) {  // warp-uniform; invariant: cnt <= DTRIG = C - 16 before every 16 columns
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float thr = st.thr;
-          uint32_t cur = st.vb + st.cnt * ES;  // list cursor as an address: one predicated add per element
-#pragma unroll
-          for (int e = 0; e < 16; e += 4)
-            cur = append4_if_gt(v[16 * h + e], v[16 * h + e + 1], v[16 * h + e + 2], v[16 * h + e + 3], thr, cur,
-                                col + 16 * h + e);
-          const int cnt = static_cast<int>(cur - st.vb) / ES;
-          st.dc[4] += cnt - st.cnt;
-          st.cnt = cnt;
-          if (__any_sync(0xffffffffu, cnt > DTRIG)) {
-            ++st.dc[3];
-            if (cnt > JOIN) {
-              const unsigned long long r = quad_shrink(st.thr, cnt, st.vb, st.ib, my_h8);
-              st.thr = __uint_as_float(static_cast<unsigned>(r >> 32));
-              st.cnt = static_cast<int>(r & 0xffffffffu);
-              if (shared_thr != nullptr) atomicMax(shared_thr, f32_key(st.thr));
-            }
-          }
-        }
+        dense_chunk(st, v, col, my_h8, shared_thr);
         return;
       }
       if (MODE == 1) return;  // compile-time: nothing below exists in the dense-only kernel
@@ -722,6 +729,216 @@ struct EpiGrad {
         }
       }
     });
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// double_sim in the epilogue (video_Retrieval_caption_double_sim.py:170-179; raw variant
+// image_Retrieval_caption.py:239-246):   F = w1 * f(S) + w2 * f(max_n C_n),  S = V T^T,  C_n = cap_n T^T.
+// The video rows and their n caption queries are INTERLEAVED into one operand "VC" in groups of G rows
+// (G = 2, 4, 8 >= n + 1; row G i = video i, rows G i + 1 .. G i + n = its captions, the rest repeat the last
+// caption), so ONE accumulator tile holds S and every C_n of a block of videos and the plain mainloop serves:
+//   orientation B (rows = texts, columns = VC): a thread finds S and the C_n of a (text, video) pair in G
+//                 adjacent registers;
+//   orientation A (rows = VC, columns = texts): in G adjacent lanes -- log2 G shuffles.
+// Pass 1 (EpiDsStats, orientation B, nothing stored but 2 floats per text): global min / max of S and of
+// max_n C_n (norm_score, :87-91) and, for every text, S and max C at its ground-truth video.  Pass 2
+// (EpiDsTopK, both orientations in one launch): recompute, fuse with the reference's fp32 operation order,
+// count the scores above the row's best ground-truth score (rank = number of strictly greater, as everywhere
+// in this library) and feed the per-row top-k lists.  The N x M matrices never reach HBM.
+// ------------------------------------------------------------------------------------------
+struct DsFuse {
+  float smax, sden, cmax, cden, w1, w2;
+  int mode;  // 1 norm, 2 raw
+  __device__ __forceinline__ float operator()(float s, float c) const {
+    if (mode == 1) {
+      s = -__fdiv_rn(__fsub_rn(smax, s), sden);
+      c = -__fdiv_rn(__fsub_rn(cmax, c), cden);
+    }
+    return __fadd_rn(__fmul_rn(w1, s), __fmul_rn(w2, c));
+  }
+};
+__device__ __forceinline__ float ds_ordered_f32(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ __forceinline__ DsFuse ds_fuse_load(const unsigned* mm, float w1, float w2, int mode) {
+  DsFuse f;
+  f.w1 = w1;
+  f.w2 = w2;
+  f.mode = mode;
+  f.smax = f.cmax = 0.f;
+  f.sden = f.cden = 1.f;
+  if (mode == 1) {
+    f.smax = ds_ordered_f32(mm[0]);
+    f.sden = __fsub_rn(f.smax, ds_ordered_f32(mm[1]));
+    f.cmax = ds_ordered_f32(mm[2]);
+    f.cden = __fsub_rn(f.cmax, ds_ordered_f32(mm[3]));
+  }
+  return f;
+}
+
+template <int G>
+struct EpiDsStats {
+  struct Params {
+    int n_cap;              // caption queries per video (1 <= n_cap < G)
+    int n_groups;           // videos
+    const int* gt_group;    // [n_rows] ground-truth video of every text, or null
+    float* gt_s;            // [n_rows] S at the ground truth
+    float* gt_c;            // [n_rows] max_n C_n at the ground truth
+    unsigned* mm;           // ordered-uint {max S, min S, max C, min C} (mm_init_kernel)
+  };
+  static constexpr int kWGs = 2;
+  static constexpr bool kSplitCols = false;
+  static constexpr int kSmemBytes = 16;
+  struct State {
+    float smax, smin, cmax, cmin;
+    int gt;
+  };
+  __device__ static void begin(State& st, const Params& P, const ItemCtx& c) {
+    st.smax = st.cmax = -CUDART_INF_F;
+    st.smin = st.cmin = CUDART_INF_F;
+    st.gt = (P.gt_group != nullptr && c.row < c.n_rows) ? __ldg(P.gt_group + c.row) : -1;
+  }
+  __device__ static void prefetch(State&, const Params&, const ItemCtx&) {}
+  __device__ static void tile(State& st, const Params& P, const ItemCtx& c, uint32_t taddr, int col0) {
+    const bool row_ok = c.row < c.n_rows;
+    const int n_cap = P.n_cap;
+    for_each_chunk(taddr, col0, c.n_cols, [&](float(&v)[32], int col) {
+#pragma unroll
+      for (int q = 0; q < 32 / G; ++q) {
+        const int grp = col / G + q;
+        const float s = v[q * G];
+        float cm = v[q * G + 1];
+#pragma unroll
+        for (int k = 2; k < G; ++k)
+          if (k <= n_cap) cm = fmaxf(cm, v[q * G + k]);
+        if (row_ok && grp < P.n_groups) {
+          st.smax = fmaxf(st.smax, s);
+          st.smin = fminf(st.smin, s);
+          st.cmax = fmaxf(st.cmax, cm);
+          st.cmin = fminf(st.cmin, cm);
+          if (grp == st.gt) {
+            P.gt_s[c.row] = s;
+            P.gt_c[c.row] = cm;
+          }
+        }
+      }
+    });
+  }
+  __device__ static void end(State& st, const Params& P, const ItemCtx& c) {
+    const float a = warp_max(st.smax), b = warp_min(st.smin), d = warp_max(st.cmax), e = warp_min(st.cmin);
+    if (c.lane == 0 && a >= b) {  // a < b: this warp saw no valid element
+      atomicMax(P.mm + 0, f32_key(a));
+      atomicMin(P.mm + 1, f32_key(b));
+      atomicMax(P.mm + 2, f32_key(d));
+      atomicMin(P.mm + 3, f32_key(e));
+    }
+  }
+};
+
+// Pass 2.  Problem 1 = orientation B (rows texts, columns VC; stored column = video index): BOTH rank
+// directions are counted here, from the same accumulator bits pass 1 took the ground-truth scores from (the
+// other orientation sums its split-precision blocks in another order and may differ in the last bit, which
+// would let a ground-truth element beat itself): a text's own row count is thread-local, a video's count is an
+// atomicAdd per score that beats the video's best ground truth (a handful per video).  Problem 0 = orientation
+// A (rows VC, columns texts) exists only for the per-video top-k lists (list rows are VC rows, only rows G i
+// carry data) and is left out when no lists are wanted.  Lists, thresholds, shrink rounds and the write-out
+// are EpiTopK's (two warpgroups, dense).
+template <int G>
+struct EpiDsTopK : EpiTopK<16, 64, 2, 1> {
+  using Base = EpiTopK<16, 64, 2, 1>;
+  struct Params : Base::Params {
+    int n_cap, n_groups;
+    const unsigned* mm;
+    float w1, w2;
+    int mode;
+    int b_problem;           // index of the orientation-B problem in the launch (0 when A is left out)
+    const float* txt_best;   // [n_texts] fused score at the text's ground-truth video, or null (no ranks)
+    const float* vid_best;   // [n_groups] best fused ground-truth score of the video
+    int* rank_txt;           // [n_texts]  zeroed, atomically accumulated
+    int* rank_vid;           // [n_groups]
+  };
+  struct State : Base::State {
+    DsFuse fuse;
+    float gt;
+    int above;
+  };
+  __device__ static void begin(State& st, const Params& P, const ItemCtx& c) {
+    Base::begin(st, P, c);
+    st.fuse = ds_fuse_load(P.mm, P.w1, P.w2, P.mode);
+    st.above = 0;
+    st.gt = (c.p == P.b_problem && P.txt_best != nullptr && c.row < c.n_rows) ? __ldg(P.txt_best + c.row) : CUDART_INF_F;
+  }
+  __device__ static void prefetch(State& st, const Params& P, const ItemCtx& c) { Base::prefetch(st, P, c); }
+  __device__ static void tile(State& st, const Params& P, const ItemCtx& c, uint32_t taddr, int col0) {
+    const int n_cols = c.n_cols;
+    unsigned* shared_thr = (P.row_thr[c.p] != nullptr && c.row < c.n_rows) ? P.row_thr[c.p] + c.row : nullptr;
+    if (st.pre_key > f32_key(st.thr)) st.thr = key_f32(st.pre_key);
+    {
+      const unsigned u = min(st.own_h8, st.pre_h8);
+      if (u > f32_key(st.thr)) st.thr = key_f32(u);
+    }
+    unsigned* my_h8 = (P.row_h8[c.p] != nullptr && c.row < c.n_rows)
+                          ? P.row_h8[c.p] + 2 * static_cast<long long>(c.row) + c.wg : nullptr;
+    if (__any_sync(0xffffffffu, st.cnt > Base::DTRIG)) {
+      if (st.cnt > Base::JOIN) {
+        const unsigned long long r = Base::quad_shrink(st.thr, st.cnt, st.vb, st.ib, my_h8);
+        st.thr = __uint_as_float(static_cast<unsigned>(r >> 32));
+        st.cnt = static_cast<int>(r & 0xffffffffu);
+        if (shared_thr != nullptr) atomicMax(shared_thr, f32_key(st.thr));
+      }
+    }
+    const int n_cap = P.n_cap;
+    const bool row_ok = c.row < c.n_rows;
+    if (c.p != P.b_problem) {
+      // orientation A: lane = VC row; the G lanes of a video combine with shuffles
+      const int m = c.row % G;                       // 0 video, 1..n_cap captions, above: padding
+      const bool head = m == 0 && row_ok;
+      const int base_lane = c.lane & ~(G - 1);
+      for_each_chunk(taddr, col0, n_cols, [&](float(&v)[32], int lcol) {
+        float w[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          float x = (m >= 1 && m <= n_cap) ? v[e] : -CUDART_INF_F;
+#pragma unroll
+          for (int o = 1; o < G; o <<= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+          const float s = __shfl_sync(0xffffffffu, v[e], base_lane);
+          w[e] = (head && lcol + e < n_cols) ? st.fuse(s, x) : -CUDART_INF_F;
+        }
+        Base::dense_chunk(st, w, lcol, my_h8, shared_thr);
+      }, BN / 32 / kWGs);
+    } else {
+      // orientation B: G adjacent columns = one video
+      const int n_groups = P.n_groups;
+      const bool ranks = P.txt_best != nullptr;
+      for_each_chunk(taddr, col0, n_cols, [&](float(&v)[32], int lcol) {
+        float w[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) w[e] = -CUDART_INF_F;
+#pragma unroll
+        for (int q = 0; q < 32 / G; ++q) {
+          const float s = v[q * G];
+          float cm = v[q * G + 1];
+#pragma unroll
+          for (int k = 2; k < G; ++k)
+            if (k <= n_cap) cm = fmaxf(cm, v[q * G + k]);
+          const float f = st.fuse(s, cm);
+          const int grp = lcol / G + q;
+          const bool ok = row_ok && grp < n_groups;
+          w[q] = ok ? f : -CUDART_INF_F;
+          if (ranks && ok) {
+            st.above += f > st.gt ? 1 : 0;
+            if (f > __ldg(P.vid_best + grp)) atomicAdd(P.rank_vid + grp, 1);
+          }
+        }
+        Base::dense_chunk(st, w, lcol / G, my_h8, shared_thr);   // stored column = video index (+ e)
+      }, BN / 32 / kWGs);
+    }
+  }
+  __device__ static void end(State& st, const Params& P, const ItemCtx& c) {
+    if (c.p == P.b_problem && P.rank_txt != nullptr && st.above > 0 && c.row < c.n_rows)
+      atomicAdd(P.rank_txt + c.row, st.above);
+    Base::end(st, P, c);
   }
 };
 

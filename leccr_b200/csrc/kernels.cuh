@@ -1238,6 +1238,30 @@ __global__ void fuse_scores_kernel(float* __restrict__ S, const float* __restric
   }
 }
 
+// Ground-truth scores of the fused double_sim evaluation (between its two tensor-core passes): thread t < n_txt
+// fuses (S, max C) of text t at its ground-truth video -> the score text t has to beat in the t2i direction;
+// thread n_txt + i takes the best of video i's ground-truth texts (rank = min over the ground truth =
+// number of scores above the BEST ground-truth score, image_Retrieval_caption.py:274-278).
+__global__ void ds_gt_scores_kernel(const float* __restrict__ gt_s, const float* __restrict__ gt_c, int n_txt,
+                                    const int* __restrict__ vid_off, const int* __restrict__ vid_ids, int n_vid,
+                                    const unsigned* __restrict__ mm, float w1, float w2, int mode,
+                                    float* __restrict__ txt_gt, float* __restrict__ vid_best) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_txt + n_vid) return;
+  const DsFuse fuse = ds_fuse_load(mm, w1, w2, mode);
+  if (t < n_txt) {
+    txt_gt[t] = fuse(gt_s[t], gt_c[t]);
+  } else {
+    const int i = t - n_txt;
+    float best = -CUDART_INF_F;
+    for (int e = vid_off[i]; e < vid_off[i + 1]; ++e) {
+      const int g = vid_ids[e];
+      best = fmaxf(best, fuse(gt_s[g], gt_c[g]));
+    }
+    vid_best[i] = vid_off[i + 1] > vid_off[i] ? best : CUDART_INF_F;
+  }
+}
+
 // --------------------------------------------------------------------------------
 // Cross-rank exchange helpers over peer memory (one node, NVLink / NVSwitch).
 // --------------------------------------------------------------------------------

@@ -317,11 +317,12 @@ def prepare_gt(txt2img, img2txt, n_img, n_txt, device=None):
 
 
 @torch.no_grad()
-def _fused_eval_double_sim(image_embeds, text_embeds, caption_embeds, txt2img, img2txt, k, alpha, fusion, return_topk, gt):
-    """double_sim variant of fused_eval: the fused matrix alpha * f(S) + (1 - alpha) * f(max_n C_n) is
-    materialised on the device (max_n needs every C_n tile beside the S tile: (n + 1) * 256 TMEM columns,
-    DESIGN.md section 7), ranked exactly there (leccr_rank_rows / leccr_rank_cols) and its top-k lists read by
-    leccr_topk_dense; only the six counts cross PCIe."""
+def _fused_eval_double_sim_materialized(image_embeds, text_embeds, caption_embeds, txt2img, img2txt, k, alpha, fusion,
+                                        return_topk, gt):
+    """double_sim with the fused matrix alpha * f(S) + (1 - alpha) * f(max_n C_n) MATERIALISED on the device,
+    ranked there (leccr_rank_rows / leccr_rank_cols) and its top-k lists read by leccr_topk_dense; only the six
+    counts cross PCIe.  The fallback of _fused_eval_double_sim for ground-truth maps the epilogue path does not
+    take (texts with several ground-truth videos, maps that are not inverses, more than 7 caption queries)."""
     dev = _device()
     F_ = double_sim_matrix(image_embeds, text_embeds, caption_embeds, alpha, fusion)
     n_img, n_txt = F_.shape
@@ -334,6 +335,86 @@ def _fused_eval_double_sim(image_embeds, text_embeds, caption_embeds, txt2img, i
     if not return_topk:
         return ev
     return ev, {'i2t': ops.topk_dense(F_, k), 't2i': ops.topk_dense(F_, k, by_columns=True)}
+
+
+_gt_inverse_ok = {}
+
+
+def _single_gt_per_text(gt, n_img, n_txt):
+    """txt_gt [n_txt] int32 when every text has exactly one ground-truth video AND the video CSR is the inverse
+    map (what the reference's datasets build, dataset/retrieval_dataset_video.py:201-219); else None."""
+    (v_off, v_ids), (t_off, t_ids) = gt
+    key = (v_off.data_ptr(), v_ids.data_ptr(), t_off.data_ptr(), t_ids.data_ptr(), n_img, n_txt)
+    ok = _gt_inverse_ok.get(key)
+    if ok is None:
+        ok = False
+        if t_ids.numel() == n_txt and v_ids.numel() == n_txt and t_off.numel() == n_txt + 1:
+            counts = (v_off[1:] - v_off[:-1]).long()
+            owner = torch.repeat_interleave(torch.arange(n_img, device=v_off.device), counts)
+            ok = bool(torch.equal(t_off.long(), torch.arange(n_txt + 1, device=t_off.device))) and \
+                bool(torch.equal(t_ids.long()[v_ids.long()], owner))
+        if len(_gt_inverse_ok) > 64:
+            _gt_inverse_ok.clear()
+        _gt_inverse_ok[key] = ok
+    return t_ids if ok else None
+
+
+@torch.no_grad()
+def _fused_eval_double_sim(image_embeds, text_embeds, caption_embeds, txt2img, img2txt, k, alpha, fusion, return_topk, gt,
+                           precision="f16x3"):
+    """double_sim evaluation with the fusion IN the tensor-core epilogue (leccr_double_sim_topk): the videos and
+    their caption queries are interleaved into one operand, pass 1 reduces the global min / max of S and
+    max_n C_n and picks up the ground-truth scores, pass 2 recomputes, fuses with the reference's fp32 operation
+    order (video_Retrieval_caption_double_sim.py:87-91,175-179), counts ranks and keeps the top-k lists.
+    No N x M buffer exists; six counts cross PCIe."""
+    dev = _device()
+    img = _to_device(image_embeds, dev, torch.float32)
+    txt = _to_device(text_embeds, dev, torch.float32)
+    cap = _to_device(caption_embeds, dev, torch.float32)
+    n_cap, n_img, d = cap.shape
+    n_txt = txt.shape[0]
+    if gt is None:
+        gt = prepare_gt(txt2img, img2txt, n_img, n_txt, dev)
+    txt_gt = _single_gt_per_text(gt, n_img, n_txt)
+    if txt_gt is None or n_cap > 7 or d % 8 != 0:
+        return _fused_eval_double_sim_materialized(img, txt, cap, txt2img, img2txt, k, alpha, fusion, return_topk, gt)
+    lib = N.load()
+    fmt = ops.fmt_of(precision)
+    x3 = precision.endswith("x3")
+    G = 2 if n_cap == 1 else (4 if n_cap <= 3 else 8)
+    K = 3 * d if x3 else d
+    dt16 = torch.float16 if fmt == N.FMT_F16 else torch.bfloat16
+    vc = torch.empty((G * n_img, K), dtype=dt16, device=dev)
+    lay_vc = N.LAYOUT_X3_COLS if x3 else N.LAYOUT_HI
+    if not img.is_contiguous():
+        img = img.contiguous()
+    if not cap.is_contiguous():
+        cap = cap.contiguous()
+    st = N.stream_ptr()
+    for m in range(G):  # row G i + m of the interleaved operand: the video, its captions, the last caption again
+        src = img if m == 0 else cap[min(m, n_cap) - 1]
+        N.check(lib.leccr_prep(N.ptr(src), n_img, d, src.stride(0), 0, fmt, lay_vc, vc.data_ptr() + m * K * 2, G * K,
+                               None, None, None, st), "leccr_prep")
+    t16 = ops.prep(txt, fmt, N.LAYOUT_X3_ROWS if x3 else N.LAYOUT_HI, want_stats=False).t16
+    f32, i32 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.int32, device=dev)
+    rank_v, rank_t = torch.empty(n_img, **i32), torch.empty(n_txt, **i32)
+    counts = torch.empty(6, **i32)
+    tv_vc = ti_vc = tv_t = ti_t = None
+    if return_topk:
+        tv_vc, ti_vc = torch.empty((G * n_img, k), **f32), torch.empty((G * n_img, k), **i32)
+        tv_t, ti_t = torch.empty((n_txt, k), **f32), torch.empty((n_txt, k), **i32)
+    ws = torch.empty(lib.leccr_double_sim_topk_workspace(n_img, n_txt, G), dtype=torch.uint8, device=dev)
+    (v_off, v_ids) = gt[0]
+    N.check(lib.leccr_double_sim_topk(N.ptr(vc), N.ptr(t16), n_img, n_txt, K, fmt, G, n_cap, float(alpha),
+                                      float(1.0 - alpha), N.FUSE_NORM if fusion == "norm" else N.FUSE_RAW,
+                                      N.ptr(txt_gt), N.ptr(v_off), N.ptr(v_ids), k, N.ptr(tv_vc), N.ptr(ti_vc), N.ptr(tv_t),
+                                      N.ptr(ti_t), N.ptr(rank_v), N.ptr(rank_t), N.ptr(counts), N.ptr(ws), ws.numel(), st),
+            "leccr_double_sim_topk")
+    host = counts.cpu().tolist()
+    ev = metrics_from_counts(host[0:3], n_img, host[3:6], n_txt)
+    if not return_topk:
+        return ev
+    return ev, {'i2t': (tv_vc[::G], ti_vc[::G]), 't2i': (tv_t, ti_t), 'rank_i2t': rank_v, 'rank_t2i': rank_t}
 
 
 @torch.no_grad()

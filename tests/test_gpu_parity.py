@@ -777,3 +777,40 @@ def test_feature_gallery_equals_the_cast_of_the_concatenation():
             assert op.n == whole.shape[0] and torch.equal(op.t16, want)
     with pytest.raises(N.LeccrError):
         leccr_b200.FeatureGallery(64).append(torch.zeros(3, 32, device="cuda"))
+
+
+@pytest.mark.parametrize("n_vid,per,n_cap,d,fusion,alpha", [(77, 3, 3, 64, "norm", 0.9), (130, 2, 4, 128, "norm", 0.7),
+                                                           (300, 1, 1, 256, "raw", 0.8), (129, 5, 7, 64, "norm", 0.9)])
+def test_double_sim_in_the_epilogue_ragged_shapes_and_caption_counts(n_vid, per, n_cap, d, fusion, alpha):
+    """leccr_double_sim_topk (fusion inside the tensor-core epilogue, no N x M buffer) on ragged shapes, every group
+    size of the interleaved operand (G = 2, 4, 8) and several ground-truth texts per video: Recall dict equal to
+    the oracle's (fused matrices of video_Retrieval_caption_double_sim.py:170-179 ranked by count), ranks equal
+    row by row, top-k lists equal to a sort of the oracle's matrices; and equal to the materialised fallback."""
+    rs = synth.retrieval_set(n_vid, per, d=d, seed=100 + n_vid, n_caption_queries=n_cap)
+    want_i2t, want_t2i = oracle.double_sim_matrices(rs.image, rs.text, rs.caption, alpha=alpha, fusion=fusion)
+    want_t2i = np.ascontiguousarray(want_t2i)
+    want = oracle.itm_eval_by_count(want_i2t, want_t2i, rs.txt2img, rs.img2txt)
+    ev, topk = leccr_b200.fused_eval(rs.image, rs.text, rs.txt2img, rs.img2txt, k=10, caption_embeds=rs.caption,
+                                     alpha=alpha, fusion=fusion)
+    assert "rank_i2t" in topk                      # the epilogue path ran (the fallback has no rank entries)
+    assert_ev_equal(ev, want)
+    gi = [rs.img2txt[i] for i in range(n_vid)]
+    gt = [[rs.txt2img[t]] for t in range(n_vid * per)]
+    assert np.array_equal(topk["rank_i2t"].cpu().numpy(), oracle.ranks_by_count(want_i2t, gi))
+    assert np.array_equal(topk["rank_t2i"].cpu().numpy(), oracle.ranks_by_count(want_t2i, gt))
+    for name, ref in (("i2t", want_i2t), ("t2i", want_t2i)):
+        kk = min(10, ref.shape[1])
+        val, idx = topk[name][0].cpu().numpy()[:, :kk], topk[name][1].cpu().numpy().astype(np.int64)[:, :kk]
+        wv = np.sort(ref, axis=1)[:, ::-1][:, :kk]
+        assert np.abs(val - wv).max() < 2e-5
+        assert np.abs(np.take_along_axis(ref, idx, 1) - wv).max() < 2e-5
+    ev_m = leccr_b200.evaluation._fused_eval_double_sim_materialized(rs.image, rs.text, rs.caption, rs.txt2img, rs.img2txt,
+                                                                     10, alpha, fusion, False, None)
+    assert_ev_equal(ev_m, want)
+    # a text with two ground-truth videos is outside the epilogue path's contract: the materialised path answers
+    t2 = dict(rs.txt2img)
+    i2 = {i: list(v) for i, v in rs.img2txt.items()}
+    i2[1] = i2[1] + [i2[0][0]]
+    ev_f, topk_f = leccr_b200.fused_eval(rs.image, rs.text, t2, i2, k=10, caption_embeds=rs.caption, alpha=alpha, fusion=fusion)
+    assert "rank_i2t" not in topk_f
+    assert_ev_equal(ev_f, oracle.itm_eval_by_count(want_i2t, want_t2i, t2, i2))
