@@ -844,7 +844,8 @@ struct EpiDsStats {
 // A (rows VC, columns texts) exists only for the per-video top-k lists (list rows are VC rows, only rows G i
 // carry data) and is left out when no lists are wanted.  Lists, thresholds, shrink rounds and the write-out
 // are EpiTopK's (two warpgroups, dense).
-template <int G>
+// (the template parameter must not be called G: the non-dependent base has a member G that would hide it)
+template <int GRP>
 struct EpiDsTopK : EpiTopK<16, 64, 2, 1> {
   using Base = EpiTopK<16, 64, 2, 1>;
   struct Params : Base::Params {
@@ -891,24 +892,24 @@ struct EpiDsTopK : EpiTopK<16, 64, 2, 1> {
     const int n_cap = P.n_cap;
     const bool row_ok = c.row < c.n_rows;
     if (c.p != P.b_problem) {
-      // orientation A: lane = VC row; the G lanes of a video combine with shuffles
-      const int m = c.row % G;                       // 0 video, 1..n_cap captions, above: padding
+      // orientation A: lane = VC row; the GRP lanes of a video combine with shuffles
+      const int m = c.row % GRP;                       // 0 video, 1..n_cap captions, above: padding
       const bool head = m == 0 && row_ok;
-      const int base_lane = c.lane & ~(G - 1);
+      const int base_lane = c.lane & ~(GRP - 1);
       for_each_chunk(taddr, col0, n_cols, [&](float(&v)[32], int lcol) {
         float w[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
           float x = (m >= 1 && m <= n_cap) ? v[e] : -CUDART_INF_F;
 #pragma unroll
-          for (int o = 1; o < G; o <<= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+          for (int o = 1; o < GRP; o <<= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
           const float s = __shfl_sync(0xffffffffu, v[e], base_lane);
           w[e] = (head && lcol + e < n_cols) ? st.fuse(s, x) : -CUDART_INF_F;
         }
         Base::dense_chunk(st, w, lcol, my_h8, shared_thr);
       }, BN / 32 / kWGs);
     } else {
-      // orientation B: G adjacent columns = one video
+      // orientation B: GRP adjacent columns = one video
       const int n_groups = P.n_groups;
       const bool ranks = P.txt_best != nullptr;
       for_each_chunk(taddr, col0, n_cols, [&](float(&v)[32], int lcol) {
@@ -916,14 +917,14 @@ struct EpiDsTopK : EpiTopK<16, 64, 2, 1> {
 #pragma unroll
         for (int e = 0; e < 32; ++e) w[e] = -CUDART_INF_F;
 #pragma unroll
-        for (int q = 0; q < 32 / G; ++q) {
-          const float s = v[q * G];
-          float cm = v[q * G + 1];
+        for (int q = 0; q < 32 / GRP; ++q) {
+          const float s = v[q * GRP];
+          float cm = v[q * GRP + 1];
 #pragma unroll
-          for (int k = 2; k < G; ++k)
-            if (k <= n_cap) cm = fmaxf(cm, v[q * G + k]);
+          for (int k = 2; k < GRP; ++k)
+            if (k <= n_cap) cm = fmaxf(cm, v[q * GRP + k]);
           const float f = st.fuse(s, cm);
-          const int grp = lcol / G + q;
+          const int grp = lcol / GRP + q;
           const bool ok = row_ok && grp < n_groups;
           w[q] = ok ? f : -CUDART_INF_F;
           if (ranks && ok) {
@@ -931,7 +932,7 @@ struct EpiDsTopK : EpiTopK<16, 64, 2, 1> {
             if (f > __ldg(P.vid_best + grp)) atomicAdd(P.rank_vid + grp, 1);
           }
         }
-        Base::dense_chunk(st, w, lcol / G, my_h8, shared_thr);   // stored column = video index (+ e)
+        Base::dense_chunk(st, w, lcol / GRP, my_h8, shared_thr);   // stored column = video index (+ e)
       }, BN / 32 / kWGs);
     }
   }
