@@ -36,7 +36,9 @@ class _CaptionInfoNCE(torch.autograd.Function):
         N.check(lib.leccr_caploss_fwd(N.ptr(cap.t16), cap.t16.stride(0), N.ptr(txt.t16), txt.t16.stride(0), n, B, 3 * D,
                                       fmt, N.ptr(temp_dev), N.ptr(out), N.ptr(L), N.ptr(amax), N.ptr(stats), N.ptr(ws),
                                       ws.numel(), N.stream_ptr()), "leccr_caploss_fwd")
-        # |x| > 65504 cannot be an fp16 operand: same loud failure as the evaluation path
+        # |x| > 65504 cannot be an fp16 operand: the cast then yields inf and the loss comes out inf / NaN (as under
+        # fp16 autocast), it is never a plausible wrong number.  No flag is read back here -- that would cost a host
+        # sync per training step; un-normalised inputs of that size want precision="bf16" (fp32 range).
         ctx.save_for_backward(cap.t16, txt.t16, temp_dev, out, L, amax, stats, cap.stats, txt.stats)
         ctx.meta = (n, B, D, fmt)
         return out[0].clone()

@@ -54,6 +54,24 @@ def _pick_windows(row_blocks: int, part_rows: int, sms: int = 148):
     return best[1], best[2]
 
 
+def _window_bounds(part_rows: int, windows: int):
+    """Row ranges of the gallery windows of the host path.  Only the FIRST window's upload is exposed (the others
+    cross PCIe while the tensor cores rank the window before), and a pass over a window takes several times
+    longer than its upload, so the windows grow geometrically: 1 : 2 : 4 ... -- the first one is 1 / (2^W - 1)
+    of the part instead of 1 / W.  Boundaries are multiples of 256 rows (whole column tiles)."""
+    if windows <= 1:
+        return [(0, part_rows)]
+    total = (1 << windows) - 1
+    bounds, b, acc = [], 0, 0
+    for w in range(windows):
+        acc += 1 << w
+        e = part_rows if w == windows - 1 else min(part_rows, (part_rows * acc // total + 255) // 256 * 256)
+        if e > b:
+            bounds.append((b, e))
+        b = max(b, e)
+    return bounds
+
+
 class GallerySearchPlan:
     """Static buffers + the launch sequence of one search shape.
 
@@ -151,9 +169,7 @@ class GallerySearchPlan:
             if W < 1 or W > 8:
                 raise N.LeccrError("1 to 8 gallery windows")
         self.subs = subs
-        step = -(-self.Gp // W)
-        step = (step + 255) // 256 * 256
-        self.bounds = [(b, min(self.Gp, b + step)) for b in range(0, self.Gp, step)]
+        self.bounds = _window_bounds(self.Gp, W)
         W = len(self.bounds)
         self.ws_stream = torch.empty(lib.leccr_sim_topk_stream_workspace(self.Qs, W * subs), dtype=torch.uint8, device=dev)
         self.stream_calls = []

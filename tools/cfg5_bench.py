@@ -21,6 +21,7 @@ import torch
 import torch.distributed as dist
 
 from leccr_b200 import ops, peer, sharding, synth
+from bench import ClockSampler
 
 
 def main():
@@ -80,6 +81,8 @@ def main():
 
     Qop, Gop = ops.prep(qry, want_stats=False), ops.prep(gal, want_stats=False)
     results = []
+    sampler = ClockSampler(local)
+    sampler.start()
     # ---- query sharding: my slice of the queries against the whole gallery
     qb, qe = sharding.shard_range(Q, rank, world)
     Qs = Qop.rows(qb, qe)
@@ -123,6 +126,7 @@ def main():
             mv, mi, (mb, me) = out2
             same = check(mv, mi, qb2 + mb, qb2 + me, "2d")
             results.append((f"query x gallery ({world // P} x {P})", ms, same))
+    clocks = sampler.stop()
     if rank == 0:
         for name, ms, same in results:
             print(json.dumps({
@@ -131,7 +135,7 @@ def main():
                 "frac_of_peak": flops / ms / 1e9 / (peak * world), "peak_tflops_per_gpu": peak,
                 # launches of tens of milliseconds run at sustained clocks: the back-to-back cuBLAS figure
                 "frac_of_sustained_peak": flops / ms / 1e9 / (peak_sus * world), "sustained_peak_tflops_per_gpu": peak_sus,
-                "sampled_rows_identical_to_fp32_topk": same, "timing": "CUDA events, best of reps, max over ranks",
+                "sampled_rows_identical_to_fp32_topk": same, "clocks": clocks, "timing": "CUDA events, best of reps, max over ranks",
                 "peer_memory": None if name == "query" else any(kk[0] == "topk" and v is not None for kk, v in peer._cache.items())}))
     if world > 1:
         dist.destroy_process_group()
