@@ -169,7 +169,7 @@ sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typ
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t item_n = 0;
@@ -201,7 +201,7 @@ sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typ
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t idesc = make_idesc_f16(L.fmt, BM, BN);
       int stage = 0;
       uint32_t phase = 0;
