@@ -272,3 +272,40 @@ def test_caption_vision_projection_gradients_two_ranks_gloo():
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+def test_gallery_plan_layout_helpers():
+    """Pure host logic of GallerySearchPlan: window bounds tile the gallery part in whole 256-row column tiles and
+    grow geometrically; the (windows, slots) choice respects the 8 list slots per query row; shard ranges tile."""
+    from leccr_b200.gallery import _pick_windows, _window_bounds
+    from leccr_b200.sharding import shard_range
+
+    for part, w in ((1_000_000, 4), (500_000, 2), (500_000, 3), (70_000, 2), (300, 2), (257, 8), (1, 1)):
+        b = _window_bounds(part, w)
+        assert b[0][0] == 0 and b[-1][1] == part and len(b) <= w
+        assert all(e0 == b1 for (_, e0), (b1, _) in zip(b[:-1], b[1:]))          # contiguous, no overlap
+        assert all(e > s for s, e in b) and all(s % 256 == 0 for s, _ in b)      # whole column tiles
+        if len(b) > 2:
+            sizes = [e - s for s, e in b]
+            assert sizes == sorted(sizes)                                         # only the first upload is exposed
+    for rb, part in ((782, 1_000_000), (391, 500_000), (196, 500_000), (3, 70_000), (1, 1000)):
+        w, s = _pick_windows(rb, part)
+        assert 1 <= w and 1 <= s and w * s <= 8
+        assert w == 1 or part // w >= 32768
+    for n, world in ((100_000, 8), (1_000_003, 8), (5, 8), (7, 2)):
+        spans = [shard_range(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+        assert max(e - s for s, e in spans) - min(e - s for s, e in spans) <= 1
+
+
+def test_new_entries_fail_loudly_without_a_gpu():
+    import leccr_b200
+    from leccr_b200 import _native as N
+
+    with pytest.raises(N.LeccrError):
+        leccr_b200.GallerySearchPlan(1000, 10, 64)
+    with pytest.raises(N.LeccrError):
+        leccr_b200.normalize_rows(torch.randn(4, 8))
+    with pytest.raises(N.LeccrError):
+        leccr_b200.FeatureGallery(64)
