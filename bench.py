@@ -204,6 +204,10 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
         return bool(t.item())
 
+    # ---- host side of the e2e path: this rank's pinned staging memory on its GPU's NUMA node
+    from leccr_b200 import peer as _peer
+
+    numa_bound = _peer.bind_host_thread_to_device(local_rank) if world > 1 else False
     # ---- data: every rank generates the same seeded workload on its GPU; host copies are pinned
     gal, qry, gt = synth.cfg5_gallery(N_GALLERY, N_QUERY, device=dev)
     gal_h = torch.empty(gal.shape, dtype=gal.dtype).pin_memory()
@@ -304,7 +308,7 @@ def run_ours(args, rank, world, local_rank):
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(plan.d2h_bytes),
                 "ms_per_step": ms_e2e / steps, "wall_ms_per_step": wall_e2e / steps,
                 "api": "leccr_b200.GallerySearchPlan.search_host(pinned host bf16 gallery, queries)",
-                "bytes_are": "per rank (max over ranks)"},
+                "bytes_are": "per rank (max over ranks)", "host_thread_bound_to_gpu_numa_node": numa_bound},
         "gpu_launches": plan.launches_per_search * steps,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "sim_gemm_kernel<EpiTopK<16,31,2>, kARes> (filter epilogue)",

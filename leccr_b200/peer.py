@@ -24,6 +24,23 @@ _cache = {}
 _warned = False
 
 
+def bind_host_thread_to_device(device_index: int) -> bool:
+    """Pin the calling thread to the CPUs next to GPU `device_index` (NVML's ideal affinity), so that host memory it
+    allocates and first touches afterwards -- the pinned staging buffers of the host paths -- lands on the GPU's
+    NUMA node.  torchrun does not place its ranks; with eight ranks streaming pinned memory at once, buffers that
+    all sit on one socket share its memory controllers and the inter-socket link.  Returns False when NVML or the
+    container's cpuset does not allow it (nothing changes then)."""
+    try:
+        import pynvml as nv
+
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(int(device_index))
+        nv.nvmlDeviceSetCpuAffinity(h)
+        return True
+    except Exception:
+        return False
+
+
 def available(device) -> bool:
     """Peer exchange is used for NCCL process groups of CUDA ranks on one node."""
     if _DISABLED or not (dist.is_available() and dist.is_initialized()):
