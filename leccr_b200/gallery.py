@@ -9,7 +9,8 @@ Layout (north_star): the QUERY set is sharded over S = world / P groups of ranks
 into P parts inside each group.  Rank r = (shard r // P, part r % P) ranks its query shard against its gallery
 part with the fused tensor-core pass (the Q x G scores never reach HBM), finalize writes the local [Qs, k]
 lists straight into a peer-mapped buffer, ONE cross-rank barrier, and `leccr_topk_merge_peers` pulls the P
-partial lists of this rank's slice of the shard over NVLink while merging them.  P = 1 is pure query sharding
+partial lists of this rank's slice of the shard over NVLink while merging them (without peer memory: an NCCL
+all-gather of the lists inside the shard's sub-group, merged by the same kernel).  P = 1 is pure query sharding
 (no exchange); world = 1 is the single-GPU search.
 
 Two entries:
@@ -129,19 +130,28 @@ class GallerySearchPlan:
         f32, i32 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.int32, device=dev)
         # local lists: a private pair when there is nothing to merge, else the two slots of a peer-mapped buffer
         self.pb = None
+        self.nccl_group = None
         if P > 1:
-            if not peer.available(dev):
-                raise N.LeccrError("a partitioned gallery needs the NCCL process group of one NVLink node")
-            qs_max = -(-n_query // self.S)
-            self.pb = peer.get_buffer(("gallery_search", n_query, self.S, k), qs_max * k * 8, dev)
-            if self.pb is None:
-                raise N.LeccrError("peer-mapped memory is not available on this system")
-            self.local = []
-            for slot in range(2):
-                off = self.pb.slot_offset(slot)
-                self.local.append((self.pb.local(off, (self.Qs, k), torch.float32),
-                                   self.pb.local(off + self.Qs * k * 4, (self.Qs, k), torch.int32), off))
+            if not (dist.is_available() and dist.is_initialized()):
+                raise N.LeccrError("a partitioned gallery needs an initialised torch.distributed process group")
+            if peer.available(dev):
+                qs_max = -(-n_query // self.S)
+                self.pb = peer.get_buffer(("gallery_search", n_query, self.S, k), qs_max * k * 8, dev)
             self.group = [self.shard * P + i for i in range(P)]
+            if self.pb is not None:
+                self.local = []
+                for slot in range(2):
+                    off = self.pb.slot_offset(slot)
+                    self.local.append((self.pb.local(off, (self.Qs, k), torch.float32),
+                                       self.pb.local(off + self.Qs * k * 4, (self.Qs, k), torch.int32), off))
+            else:
+                # no peer memory (LECCR_PEER=0, several nodes): the P lists of a shard are all-gathered with NCCL
+                # inside the shard's sub-group and merged by the same kernel over the gathered buffer
+                groups = [dist.new_group(ranks=[sh * P + i for i in range(P)]) for sh in range(self.S)]
+                self.nccl_group = groups[self.shard]
+                self.local = [(torch.empty((self.Qs, k), **f32), torch.empty((self.Qs, k), **i32), 0)]
+                self.gath_val = torch.empty((P, self.Qs, k), **f32)
+                self.gath_idx = torch.empty((P, self.Qs, k), **i32)
             self.part_offsets = (ctypes.c_int64 * P)(*[shard_range(n_gallery, i, P)[0] for i in range(P)])
             mb, me = shard_range(self.Qs, self.part, P)
             self.merge_rows = (mb, me)
@@ -216,14 +226,22 @@ class GallerySearchPlan:
                 self.endb.barrier()
             return
         pb = self.pb
-        pb.barrier()
-        off = self.local[slot][2]
         tabs = self._tabs.get(slot)
-        if tabs is None:
-            tabs = (torch.tensor([pb.ptrs[r] + off for r in self.group], dtype=torch.int64, device=self.dev),
-                    torch.tensor([pb.ptrs[r] + off + self.Qs * self.k * 4 for r in self.group], dtype=torch.int64,
-                                 device=self.dev))
-            self._tabs[slot] = tabs
+        if pb is None:
+            dist.all_gather_into_tensor(self.gath_val, self.local[0][0], group=self.nccl_group)
+            dist.all_gather_into_tensor(self.gath_idx, self.local[0][1], group=self.nccl_group)
+            if tabs is None:
+                tabs = (torch.tensor([self.gath_val[i].data_ptr() for i in range(self.P)], dtype=torch.int64, device=self.dev),
+                        torch.tensor([self.gath_idx[i].data_ptr() for i in range(self.P)], dtype=torch.int64, device=self.dev))
+                self._tabs[slot] = tabs
+        else:
+            pb.barrier()
+            off = self.local[slot][2]
+            if tabs is None:
+                tabs = (torch.tensor([pb.ptrs[r] + off for r in self.group], dtype=torch.int64, device=self.dev),
+                        torch.tensor([pb.ptrs[r] + off + self.Qs * self.k * 4 for r in self.group], dtype=torch.int64,
+                                     device=self.dev))
+                self._tabs[slot] = tabs
         mb, me = self.merge_rows
         N.check(self.lib.leccr_topk_merge_peers(N.ptr(tabs[0]), N.ptr(tabs[1]), self.P, self.k, mb, me - mb,
                                                 self.part_offsets, self.k, N.ptr(self.out_val), N.ptr(self.out_idx),
