@@ -549,7 +549,30 @@ def extras_single_gpu(torch, leccr_b200, ops, synth, lib, dev, peak):
                                 "frac": flops / (gemm_ms * 1e-3) / 1e12 / peak, "kernel_ms": gemm_ms,
                                 "flops_per_launch": flops, "traffic": traffic_from_profile("dram_bytes_per_launch")},
                    "recall_check": {k: ev[k] for k in ("txt_r1", "txt_r5", "txt_r10", "img_r1", "img_r5", "img_r10")}}
-    del plan, splan, flush
+    # the same evaluation when only the Recall dict is wanted (all the reference's itm_eval returns): counting
+    # epilogue, no candidate lists (leccr_sim_rank)
+    rplan = leccr_b200.FusedEvalPlan(n_img, n_txt, DIM, k=TOPK, gt=gt, lists=False)
+    rplan.img.copy_(img_d)
+    rplan.txt.copy_(txt_d)
+    assert rplan.run(img_h, txt_h) == ev_eager, "cfg2: Recall-only path disagrees"
+    ms_rank = timed(rplan.launch, 20)
+    lib.leccr_profile_enable(1)
+    for _ in range(10):
+        flush.zero_()
+        I, T = ops.prep(img_d), ops.prep(txt_d)
+        ops.sim_rank([(I, T, gt[0]), (T, I, gt[1])])
+    torch.cuda.synchronize()
+    lib.leccr_profile_read(ctypes.byref(tot), ctypes.byref(cnt))
+    lib.leccr_profile_enable(0)
+    rank_ms = tot.value / max(1, cnt.value)
+    out["cfg2_recall_only"] = {"workload": "mscoco5k_eval_5000img_x_25000txt_d256_i2t+t2i_recall (no top-k lists: what itm_eval returns)",
+                               "value_queries_per_s": q / (ms_rank * 1e-3), "ms_per_step": ms_rank,
+                               "roofline": {"bound": "tensor", "kernel": "sim_gemm_kernel<EpiRank> (both directions, one launch)",
+                                            "achieved": flops / (rank_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                                            "frac": flops / (rank_ms * 1e-3) / 1e12 / peak, "kernel_ms": rank_ms,
+                                            "flops_per_launch": flops},
+                               "recall_check": "equal to cfg2.recall_check (asserted)"}
+    del plan, splan, rplan, flush
     # ---- cfg1 / cfg4: microseconds per evaluation through the public API, inputs resident in HBM
     def us_per_call(fn, reps=30):
         for _ in range(5):

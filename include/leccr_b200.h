@@ -147,6 +147,18 @@ int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
                    int tiles_per_chunk /* 0 = auto */, void* workspace, size_t workspace_bytes,
                    leccr_stream_t stream);
 
+/* leccr_sim_rank: Recall evaluation WITHOUT candidate lists -- exactly what the reference's itm_eval returns
+ * (image_Retrieval_caption.py:261-317: the position of each row's best ground-truth column, Recall@1/5/10; no
+ * top-k list leaves that function).  Same problem description as leccr_sim_topk (gt_off .. gt_score required,
+ * topk_val / topk_idx ignored).  The best ground-truth score of every row is computed exactly first; the
+ * tensor-core pass only COUNTS the scores that are definitely greater (16-bit-operand score > t + eps) and writes
+ * the rare (row, column) pairs inside the band t +- eps, which are re-scored exactly afterwards; a row whose pairs
+ * overflow takes the exact fallback.  rank[row] = exact number of columns scoring above the row's best ground
+ * truth (LECCR_RANK_CAP for rows without one); recall_counts += #{rank < 1, 5, 10}. */
+size_t leccr_sim_rank_workspace(const leccr_topk_problem* probs, int n_prob);
+int leccr_sim_rank(const leccr_topk_problem* probs, int n_prob, int D, int fmt, void* workspace, size_t workspace_bytes,
+                   leccr_stream_t stream);
+
 /* Streamed evaluation: the columns of a problem arrive in windows (e.g. while the rest of the gallery is
  * still crossing PCIe).  Each call may run the tensor-core phase over ONE window (cols16 / n_cols describe
  * the window, col_begin its global position; the candidates go to list slots [sub_begin, sub_begin +

@@ -99,6 +99,8 @@ _SIGNATURES = {
     "leccr_stats16": (c_int, [vp, c_int, i64, c_int, i64, vp, vp, vp, vp]),
     "leccr_transpose16": (c_int, [vp, i64, c_int, i64, vp, i64, vp]),
     "leccr_sim_f32": (c_int, [vp, i64, vp, i64, i64, i64, c_int, c_int, vp, i64, c_float, vp, vp]),
+    "leccr_sim_rank_workspace": (sz, [ctypes.POINTER(TopkProblem), c_int]),
+    "leccr_sim_rank": (c_int, [ctypes.POINTER(TopkProblem), c_int, c_int, c_int, vp, sz, vp]),
     "leccr_sim_topk_workspace": (sz, [ctypes.POINTER(TopkProblem), c_int, c_int]),
     "leccr_sim_topk": (c_int, [ctypes.POINTER(TopkProblem), c_int, c_int, c_int, c_int, c_int, vp, sz, vp]),
     "leccr_infonce_fwd_workspace": (sz, [i64, c_int]),

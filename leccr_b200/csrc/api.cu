@@ -863,6 +863,140 @@ int leccr_sim_topk_stream(const leccr_topk_problem* probs, const leccr_topk_stre
   return topk_core(probs, streams, plans, n_prob, D, fmt, k, two ? 1 : 0, stream);
 }
 
+// ------------------------------------------------------------------------------------ Recall only (EpiRank)
+// Similarity + exact ranks of the ground truth + Recall@1/5/10 with NO candidate lists: what itm_eval returns.
+static size_t rank_ws_bytes(int64_t n_rows) {
+  const size_t cap = std::max<size_t>(4096, static_cast<size_t>(n_rows) * 8);
+  return 3 * align256(static_cast<size_t>(n_rows) * 4) /* best, lo, hi */ + align256(static_cast<size_t>(n_rows) * 4) /* row_flag */ +
+         align256(static_cast<size_t>(n_rows) * 4 + 16) /* flag count + list */ + 256 /* pair count */ + align256(cap * 8);
+}
+
+size_t leccr_sim_rank_workspace(const leccr_topk_problem* probs, int n_prob) {
+  if (probs == nullptr || n_prob < 1 || n_prob > 2) return 0;
+  size_t b = 0;
+  for (int p = 0; p < n_prob; ++p) b += rank_ws_bytes(probs[p].n_rows);
+  return b;
+}
+
+int leccr_sim_rank(const leccr_topk_problem* probs, int n_prob, int D, int fmt, void* workspace, size_t workspace_bytes,
+                   leccr_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (probs == nullptr || n_prob < 1 || n_prob > 2 || D <= 0 || bad_fmt(fmt)) return LECCR_ERR_ARG;
+  for (int p = 0; p < n_prob; ++p) {
+    const leccr_topk_problem& q = probs[p];
+    if (q.rows16 == nullptr || q.cols16 == nullptr || q.n_rows <= 0 || q.n_cols <= 0 || q.gt_off == nullptr ||
+        q.gt_ids == nullptr || q.rows_x == nullptr || q.cols_x == nullptr || q.rn_hi == nullptr || q.rn_lo == nullptr ||
+        q.col_stats == nullptr || q.rank == nullptr || q.x_dtype < 0 || q.x_dtype > 2)
+      return LECCR_ERR_ARG;
+  }
+  int rc = leccr_check_device();
+  if (rc != LECCR_OK) return rc;
+  if (workspace == nullptr || workspace_bytes < leccr_sim_rank_workspace(probs, n_prob)) return LECCR_ERR_WORKSPACE;
+  // work decomposition: ~6 equally long items per SM over both problems (counts are accumulated atomically, so a
+  // row may be split into any number of column chunks)
+  int64_t total_tiles = 0;
+  for (int p = 0; p < n_prob; ++p)
+    total_tiles += ((probs[p].n_rows + BM - 1) / BM) * ((probs[p].n_cols + BN - 1) / BN);
+  const int tpc = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(total_tiles / (6LL * num_sms()), 64)));
+  SimLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.n_prob = n_prob;
+  L.fmt = fmt;
+  L.k_chunks = (D + BK - 1) / BK;
+  EpiRank::Params EP;
+  memset(&EP, 0, sizeof(EP));
+  TopkFinalizeParams post[2];
+  memset(post, 0, sizeof(post));
+  float* best[2];
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  int item_base = 0;
+  for (int p = 0; p < n_prob; ++p) {
+    const leccr_topk_problem& q = probs[p];
+    const size_t nb = align256(static_cast<size_t>(q.n_rows) * 4);
+    const int cap = static_cast<int>(std::max<size_t>(4096, static_cast<size_t>(q.n_rows) * 8));
+    best[p] = reinterpret_cast<float*>(ws);
+    float* lo = reinterpret_cast<float*>(ws + nb);
+    float* hi = reinterpret_cast<float*>(ws + 2 * nb);
+    ws += 3 * nb;
+    int* row_flag = reinterpret_cast<int*>(ws);
+    ws += nb;
+    int* flag = reinterpret_cast<int*>(ws);
+    ws += align256(static_cast<size_t>(q.n_rows) * 4 + 16);
+    int* amb_count = reinterpret_cast<int*>(ws);
+    ws += 256;
+    int2* amb_list = reinterpret_cast<int2*>(ws);
+    ws += align256(static_cast<size_t>(cap) * 8);
+    CUDA_TRY(cudaMemsetAsync(row_flag, 0, nb + 16 /* row flags, then the flag count + barrier word */, stream));
+    CUDA_TRY(cudaMemsetAsync(amb_count, 0, 4, stream));
+    GtBestParams G;
+    G.gt_off = q.gt_off;
+    G.gt_ids = q.gt_ids;
+    G.rows_x = q.rows_x;
+    G.cols_x = q.cols_x;
+    G.ld_rows = q.ld_rows_x;
+    G.ld_cols = q.ld_cols_x;
+    G.D = D;
+    G.x_dtype = q.x_dtype;
+    G.n_rows = static_cast<int>(q.n_rows);
+    G.rn_hi = q.rn_hi;
+    G.rn_lo = q.rn_lo;
+    G.col_stats = q.col_stats;
+    G.acc_slack = 2.0f * 1.1920929e-7f * static_cast<float>(D);
+    G.best = best[p];
+    G.lo = lo;
+    G.hi = hi;
+    G.gt_score = q.gt_score;
+    G.rank = q.rank;
+    gt_best_kernel<<<static_cast<unsigned>((q.n_rows + 7) / 8), 256, 0, stream>>>(G);
+    LAUNCH_CHECK("gt_best_kernel");
+    const Plan pl = plan_problem(q.n_cols, 0, q.n_rows, tpc);
+    rc = fill_problem(L.prob[p], q.rows16, q.ld_rows16, q.cols16, q.ld_cols16, q.n_rows, q.n_cols, D, fmt, pl, item_base);
+    if (rc != LECCR_OK) return rc;
+    item_base += pl.row_blocks * pl.n_chunks;
+    EP.lo[p] = lo;
+    EP.hi[p] = hi;
+    EP.rank[p] = q.rank;
+    EP.amb_count[p] = amb_count;
+    EP.amb_list[p] = amb_list;
+    EP.amb_cap[p] = cap;
+    EP.row_flag[p] = row_flag;
+    EP.flag_count[p] = flag;
+    EP.flag_list[p] = flag + 4;
+    TopkFinalizeParams& F = post[p];
+    F.n_rows = static_cast<int>(q.n_rows);
+    F.n_cols = static_cast<int>(q.n_cols);
+    F.gt_off = q.gt_off;
+    F.gt_ids = q.gt_ids;
+    F.rows_x = q.rows_x;
+    F.cols_x = q.cols_x;
+    F.ld_rows = q.ld_rows_x;
+    F.ld_cols = q.ld_cols_x;
+    F.D = D;
+    F.x_dtype = q.x_dtype;
+    F.rank = q.rank;
+    F.flag_count = flag;
+    F.flag_list = flag + 4;
+    F.gt_score = nullptr;
+  }
+  L.n_items = item_base;
+  if (L.k_chunks <= kAResChunks) rc = launch_gemm<EpiRank, BK, true>(L, EP, stream);
+  else rc = launch_gemm<EpiRank>(L, EP, stream);
+  if (rc != LECCR_OK) return rc;
+  for (int p = 0; p < n_prob; ++p) {
+    const leccr_topk_problem& q = probs[p];
+    rank_resolve_kernel<<<static_cast<unsigned>(num_sms()), 256, 0, stream>>>(
+        EP.amb_list[p], EP.amb_count[p], EP.amb_cap[p], q.rows_x, q.ld_rows_x, q.cols_x, q.ld_cols_x, D, q.x_dtype, best[p],
+        q.rank);
+    LAUNCH_CHECK("rank_resolve_kernel");
+  }
+  if (n_prob == 1) memset(&post[1], 0, sizeof(post[1]));
+  dim3 g(static_cast<unsigned>(num_sms()), static_cast<unsigned>(n_prob));
+  rank_post_kernel<<<g, 256, 0, stream>>>(post[0], post[1], probs[0].recall_counts,
+                                          n_prob > 1 ? probs[1].recall_counts : nullptr);
+  LAUNCH_CHECK("rank_post_kernel");
+  return LECCR_OK;
+}
+
 // ------------------------------------------------------------------------------------ double_sim, fused
 // Two tensor-core passes over the interleaved video/caption operand (EpiDsStats, EpiDsTopK); no N x M buffer.
 // Problem order of the plans: [0] orientation A (rows VC, columns texts), [1] orientation B.

@@ -943,4 +943,82 @@ struct EpiDsTopK : EpiTopK<16, 64, 2, 1> {
   }
 };
 
+// ------------------------------------------------------------------------------------------
+// EpiRank: Recall@K without candidate lists -- what the reference's itm_eval actually returns
+// (image_Retrieval_caption.py:261-317: per row the position of its best ground-truth column, then
+// Recall@1/5/10; no top-k list leaves that function).  The row's best ground-truth score t is known EXACTLY
+// before the pass (fp32 dots of the original inputs, gt_best_kernel), with the rigorous bound eps on the error of
+// a 16-bit-operand score.  Per element the epilogue only counts: s > t + eps is definitely greater, s <= t - eps
+// definitely not; the rare scores inside the band are written as (row, column) pairs and re-scored exactly
+// afterwards (rank_resolve_kernel).  ~4 ALU instructions per element, no shared memory, no per-element store --
+// the short-row evaluations (cfg1 / cfg2), which the list epilogue runs at a third of the tensor peak, run at the
+// mainloop's pace.  Both warpgroups drain every tile (half its columns each).
+// ------------------------------------------------------------------------------------------
+struct EpiRank {
+  struct Params {
+    const float* lo[2];     // [n_rows] t - eps   (+inf: the row has no ground truth)
+    const float* hi[2];     // [n_rows] t + eps
+    int* rank[2];           // [n_rows] += number of definitely greater scores
+    int* amb_count[2];      // pairs written so far
+    int2* amb_list[2];      // (row, column) pairs inside the band
+    int amb_cap[2];
+    int* row_flag[2];       // [n_rows] 0/1: the pair list overflowed for this row -> exact fallback
+    int* flag_count[2];
+    int* flag_list[2];
+  };
+  static constexpr int kWGs = 2;
+  static constexpr bool kSplitCols = true;
+  static constexpr int kSmemBytes = 16;
+  struct State {
+    float lo, hi;
+    int above;
+  };
+  __device__ static void begin(State& st, const Params& P, const ItemCtx& c) {
+    const bool ok = c.row < c.n_rows;
+    st.lo = ok ? __ldg(P.lo[c.p] + c.row) : CUDART_INF_F;
+    st.hi = ok ? __ldg(P.hi[c.p] + c.row) : CUDART_INF_F;
+    st.above = 0;
+  }
+  __device__ static void prefetch(State&, const Params&, const ItemCtx&) {}
+  __device__ __noinline__ static void push_band(const Params& P, int p, int row, int col) {
+    const int slot = atomicAdd(P.amb_count[p], 1);
+    if (slot < P.amb_cap[p]) {
+      P.amb_list[p][slot] = make_int2(row, col);
+    } else if (atomicExch(P.row_flag[p] + row, 1) == 0) {
+      P.flag_list[p][atomicAdd(P.flag_count[p], 1)] = row;
+    }
+  }
+  __device__ static void tile(State& st, const Params& P, const ItemCtx& c, uint32_t taddr, int col0) {
+    const int n_cols = c.n_cols;
+    const float lo = st.lo, hi = st.hi;
+    for_each_chunk(taddr, col0, n_cols, [&](float(&v)[32], int lcol) {
+      if (lcol + 32 > n_cols) {  // ragged last columns (TMA zero-filled): exclude them
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (lcol + e >= n_cols) v[e] = -CUDART_INF_F;
+      }
+      int chi[4] = {0, 0, 0, 0}, clo[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        chi[e & 3] += v[e] > hi ? 1 : 0;
+        clo[e & 3] += v[e] > lo ? 1 : 0;
+      }
+      const int nhi = (chi[0] + chi[1]) + (chi[2] + chi[3]);
+      const int nlo = (clo[0] + clo[1]) + (clo[2] + clo[3]);
+      st.above += nhi;
+      if (__any_sync(0xffffffffu, nlo != nhi)) {  // rare: some score of the warp's 32 x 32 block sits inside a band
+        if (nlo != nhi) {
+#pragma unroll  // static register indices (a dynamic index would move v[] to local memory)
+          for (int e = 0; e < 32; ++e)
+            if (v[e] > lo && !(v[e] > hi)) push_band(P, c.p, c.row, lcol + e);
+        }
+        __syncwarp();
+      }
+    }, BN / 32 / kWGs);
+  }
+  __device__ static void end(State& st, const Params& P, const ItemCtx& c) {
+    if (st.above > 0 && c.row < c.n_rows) atomicAdd(P.rank[c.p] + c.row, st.above);
+  }
+};
+
 }  // namespace leccr

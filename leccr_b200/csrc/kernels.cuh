@@ -942,6 +942,77 @@ __device__ __forceinline__ void topk_finalize_body(const TopkFinalizeParams& P, 
   }
 }
 
+// --------------------------------------------------------------------------------
+// Recall-only evaluation (EpiRank): before the tensor-core pass, one warp per row computes the EXACT score of every
+// ground-truth column of the row (fp32 dots of the original inputs), keeps the best one t and the row's rigorous
+// bound eps on |16-bit-operand score - exact score| (the one topk_finalize uses), and publishes the band
+// (t - eps, t + eps].  Rows without ground truth get rank kRankCap and an empty band.  After the pass,
+// rank_resolve re-scores the (row, column) pairs that fell inside a band exactly: one warp per pair.
+// --------------------------------------------------------------------------------
+struct GtBestParams {
+  const int* gt_off;
+  const int* gt_ids;
+  const void* rows_x;
+  const void* cols_x;
+  long long ld_rows, ld_cols;
+  int D, x_dtype, n_rows;
+  const float* rn_hi;
+  const float* rn_lo;
+  const float* col_stats;
+  float acc_slack;
+  float* best;      // [n_rows] exact best ground-truth score
+  float* lo;        // [n_rows]
+  float* hi;        // [n_rows]
+  float* gt_score;  // [nnz] or null
+  int* rank;        // [n_rows] initialised here: 0, or kRankCap for rows without ground truth
+};
+
+__global__ void gt_best_kernel(const GtBestParams P) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= P.n_rows) return;
+  const int g0 = P.gt_off[row], g1 = P.gt_off[row + 1];
+  const bool fast = vec_ok(P.rows_x, P.ld_rows, P.D, P.x_dtype) && vec_ok(P.cols_x, P.ld_cols, P.D, P.x_dtype);
+  RowRegs qrow;
+  if (fast) load_row_regs(qrow, P.rows_x, P.ld_rows, row, P.D, lane);
+  float best = -CUDART_INF_F;
+  for (int gi = g0; gi < g1; ++gi) {
+    const int g = P.gt_ids[gi];
+    float tg;
+    if (fast) {
+      RowRegs crow;
+      load_row_regs(crow, P.cols_x, P.ld_cols, g, P.D, lane);
+      tg = dot_row_regs(qrow, crow);
+    } else {
+      tg = warp_dot(P.rows_x, P.ld_rows, row, P.cols_x, P.ld_cols, g, P.D, P.x_dtype, lane);
+    }
+    if (P.gt_score != nullptr && lane == 0) P.gt_score[gi] = tg;
+    best = fmaxf(best, tg);
+  }
+  if (lane == 0) {
+    const float ch = P.col_stats[0], cl = P.col_stats[1];
+    const float rh = P.rn_hi[row], rl = P.rn_lo[row];
+    const float eps = rl * ch + rh * cl + rl * cl + P.acc_slack * rh * ch;
+    const bool has = g1 > g0;
+    P.best[row] = has ? best : CUDART_INF_F;
+    P.lo[row] = has ? best - eps : CUDART_INF_F;
+    P.hi[row] = has ? best + eps : CUDART_INF_F;
+    P.rank[row] = has ? 0 : kRankCap;
+  }
+}
+
+__global__ void rank_resolve_kernel(const int2* __restrict__ pairs, const int* __restrict__ n_pairs, int cap,
+                                    const void* rows_x, long long ld_rows, const void* cols_x, long long ld_cols, int D,
+                                    int x_dtype, const float* __restrict__ best, int* __restrict__ rank) {
+  const int lane = threadIdx.x & 31;
+  const int n = min(*n_pairs, cap);
+  for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += gridDim.x * (blockDim.x >> 5)) {
+    const int2 pr = pairs[i];
+    const float tj = warp_dot(rows_x, ld_rows, pr.x, cols_x, ld_cols, pr.y, D, x_dtype, lane);
+    if (lane == 0 && tj > best[pr.x]) atomicAdd(rank + pr.x, 1);
+  }
+}
+
 template <int SLOTS>
 __global__ void __launch_bounds__(kFinalizeWarps * 32) topk_finalize_kernel(const TopkFinalizeParams P) {
   __shared__ float s_val[kFinalizeWarps][32];

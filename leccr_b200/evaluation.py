@@ -442,7 +442,10 @@ def fused_eval(image_embeds, text_embeds, txt2img=None, img2txt=None, k=10, prec
     I, T = ops.prep(img, fmt), ops.prep(txt, fmt)
     if gt is None:
         gt = prepare_gt(txt2img, img2txt, img.shape[0], txt.shape[0], dev)
-    r_i, r_t = ops.sim_topk([(I, T, gt[0]), (T, I, gt[1])], k=k, tiles_per_chunk=tiles_per_chunk)
+    if return_topk:
+        r_i, r_t = ops.sim_topk([(I, T, gt[0]), (T, I, gt[1])], k=k, tiles_per_chunk=tiles_per_chunk)
+    else:  # Recall only (all itm_eval returns): counting epilogue, no candidate lists (leccr_sim_rank)
+        r_i, r_t = ops.sim_rank([(I, T, gt[0]), (T, I, gt[1])])
     # the step's single D2H read: 6 Recall counts + the two operand range flags (32 bytes)
     host = torch.cat([r_i.recall_counts.float(), r_t.recall_counts.float(), I.stats[3:4], T.stats[3:4]]).cpu().tolist()
     if host[6] != 0.0 or host[7] != 0.0:
@@ -466,9 +469,12 @@ class FusedEvalPlan:
     """
 
     def __init__(self, n_img, n_txt, dim, txt2img=None, img2txt=None, k=10, precision="f16", gt=None,
-                 tiles_per_chunk=0):
+                 tiles_per_chunk=0, lists=True):
+        """lists=False: Recall only -- the counting epilogue (leccr_sim_rank) instead of the list epilogue; `run`
+        then has no top-k to return.  That is all the reference's evaluation computes (itm_eval)."""
         self.dev = dev = _device()
         self.lib = lib = N.load()
+        self.lists = bool(lists)
         self.n_img, self.n_txt, self.dim, self.k = n_img, n_txt, dim, k
         self.fmt = ops.fmt_of(precision)
         self.tpc = tiles_per_chunk
@@ -513,7 +519,8 @@ class FusedEvalPlan:
             q.rank = self.ranks[d].data_ptr()
             q.recall_counts = sp + 16 * d
             q.gt_score = self.gts[d].data_ptr()
-        self.ws = torch.empty(lib.leccr_sim_topk_workspace(self.probs, 2, self.tpc), dtype=torch.uint8, device=dev)
+        ws_bytes = lib.leccr_sim_topk_workspace(self.probs, 2, self.tpc) if self.lists else lib.leccr_sim_rank_workspace(self.probs, 2)
+        self.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         self._step()  # warm-up outside capture: lazy module load, kernel attributes
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
@@ -528,8 +535,11 @@ class FusedEvalPlan:
                                     self.rn[1].data_ptr(), sp + 32, self.txt.data_ptr(), self.n_txt, d,
                                     self.txt16.data_ptr(), d, self.rn[2].data_ptr(), self.rn[3].data_ptr(), sp + 48, d, 0,
                                     self.fmt, N.LAYOUT_HI, st), "leccr_prep_pair")
-        N.check(lib.leccr_sim_topk(self.probs, 2, d, self.fmt, self.k, self.tpc, self.ws.data_ptr(), self.ws.numel(), st),
-                "leccr_sim_topk")
+        if self.lists:
+            N.check(lib.leccr_sim_topk(self.probs, 2, d, self.fmt, self.k, self.tpc, self.ws.data_ptr(), self.ws.numel(), st),
+                    "leccr_sim_topk")
+        else:
+            N.check(lib.leccr_sim_rank(self.probs, 2, d, self.fmt, self.ws.data_ptr(), self.ws.numel(), st), "leccr_sim_rank")
 
     def launch(self, image_embeds=None, text_embeds=None):
         """Asynchronous part of a run: stage the inputs (if given) and replay the graph."""
@@ -549,6 +559,8 @@ class FusedEvalPlan:
         if float(hf[11]) != 0.0 or float(hf[15]) != 0.0:
             raise N.LeccrError("embeddings overflow the fp16 operand format; build the plan with precision='bf16'")
         ev = metrics_from_counts(h[0:3], self.n_img, h[4:7], self.n_txt)
+        if return_topk and not self.lists:
+            raise N.LeccrError("this plan was built with lists=False: it computes the Recall dict only")
         return (ev, self.topk) if return_topk else ev
 
 

@@ -195,6 +195,49 @@ def sim_topk(problems, k: int = 10, tiles_per_chunk: int = 0):
     return results
 
 
+def sim_rank(problems):
+    """Fused similarity + exact Recall ranks WITHOUT top-k lists (leccr_sim_rank) for 1 or 2 (rows, cols, gt) problems:
+    what the reference's itm_eval returns.  gt = (gt_off, gt_ids) CSR tensors (required).  Returns TopkResult objects
+    with val / idx = None."""
+    lib = N.load()
+    if not 1 <= len(problems) <= 2:
+        raise ValueError("one or two problems per launch")
+    arr = (N.TopkProblem * len(problems))()
+    keep, results = [], []
+    fmt, D = problems[0][0].fmt, problems[0][0].D
+    for i, (rows, cols, gt) in enumerate(problems):
+        if gt is None:
+            raise N.LeccrError("sim_rank needs the ground truth of every problem")
+        if rows.layout != N.LAYOUT_HI or cols.layout != N.LAYOUT_HI:
+            raise N.LeccrError("sim_rank takes single-pass (HI) operands")
+        if rows.fmt != fmt or cols.fmt != fmt or rows.D != D or cols.D != D:
+            raise N.LeccrError("all operands of a launch must share format and dimension")
+        if rows.x.dtype != cols.x.dtype:
+            raise N.LeccrError("exact re-scoring needs both originals in one dtype")
+        if rows.rn_hi is None or cols.stats is None:
+            raise N.LeccrError("sim_rank needs operands prepared with statistics (ops.prep(..., want_stats=True))")
+        dev = rows.t16.device
+        gt_off, gt_ids = gt
+        rank = torch.empty(rows.n, dtype=torch.int32, device=dev)
+        counts = torch.zeros(3, dtype=torch.int32, device=dev)
+        gts = torch.empty(max(1, gt_ids.numel()), dtype=torch.float32, device=dev)
+        p = arr[i]
+        p.rows16, p.cols16 = N.ptr(rows.t16), N.ptr(cols.t16)
+        p.ld_rows16, p.ld_cols16 = rows.t16.stride(0), cols.t16.stride(0)
+        p.n_rows, p.n_cols = rows.n, cols.n
+        p.gt_off, p.gt_ids = N.ptr(gt_off), N.ptr(gt_ids)
+        p.rows_x, p.cols_x = N.ptr(rows.x), N.ptr(cols.x)
+        p.ld_rows_x, p.ld_cols_x = rows.x.stride(0), cols.x.stride(0)
+        p.x_dtype = rows.x_dtype
+        p.rn_hi, p.rn_lo, p.col_stats = N.ptr(rows.rn_hi), N.ptr(rows.rn_lo), N.ptr(cols.stats)
+        p.rank, p.recall_counts, p.gt_score = N.ptr(rank), N.ptr(counts), N.ptr(gts)
+        keep += [gt_off, gt_ids]
+        results.append(TopkResult(None, None, rank, counts, gts))
+    ws = torch.empty(lib.leccr_sim_rank_workspace(arr, len(problems)), dtype=torch.uint8, device=problems[0][0].t16.device)
+    N.check(lib.leccr_sim_rank(arr, len(problems), D, fmt, N.ptr(ws), ws.numel(), N.stream_ptr()), "leccr_sim_rank")
+    return results
+
+
 def infonce_forward(a: Operand, b: Operand, idx: Optional[torch.Tensor], temp: torch.Tensor,
                     tiles_per_chunk: int = 0):
     """Returns (out[6] = loss, dloss/dtemp, loss_i2t, loss_t2i, dloss_i2t/dtemp, dloss_t2i/dtemp ; lse2 [2, n] ;

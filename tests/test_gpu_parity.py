@@ -814,3 +814,59 @@ def test_double_sim_in_the_epilogue_ragged_shapes_and_caption_counts(n_vid, per,
     ev_f, topk_f = leccr_b200.fused_eval(rs.image, rs.text, t2, i2, k=10, caption_embeds=rs.caption, alpha=alpha, fusion=fusion)
     assert "rank_i2t" not in topk_f
     assert_ev_equal(ev_f, oracle.itm_eval_by_count(want_i2t, want_t2i, t2, i2))
+
+
+# ----------------------------------------------------------------------------- Recall only (leccr_sim_rank, EpiRank)
+@pytest.mark.parametrize("cfg", ["cfg1", "ragged", "bf16", "dups"])
+def test_recall_only_path_ranks_exactly(golden, cfg):
+    """fused_eval(..., return_topk=False) = the counting epilogue (no candidate lists): the 13-key dict equals the
+    reference's, and every row's rank equals the oracle's count of strictly greater fp32 scores -- exact for ALL ranks,
+    not only below 10.  'dups': thousands of columns tie exactly with the ground truth, so the (row, column) pair list of
+    the band overflows and the exact fallback answers."""
+    if cfg == "cfg1":
+        rs = synth.cfg1_multi30k()
+        image, text, t2i_map, i2t_map = rs.image, rs.text, rs.txt2img, rs.img2txt
+    elif cfg == "ragged":
+        rs = synth.retrieval_set(333, 3, d=72, seed=31)
+        image, text, t2i_map, i2t_map = rs.image, rs.text, rs.txt2img, rs.img2txt
+    elif cfg == "bf16":
+        rs = synth.retrieval_set(300, 5, d=256, seed=32)
+        image, text = rs.image.to(torch.bfloat16), rs.text.to(torch.bfloat16)
+        t2i_map, i2t_map = rs.txt2img, rs.img2txt
+    else:
+        rs = synth.retrieval_set(64, 2, d=64, seed=33)
+        image = rs.image.clone()
+        text = rs.text.clone()
+        text[0] = rs.image[0]
+        text[1] = rs.image[0]
+        image = torch.cat([image, rs.image[:1].repeat(3000, 1)])     # 3000 more images identical to image 0: texts 0 and 1
+        t2i_map = dict(rs.txt2img)                                   # tie with 3000 columns each (6000 pairs > the 4096 slots)
+        i2t_map = {i: list(v) for i, v in rs.img2txt.items()}
+        for i in range(64, 3064):
+            i2t_map[i] = [0]
+    i2t, t2i = oracle.score_matrices(image.float(), text.float())
+    n_img, n_txt = i2t.shape
+    want = oracle.itm_eval_by_count(i2t, np.ascontiguousarray(t2i), t2i_map, i2t_map)
+    ev = leccr_b200.fused_eval(image, text, t2i_map, i2t_map, return_topk=False)
+    assert_ev_equal(ev, want)
+    dev = torch.device("cuda")
+    I, T = ops.prep(image.cuda()), ops.prep(text.cuda())
+    gt = leccr_b200.prepare_gt(t2i_map, i2t_map, n_img, n_txt, dev)
+    r_i, r_t = ops.sim_rank([(I, T, gt[0]), (T, I, gt[1])])
+    want_i = oracle.ranks_by_count(i2t, [i2t_map[i] for i in range(n_img)])
+    want_t = oracle.ranks_by_count(np.ascontiguousarray(t2i), [[t2i_map[t]] for t in range(n_txt)])
+    if cfg == "bf16":   # fp32 matmul of bf16 inputs vs fp32 FMA dots: compare where the oracle's margin is unambiguous
+        assert (r_i.rank.cpu().numpy() == want_i).mean() > 0.99 and (r_t.rank.cpu().numpy() == want_t).mean() > 0.99
+    else:
+        assert np.array_equal(r_i.rank.cpu().numpy(), want_i)
+        assert np.array_equal(r_t.rank.cpu().numpy(), want_t)
+
+
+def test_recall_only_plan_cfg2_equals_the_reference_dict(golden):
+    g = golden("baseline_configs.npz")
+    rs = synth.cfg2_mscoco5k()
+    plan = leccr_b200.FusedEvalPlan(5000, 25000, 256, rs.txt2img, rs.img2txt, lists=False)
+    assert_ev_equal(plan.run(rs.image, rs.text), ev_of(g, "cfg2_ev_"))
+    assert_ev_equal(plan.run(rs.image, rs.text), ev_of(g, "cfg2_ev_"))      # graph replay, state re-zeroed
+    with pytest.raises(N.LeccrError):
+        plan.run(rs.image, rs.text, return_topk=True)
