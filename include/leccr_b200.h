@@ -153,8 +153,9 @@ int leccr_sim_topk(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
  * topk_val / topk_idx ignored).  The best ground-truth score of every row is computed exactly first; the
  * tensor-core pass only COUNTS the scores that are definitely greater (16-bit-operand score > t + eps) and writes
  * the rare (row, column) pairs inside the band t +- eps, which are re-scored exactly afterwards; a row whose pairs
- * overflow takes the exact fallback.  rank[row] = exact number of columns scoring above the row's best ground
- * truth (LECCR_RANK_CAP for rows without one); recall_counts += #{rank < 1, 5, 10}. */
+ * overflow takes the exact fallback.  rank[row] = number of columns scoring above the row's best ground truth:
+ * exact when < LECCR_RANK_CAP, otherwise a lower bound >= LECCR_RANK_CAP (the same contract as leccr_sim_topk;
+ * LECCR_RANK_CAP for rows without ground truth); recall_counts += #{rank < 1, 5, 10}. */
 size_t leccr_sim_rank_workspace(const leccr_topk_problem* probs, int n_prob);
 int leccr_sim_rank(const leccr_topk_problem* probs, int n_prob, int D, int fmt, void* workspace, size_t workspace_bytes,
                    leccr_stream_t stream);

@@ -866,7 +866,7 @@ int leccr_sim_topk_stream(const leccr_topk_problem* probs, const leccr_topk_stre
 // ------------------------------------------------------------------------------------ Recall only (EpiRank)
 // Similarity + exact ranks of the ground truth + Recall@1/5/10 with NO candidate lists: what itm_eval returns.
 static size_t rank_ws_bytes(int64_t n_rows) {
-  const size_t cap = std::max<size_t>(4096, static_cast<size_t>(n_rows) * 8);
+  const size_t cap = std::max<size_t>(4096, static_cast<size_t>(n_rows) * 64);
   return 3 * align256(static_cast<size_t>(n_rows) * 4) /* best, lo, hi */ + align256(static_cast<size_t>(n_rows) * 4) /* row_flag */ +
          align256(static_cast<size_t>(n_rows) * 4 + 16) /* flag count + list */ + 256 /* pair count */ + align256(cap * 8);
 }
@@ -897,7 +897,8 @@ int leccr_sim_rank(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
   int64_t total_tiles = 0;
   for (int p = 0; p < n_prob; ++p)
     total_tiles += ((probs[p].n_rows + BM - 1) / BM) * ((probs[p].n_cols + BN - 1) / BN);
-  const int tpc = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(total_tiles / (6LL * num_sms()), 64)));
+  int tpc = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(total_tiles / (6LL * num_sms()), 64)));
+  if (const char* e = getenv("LECCR_RANK_TPC")) tpc = std::max(1, atoi(e));  // measurement aid
   SimLaunch L;
   memset(&L, 0, sizeof(L));
   L.n_prob = n_prob;
@@ -908,12 +909,15 @@ int leccr_sim_rank(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
   TopkFinalizeParams post[2];
   memset(post, 0, sizeof(post));
   float* best[2];
+  GtBestParams gtp[2];
+  memset(gtp, 0, sizeof(gtp));
+  int64_t max_rows = 0;
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   int item_base = 0;
   for (int p = 0; p < n_prob; ++p) {
     const leccr_topk_problem& q = probs[p];
     const size_t nb = align256(static_cast<size_t>(q.n_rows) * 4);
-    const int cap = static_cast<int>(std::max<size_t>(4096, static_cast<size_t>(q.n_rows) * 8));
+    const int cap = static_cast<int>(std::max<size_t>(4096, static_cast<size_t>(q.n_rows) * 64));
     best[p] = reinterpret_cast<float*>(ws);
     float* lo = reinterpret_cast<float*>(ws + nb);
     float* hi = reinterpret_cast<float*>(ws + 2 * nb);
@@ -926,9 +930,7 @@ int leccr_sim_rank(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
     ws += 256;
     int2* amb_list = reinterpret_cast<int2*>(ws);
     ws += align256(static_cast<size_t>(cap) * 8);
-    CUDA_TRY(cudaMemsetAsync(row_flag, 0, nb + 16 /* row flags, then the flag count + barrier word */, stream));
-    CUDA_TRY(cudaMemsetAsync(amb_count, 0, 4, stream));
-    GtBestParams G;
+    GtBestParams& G = gtp[p];
     G.gt_off = q.gt_off;
     G.gt_ids = q.gt_ids;
     G.rows_x = q.rows_x;
@@ -947,8 +949,10 @@ int leccr_sim_rank(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
     G.hi = hi;
     G.gt_score = q.gt_score;
     G.rank = q.rank;
-    gt_best_kernel<<<static_cast<unsigned>((q.n_rows + 7) / 8), 256, 0, stream>>>(G);
-    LAUNCH_CHECK("gt_best_kernel");
+    G.row_flag = row_flag;
+    G.flag_words = flag;
+    G.amb_count = amb_count;
+    max_rows = std::max<int64_t>(max_rows, q.n_rows);
     const Plan pl = plan_problem(q.n_cols, 0, q.n_rows, tpc);
     rc = fill_problem(L.prob[p], q.rows16, q.ld_rows16, q.cols16, q.ld_cols16, q.n_rows, q.n_cols, D, fmt, pl, item_base);
     if (rc != LECCR_OK) return rc;
@@ -979,14 +983,39 @@ int leccr_sim_rank(const leccr_topk_problem* probs, int n_prob, int D, int fmt, 
     F.gt_score = nullptr;
   }
   L.n_items = item_base;
-  if (L.k_chunks <= kAResChunks) rc = launch_gemm<EpiRank, BK, true>(L, EP, stream);
+  {  // exact best ground-truth scores, bands, zeroed flags and counters: one launch for both problems
+    dim3 gg(static_cast<unsigned>((max_rows + 7) / 8), static_cast<unsigned>(n_prob));
+    gt_best_kernel<<<gg, 256, 0, stream>>>(gtp[0], gtp[1]);
+    LAUNCH_CHECK("gt_best_kernel");
+  }
+  if (const char* dbg = getenv("LECCR_RANK_DEBUG")) EP.debug_mode = atoi(dbg);  // measurement aid only
+  static int ares = -1;
+  if (ares < 0) {
+    const char* e = getenv("LECCR_RANK_ARES");  // measurement aid: 0 streams the row block with the gallery
+    ares = (e != nullptr && atoi(e) == 0) ? 0 : 1;
+  }
+  if (L.k_chunks <= kAResChunks && ares) rc = launch_gemm<EpiRank, BK, true>(L, EP, stream);
   else rc = launch_gemm<EpiRank>(L, EP, stream);
   if (rc != LECCR_OK) return rc;
-  for (int p = 0; p < n_prob; ++p) {
-    const leccr_topk_problem& q = probs[p];
-    rank_resolve_kernel<<<static_cast<unsigned>(num_sms()), 256, 0, stream>>>(
-        EP.amb_list[p], EP.amb_count[p], EP.amb_cap[p], q.rows_x, q.ld_rows_x, q.cols_x, q.ld_cols_x, D, q.x_dtype, best[p],
-        q.rank);
+  {
+    ResolveParams rp[2];
+    memset(rp, 0, sizeof(rp));
+    for (int p = 0; p < n_prob; ++p) {
+      const leccr_topk_problem& q = probs[p];
+      rp[p].pairs = EP.amb_list[p];
+      rp[p].n_pairs = EP.amb_count[p];
+      rp[p].cap = EP.amb_cap[p];
+      rp[p].rows_x = q.rows_x;
+      rp[p].cols_x = q.cols_x;
+      rp[p].ld_rows = q.ld_rows_x;
+      rp[p].ld_cols = q.ld_cols_x;
+      rp[p].D = D;
+      rp[p].x_dtype = q.x_dtype;
+      rp[p].best = best[p];
+      rp[p].rank = q.rank;
+    }
+    dim3 gr(static_cast<unsigned>(4 * num_sms()), static_cast<unsigned>(n_prob));
+    rank_resolve_kernel<<<gr, 256, 0, stream>>>(rp[0], rp[1]);
     LAUNCH_CHECK("rank_resolve_kernel");
   }
   if (n_prob == 1) memset(&post[1], 0, sizeof(post[1]));

@@ -965,12 +965,22 @@ struct GtBestParams {
   float* hi;        // [n_rows]
   float* gt_score;  // [nnz] or null
   int* rank;        // [n_rows] initialised here: 0, or kRankCap for rows without ground truth
+  int* row_flag;    // [n_rows] zeroed here
+  int* flag_words;  // 4 words (flag count, grid-barrier word of rank_post, ...) zeroed here
+  int* amb_count;   // zeroed here
 };
 
-__global__ void gt_best_kernel(const GtBestParams P) {
+// blockIdx.y = problem (one launch serves both directions of an evaluation)
+__global__ void gt_best_kernel(const GtBestParams P0, const GtBestParams P1) {
+  const GtBestParams& P = blockIdx.y == 0 ? P0 : P1;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (blockIdx.x == 0 && threadIdx.x < 4) {
+    P.flag_words[threadIdx.x] = 0;
+    if (threadIdx.x == 0) *P.amb_count = 0;
+  }
   if (row >= P.n_rows) return;
+  if (lane == 0) P.row_flag[row] = 0;
   const int g0 = P.gt_off[row], g1 = P.gt_off[row + 1];
   const bool fast = vec_ok(P.rows_x, P.ld_rows, P.D, P.x_dtype) && vec_ok(P.cols_x, P.ld_cols, P.D, P.x_dtype);
   RowRegs qrow;
@@ -1001,15 +1011,38 @@ __global__ void gt_best_kernel(const GtBestParams P) {
   }
 }
 
-__global__ void rank_resolve_kernel(const int2* __restrict__ pairs, const int* __restrict__ n_pairs, int cap,
-                                    const void* rows_x, long long ld_rows, const void* cols_x, long long ld_cols, int D,
-                                    int x_dtype, const float* __restrict__ best, int* __restrict__ rank) {
+struct ResolveParams {
+  const int2* pairs;
+  const int* n_pairs;
+  int cap;
+  const void* rows_x;
+  const void* cols_x;
+  long long ld_rows, ld_cols;
+  int D, x_dtype;
+  const float* best;
+  int* rank;
+};
+
+// blockIdx.y = problem
+__global__ void rank_resolve_kernel(const ResolveParams P0, const ResolveParams P1) {
+  const ResolveParams& P = blockIdx.y == 0 ? P0 : P1;
   const int lane = threadIdx.x & 31;
-  const int n = min(*n_pairs, cap);
+  const int n = min(*P.n_pairs, P.cap);
+  // the SAME dot routine (same summation order) as gt_best_kernel: a ground-truth column must tie with itself
+  const bool fast = vec_ok(P.rows_x, P.ld_rows, P.D, P.x_dtype) && vec_ok(P.cols_x, P.ld_cols, P.D, P.x_dtype);
   for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += gridDim.x * (blockDim.x >> 5)) {
-    const int2 pr = pairs[i];
-    const float tj = warp_dot(rows_x, ld_rows, pr.x, cols_x, ld_cols, pr.y, D, x_dtype, lane);
-    if (lane == 0 && tj > best[pr.x]) atomicAdd(rank + pr.x, 1);
+    const int2 pr = P.pairs[i];
+    if (P.rank[pr.x] >= kRankCap) continue;  // decided by the definite counts alone (monotone: pairs only add)
+    float tj;
+    if (fast) {
+      RowRegs qrow, crow;
+      load_row_regs(qrow, P.rows_x, P.ld_rows, pr.x, P.D, lane);
+      load_row_regs(crow, P.cols_x, P.ld_cols, pr.y, P.D, lane);
+      tj = dot_row_regs(qrow, crow);
+    } else {
+      tj = warp_dot(P.rows_x, P.ld_rows, pr.x, P.cols_x, P.ld_cols, pr.y, P.D, P.x_dtype, lane);
+    }
+    if (lane == 0 && tj > P.best[pr.x]) atomicAdd(P.rank + pr.x, 1);
   }
 }
 

@@ -353,6 +353,22 @@ __device__ __forceinline__ uint32_t append4_if_gt(float x0, float x1, float x2, 
   return next;
 }
 
+// if (x > hi) mask_hi |= BIT; if (x > lo) mask_lo |= BIT: two compares and two predicated ORs -- the counting
+// epilogue's whole per-element work.  Masks instead of counters: popc gives the counts, mask_lo & ~mask_hi names the
+// elements inside the band without a second pass over the registers (which cannot be indexed per lane).
+template <unsigned BIT>
+__device__ __forceinline__ void mask_gt2(float x, float hi, float lo, unsigned& mask_hi, unsigned& mask_lo) {
+  asm("{\n"
+      ".reg .pred p, q;\n"
+      "setp.gt.f32 p, %2, %3;\n"
+      "setp.gt.f32 q, %2, %4;\n"
+      "@p or.b32 %0, %0, %5;\n"
+      "@q or.b32 %1, %1, %5;\n"
+      "}\n"
+      : "+r"(mask_hi), "+r"(mask_lo)
+      : "f"(x), "f"(hi), "f"(lo), "n"(BIT));
+}
+
 // Order-preserving float <-> uint32 key (any sign, +-inf included).
 __device__ __forceinline__ uint32_t f32_key(float f) {
   const uint32_t b = __float_as_uint(f);
