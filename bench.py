@@ -570,7 +570,8 @@ def extras_single_gpu(torch, leccr_b200, ops, synth, lib, dev, peak):
                                "roofline": {"bound": "tensor", "kernel": "sim_gemm_kernel<EpiRank> (both directions, one launch)",
                                             "achieved": flops / (rank_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                                             "frac": flops / (rank_ms * 1e-3) / 1e12 / peak, "kernel_ms": rank_ms,
-                                            "flops_per_launch": flops},
+                                            "flops_per_launch": flops,
+                                            "traffic": traffic_from_profile("cfg2_rank_dram_bytes_per_launch")},
                                "recall_check": "equal to cfg2.recall_check (asserted)"}
     del plan, splan, rplan, flush
     # ---- cfg1 / cfg4: microseconds per evaluation through the public API, inputs resident in HBM
