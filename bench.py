@@ -204,17 +204,18 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
         return bool(t.item())
 
-    # ---- host side of the e2e path: this rank's pinned staging memory on its GPU's NUMA node
+    # ---- data: every rank generates the same seeded workload on its GPU; the host copies are pinned, allocated
+    # while this thread sits on the CPUs of its GPU's NUMA node (restored afterwards)
     from leccr_b200 import peer as _peer
 
-    numa_bound = _peer.bind_host_thread_to_device(local_rank) if world > 1 else False
-    # ---- data: every rank generates the same seeded workload on its GPU; host copies are pinned
     gal, qry, gt = synth.cfg5_gallery(N_GALLERY, N_QUERY, device=dev)
-    gal_h = torch.empty(gal.shape, dtype=gal.dtype).pin_memory()
-    qry_h = torch.empty(qry.shape, dtype=qry.dtype).pin_memory()
-    gal_h.copy_(gal)
-    qry_h.copy_(qry)
-    plan = leccr_b200.GallerySearchPlan(N_GALLERY, N_QUERY, DIM, k=TOPK, dtype=torch.bfloat16)
+    with _peer.host_memory_near_device(local_rank) as near:
+        gal_h = torch.empty(gal.shape, dtype=gal.dtype).pin_memory()
+        qry_h = torch.empty(qry.shape, dtype=qry.dtype).pin_memory()
+        gal_h.copy_(gal)
+        qry_h.copy_(qry)
+        plan = leccr_b200.GallerySearchPlan(N_GALLERY, N_QUERY, DIM, k=TOPK, dtype=torch.bfloat16)
+    numa_bound = near.bound
     gb, ge = plan.gallery_rows
     qb, qe = plan.query_rows
     plan.load_device(gal[gb:ge], qry[qb:qe])

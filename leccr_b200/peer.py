@@ -24,20 +24,41 @@ _cache = {}
 _warned = False
 
 
-def bind_host_thread_to_device(device_index: int) -> bool:
-    """Pin the calling thread to the CPUs next to GPU `device_index` (NVML's ideal affinity), so that host memory it
-    allocates and first touches afterwards -- the pinned staging buffers of the host paths -- lands on the GPU's
-    NUMA node.  torchrun does not place its ranks; with eight ranks streaming pinned memory at once, buffers that
-    all sit on one socket share its memory controllers and the inter-socket link.  Returns False when NVML or the
-    container's cpuset does not allow it (nothing changes then)."""
-    try:
-        import pynvml as nv
+class host_memory_near_device:
+    """Context manager: while it is active the calling thread runs on the CPUs next to GPU `device_index` (NVML's
+    ideal affinity), so host memory allocated and first touched inside -- the pinned staging buffers of the host
+    paths -- lands on the GPU's NUMA node; the previous affinity is restored on exit (the training loop, its
+    autograd thread and the data loaders keep their cores).  torchrun does not place its ranks; with eight ranks
+    streaming pinned memory at once, buffers that all sit on one socket share its memory controllers and the
+    inter-socket link.  `.bound` is False when NVML or the container's cpuset does not allow it (nothing changes)."""
 
-        nv.nvmlInit()
-        h = nv.nvmlDeviceGetHandleByIndex(int(device_index))
-        nv.nvmlDeviceSetCpuAffinity(h)
-        return True
-    except Exception:
+    def __init__(self, device_index: int):
+        self.index = int(device_index)
+        self.bound = False
+        self._old = None
+
+    def __enter__(self):
+        try:
+            import os
+
+            import pynvml as nv
+
+            self._old = os.sched_getaffinity(0)
+            nv.nvmlInit()
+            nv.nvmlDeviceSetCpuAffinity(nv.nvmlDeviceGetHandleByIndex(self.index))
+            self.bound = True
+        except Exception:
+            self.bound = False
+        return self
+
+    def __exit__(self, *exc):
+        if self.bound and self._old:
+            try:
+                import os
+
+                os.sched_setaffinity(0, self._old)
+            except Exception:
+                pass
         return False
 
 
