@@ -595,6 +595,9 @@ def extras_single_gpu(torch, leccr_b200, ops, synth, lib, dev, peak):
                    "us_per_eval": us_per_call(lambda: p1.run(i1, t1)),
                    "api": "FusedEvalPlan.run(device fp32): cast, fused pass, finalize, Recall counts to the host",
                    "recall_check": {k: ev1[k] for k in ("txt_r1", "txt_r5", "txt_r10", "img_r1", "img_r5", "img_r10")}}
+    p1r = leccr_b200.FusedEvalPlan(1000, 5000, DIM, k=TOPK, gt=g1, lists=False)
+    assert p1r.run(i1, t1) == ev1, "cfg1: Recall-only path disagrees"
+    out["cfg1"]["us_per_eval_recall_only"] = us_per_call(lambda: p1r.run(i1, t1))
     r4 = synth.cfg4_msrvtt()
     i4, t4, c4 = r4.image.to(dev), r4.text.to(dev), r4.caption.to(dev)
     g4 = leccr_b200.prepare_gt(r4.txt2img, r4.img2txt, 1000, 1000, dev)

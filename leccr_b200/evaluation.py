@@ -596,9 +596,14 @@ class StreamedEvalPlan:
         if img_subs * len(fracs) > 8:
             fracs = [1.0 / max(1, 8 // img_subs)] * max(1, 8 // img_subs)
             img_subs = max(img_subs, -(-int(max(fracs) * n_txt + 255) // 256 // 32))
-        if img_subs * len(fracs) > 8 or txt_subs > 8:
-            raise N.LeccrError("StreamedEvalPlan handles up to ~65k x 65k evaluation sets; shard larger ones "
-                               "(fused_eval_sharded / topk_gallery_sharded)")
+        # Larger sets (a window or the image set beyond 8 slots x 32 tiles = 65,536 columns): every call of the
+        # plan switches to the long-chunk list shape (LECCR_TOPK_LONG: the filter epilogue of the large-gallery
+        # search, which has no chunk-length limit); the slot counts then only balance the load.
+        self.long = img_subs * len(fracs) > 8 or txt_subs > 8
+        if self.long:
+            img_subs = max(1, min(img_subs, 8 // len(fracs)))
+            txt_subs = min(txt_subs, 8)
+        long_flag = N.TOPK_LONG if self.long else 0
         self.gt = gt if gt is not None else prepare_gt(txt2img, img2txt, n_img, n_txt, self.dev)
         dev = self.dev
         dt16 = torch.float16 if self.fmt == N.FMT_F16 else torch.bfloat16
@@ -650,7 +655,7 @@ class StreamedEvalPlan:
             p.ld_rows16 = p.ld_cols16 = dim
             p.n_rows, p.n_cols = n_img, e - b
             o = so[0]
-            o.phases = N.TOPK_GEMM | (N.TOPK_INIT if w == 0 else 0)
+            o.phases = long_flag | N.TOPK_GEMM | (N.TOPK_INIT if w == 0 else 0)
             o.sub_begin, o.sub_count, o.sub_total = w * img_subs, img_subs, self.sub_total
             o.col_begin = b
             o.workspace, o.workspace_bytes = self.ws_img.data_ptr(), self.ws_img.numel()
@@ -674,7 +679,7 @@ class StreamedEvalPlan:
             p.recall_counts = self.counts.data_ptr() + 16
             p.gt_score = self.gts[1].data_ptr() + int(off_host[b]) * 4
             o = so[1]
-            o.phases = N.TOPK_INIT | N.TOPK_GEMM | N.TOPK_FINALIZE
+            o.phases = long_flag | N.TOPK_INIT | N.TOPK_GEMM | N.TOPK_FINALIZE
             o.sub_begin, o.sub_count, o.sub_total = 0, txt_subs, txt_subs
             o.workspace, o.workspace_bytes = self.ws_txt.data_ptr(), self.ws_txt.numel()
             self.calls.append((pr, so, 2))
@@ -696,7 +701,7 @@ class StreamedEvalPlan:
         p.recall_counts = self.counts.data_ptr()
         p.gt_score = self.gts[0].data_ptr()
         o = so[0]
-        o.phases = N.TOPK_FINALIZE
+        o.phases = long_flag | N.TOPK_FINALIZE
         o.sub_begin, o.sub_count, o.sub_total = 0, self.sub_total, self.sub_total
         o.n_cols_total = n_txt
         o.workspace, o.workspace_bytes = self.ws_img.data_ptr(), self.ws_img.numel()

@@ -872,3 +872,19 @@ def test_recall_only_plan_cfg2_equals_the_reference_dict(golden):
     assert_ev_equal(plan.run(rs.image, rs.text), ev_of(g, "cfg2_ev_"))      # graph replay, state re-zeroed
     with pytest.raises(N.LeccrError):
         plan.run(rs.image, rs.text, return_topk=True)
+
+
+def test_streamed_plan_beyond_65k_columns_uses_the_long_list_shape():
+    """StreamedEvalPlan on 400 images x 80,000 texts: the text windows are longer than 8 slots x 32 tiles, so every
+    call carries LECCR_TOPK_LONG (filter-epilogue lists); same Recall dict as the oracle and as the one-shot path."""
+    rs = synth.retrieval_set(400, 200, d=64, seed=77)
+    plan = leccr_b200.StreamedEvalPlan(400, 80_000, 64, rs.txt2img, rs.img2txt)
+    assert plan.long
+    ev = plan.run(rs.image.pin_memory(), rs.text.pin_memory())
+    i2t, t2i = oracle.score_matrices(rs.image, rs.text)
+    want = oracle.itm_eval_by_count(i2t, np.ascontiguousarray(t2i), rs.txt2img, rs.img2txt)
+    assert_ev_equal(ev, want)
+    assert_ev_equal(leccr_b200.fused_eval(rs.image, rs.text, rs.txt2img, rs.img2txt, return_topk=False), want)
+    ev2, topk = plan.run(rs.image.pin_memory(), rs.text.pin_memory(), return_topk=True)
+    assert_ev_equal(ev2, want)
+    check_topk_against(i2t, *topk["i2t"], 10, F16_TOL)
