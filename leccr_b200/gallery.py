@@ -39,20 +39,30 @@ def _world():
 
 
 def _pick_windows(row_blocks: int, part_rows: int, sms: int = 148):
-    """(windows, slots per window) of the host path: windows * slots <= 8 list slots per query row; prefer the
-    split whose work items fill whole waves of the persistent grid, then the one with more (smaller) windows
-    (less un-overlapped H2D in front of the first pass)."""
+    """List of list-slot counts, one per gallery window of the host path (at most 8 slots per query row in total).
+    The windows grow geometrically (_window_bounds), so only the first -- small -- one is exposed; all but the first
+    use the slot count whose work items fill whole waves of the persistent grid, the first takes what is left.
+    More windows are preferred as long as the first stays above 32,768 rows (below that a pass is launch- and
+    threshold-warm-up-bound)."""
+    def eff(s):
+        items = row_blocks * s
+        return items / (-(-items // sms) * sms)
+
     best = None
-    for w in (8, 4, 2, 1):
-        if part_rows // w < 32768 and w > 1:
-            continue  # windows this small are launch- and threshold-warm-up-bound
-        for s in range(1, 8 // w + 1):
-            items = row_blocks * s
-            eff = items / (-(-items // sms) * sms)
-            score = (int(min(eff, 0.95) / 0.05 + 1e-9), w, -s)  # 5 % buckets: 0.96 and 0.99 are the same
-            if best is None or score > best[0]:
-                best = (score, w, s)
-    return best[1], best[2]
+    for w in (4, 3, 2, 1):
+        if w > 1 and part_rows // ((1 << w) - 1) < 32768:
+            continue
+        if w == 1:
+            s_main = max(range(1, 9), key=lambda s: (int(min(eff(s), 0.95) / 0.05 + 1e-9), -s))
+            cand = [s_main]
+        else:
+            top = (8 - 1) // (w - 1)
+            s_main = max(range(1, top + 1), key=lambda s: (int(min(eff(s), 0.95) / 0.05 + 1e-9), -s))
+            cand = [max(1, min(s_main, 8 - s_main * (w - 1)))] + [s_main] * (w - 1)
+        score = (int(min(eff(s_main), 0.95) / 0.05 + 1e-9), w)
+        if best is None or score > best[0]:
+            best = (score, cand)
+    return best[1]
 
 
 def _window_bounds(part_rows: int, windows: int):
@@ -173,15 +183,18 @@ class GallerySearchPlan:
         # ---- windowed problems (host inputs)
         row_blocks = (self.Qs + 127) // 128
         if windows is None:
-            W, subs = _pick_windows(row_blocks, self.Gp)
+            subs = _pick_windows(row_blocks, self.Gp)
         else:
-            W, subs = int(windows), max(1, 8 // int(windows))
-            if W < 1 or W > 8:
+            if int(windows) < 1 or int(windows) > 8:
                 raise N.LeccrError("1 to 8 gallery windows")
+            subs = [max(1, 8 // int(windows))] * int(windows)
+        self.bounds = _window_bounds(self.Gp, len(subs))
+        subs = subs[len(subs) - len(self.bounds):]     # tiny parts give fewer windows: keep the main slot counts
         self.subs = subs
-        self.bounds = _window_bounds(self.Gp, W)
         W = len(self.bounds)
-        self.ws_stream = torch.empty(lib.leccr_sim_topk_stream_workspace(self.Qs, W * subs), dtype=torch.uint8, device=dev)
+        sub_total = sum(subs)
+        sub_begin = [sum(subs[:w]) for w in range(W)]
+        self.ws_stream = torch.empty(lib.leccr_sim_topk_stream_workspace(self.Qs, sub_total), dtype=torch.uint8, device=dev)
         self.stream_calls = []
         esz = 2
         for (lv, li, _off) in self.local:
@@ -192,7 +205,7 @@ class GallerySearchPlan:
                 self._fill(pr[0], self.gal16.data_ptr() + b * dim * esz, e - b, lv, li)
                 o = so[0]
                 o.phases = N.TOPK_LONG | N.TOPK_GEMM | (N.TOPK_INIT if w == 0 else 0) | (N.TOPK_FINALIZE if w == W - 1 else 0)
-                o.sub_begin, o.sub_count, o.sub_total = w * subs, subs, W * subs
+                o.sub_begin, o.sub_count, o.sub_total = sub_begin[w], subs[w], sub_total
                 o.col_begin = b
                 o.n_cols_total = self.Gp
                 o.workspace, o.workspace_bytes = self.ws_stream.data_ptr(), self.ws_stream.numel()

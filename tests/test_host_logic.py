@@ -289,9 +289,10 @@ def test_gallery_plan_layout_helpers():
             sizes = [e - s for s, e in b]
             assert sizes == sorted(sizes)                                         # only the first upload is exposed
     for rb, part in ((782, 1_000_000), (391, 500_000), (196, 500_000), (3, 70_000), (1, 1000)):
-        w, s = _pick_windows(rb, part)
-        assert 1 <= w and 1 <= s and w * s <= 8
-        assert w == 1 or part // w >= 32768
+        subs = _pick_windows(rb, part)
+        assert 1 <= len(subs) <= 4 and all(s >= 1 for s in subs) and sum(subs) <= 8
+        assert len(subs) == 1 or part // ((1 << len(subs)) - 1) >= 32768
+    assert _pick_windows(196, 500_000) == [2, 3, 3] and _pick_windows(782, 1_000_000) == [2, 2, 2, 2]
     for n, world in ((100_000, 8), (1_000_003, 8), (5, 8), (7, 2)):
         spans = [shard_range(n, r, world) for r in range(world)]
         assert spans[0][0] == 0 and spans[-1][1] == n
