@@ -3,7 +3,6 @@
 There is no CPU path: if the library is missing or a call fails, this module raises.
 """
 import ctypes
-import os
 
 from . import build as _build
 

@@ -1,7 +1,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from leccr_b200 import ops, _native as N
+from leccr_b200 import _native as N
 lib = N.load()
 def timeit(fn, iters=50):
     for _ in range(5): fn()
