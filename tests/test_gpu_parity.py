@@ -888,3 +888,19 @@ def test_streamed_plan_beyond_65k_columns_uses_the_long_list_shape():
     ev2, topk = plan.run(rs.image.pin_memory(), rs.text.pin_memory(), return_topk=True)
     assert_ev_equal(ev2, want)
     check_topk_against(i2t, *topk["i2t"], 10, F16_TOL)
+
+
+@pytest.mark.parametrize("n_per,d,dtype", [(5, 64, "f32"), (5, 72, "f32"), (3, 136, "f32"), (2, 320, "f32"), (2, 512, "f32"),
+                                          (7, 40, "f32"), (4, 256, "f16")])
+def test_recall_only_kernel_variants(n_per, d, dtype):
+    """The counting epilogue over embedding dimensions that are not multiples of the stage depth, beyond the resident
+    row block (D > 256: the row block streams with the gallery), short vectors, and fp16-stored inputs."""
+    n = 211
+    rs = synth.retrieval_set(n, n_per, d=d, seed=60 + d)
+    image, text = (rs.image.half(), rs.text.half()) if dtype == "f16" else (rs.image, rs.text)
+    i2t, t2i = oracle.score_matrices(image.float(), text.float())
+    want = oracle.itm_eval_by_count(i2t, np.ascontiguousarray(t2i), rs.txt2img, rs.img2txt)
+    assert_ev_equal(leccr_b200.fused_eval(image, text, rs.txt2img, rs.img2txt, return_topk=False), want)
+    plan = leccr_b200.FusedEvalPlan(n, n * n_per, d, rs.txt2img, rs.img2txt, lists=False) if dtype == "f32" else None
+    if plan is not None:
+        assert_ev_equal(plan.run(image, text), want)
