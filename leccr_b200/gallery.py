@@ -83,6 +83,19 @@ def _window_bounds(part_rows: int, windows: int):
     return bounds
 
 
+class SearchHandle:
+    """A search issued by `search_host_async`: `.result()` waits for it and returns the pinned host tensors
+    (val [n, k], idx int32 [n, k] global gallery rows, (q0, q1)).  The tensors are reused two searches later."""
+
+    def __init__(self, plan, lane):
+        self.plan, self.lane = plan, lane
+
+    def result(self):
+        L = self.plan.lanes[self.lane]
+        L["end"].synchronize()
+        return L["host_val"], L["host_idx"], self.plan._result_rows()
+
+
 class GallerySearchPlan:
     """Static buffers + the launch sequence of one search shape.
 
@@ -90,6 +103,10 @@ class GallerySearchPlan:
         plan.load_device(gallery_part_16bit, query_shard_16bit)      # rows plan.gallery_rows / plan.query_rows
         val, idx, (q0, q1) = plan.search()                           # this rank's merged query slice, global columns
         val_h, idx_h, (q0, q1) = plan.search_host(gallery_host, queries_host)   # pinned [G, D] / [Q, D] arrays
+        h = plan.search_host_async(gallery_host, queries_host); ...; val_h, idx_h, rows = h.result()
+
+    The host path keeps TWO lanes of input buffers: a search issued while the previous one is still being ranked
+    uploads (and exchanges) its windows meanwhile, so a stream of searches runs at the pace of the tensor cores.
     """
 
     def __init__(self, n_gallery, n_query, dim, k=10, dtype=torch.bfloat16, gallery_parts=None, windows=None,
@@ -119,26 +136,25 @@ class GallerySearchPlan:
         self.Qs, self.Gp = qe - qb, ge - gb
         if self.Qs <= 0 or self.Gp <= 0:
             raise N.LeccrError("fewer queries / gallery rows than ranks")
-        self.qry16 = torch.empty((self.Qs, dim), dtype=dtype, device=dev)
-        # gallery part: private, or -- host path with exchange -- one peer-mapped copy per rank that the S ranks
-        # holding the same part fill together (each uploads 1/S of every window and pushes it to its mates)
+        f32, i32 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.int32, device=dev)
+        esz = 2
+        # ---- input buffers, two lanes.  Gallery part: private, or -- host path with exchange -- peer-mapped, so that
+        # the S ranks holding the same part fill it together (each uploads 1/S of every window and pushes it to its
+        # mates).  Lane 0 also serves the device-resident path (load_device / search).
         if exchange_gallery is None:
             exchange_gallery = self.S > 1
         self.xchg = self.endb = None
-        self.gal16 = None
+        gal = [None, None]
         if exchange_gallery and self.S > 1 and peer.available(dev):
             gp_max = -(-n_gallery // P)
-            self.xchg = peer.get_buffer(("gallery_part", n_gallery, P, dim), gp_max * dim * 2, dev, slots=1)
+            self.xchg = peer.get_buffer(("gallery_part", n_gallery, P, dim), gp_max * dim * esz, dev, slots=2)
             if self.xchg is not None:
-                self.xchg_base = self.xchg.slot_offset(0)
-                self.gal16 = self.xchg.local(self.xchg_base, (self.Gp, dim), dtype)
                 self.mates = [self.part + P * s for s in range(self.S)]
-                if P == 1:  # no merge barrier at the end of a search: a mate must not refill a window still being ranked
+                gal = [self.xchg.local(self.xchg.slot_offset(l), (self.Gp, dim), dtype) for l in range(2)]
+                if P == 1:  # no merge barrier at the end of a search: a mate must not refill a lane still being ranked
                     self.endb = peer.get_buffer(("gallery_end",), 256, dev, slots=1)
-        if self.gal16 is None:
-            self.gal16 = torch.empty((self.Gp, dim), dtype=dtype, device=dev)
-        f32, i32 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.int32, device=dev)
-        # local lists: a private pair when there is nothing to merge, else the two slots of a peer-mapped buffer
+        # ---- local lists: private when there is nothing to merge, else the two slots of a peer-mapped buffer (or,
+        # without peer memory, private lists all-gathered with NCCL inside the shard's sub-group)
         self.pb = None
         self.nccl_group = None
         if P > 1:
@@ -149,17 +165,16 @@ class GallerySearchPlan:
                 self.pb = peer.get_buffer(("gallery_search", n_query, self.S, k), qs_max * k * 8, dev)
             self.group = [self.shard * P + i for i in range(P)]
             if self.pb is not None:
-                self.local = []
+                lists = []
                 for slot in range(2):
                     off = self.pb.slot_offset(slot)
-                    self.local.append((self.pb.local(off, (self.Qs, k), torch.float32),
-                                       self.pb.local(off + self.Qs * k * 4, (self.Qs, k), torch.int32), off))
+                    lists.append((self.pb.local(off, (self.Qs, k), torch.float32),
+                                  self.pb.local(off + self.Qs * k * 4, (self.Qs, k), torch.int32), off))
             else:
-                # no peer memory (LECCR_PEER=0, several nodes): the P lists of a shard are all-gathered with NCCL
-                # inside the shard's sub-group and merged by the same kernel over the gathered buffer
                 groups = [dist.new_group(ranks=[sh * P + i for i in range(P)]) for sh in range(self.S)]
                 self.nccl_group = groups[self.shard]
-                self.local = [(torch.empty((self.Qs, k), **f32), torch.empty((self.Qs, k), **i32), 0)]
+                one = (torch.empty((self.Qs, k), **f32), torch.empty((self.Qs, k), **i32), 0)
+                lists = [one, one]
                 self.gath_val = torch.empty((P, self.Qs, k), **f32)
                 self.gath_idx = torch.empty((P, self.Qs, k), **i32)
             self.part_offsets = (ctypes.c_int64 * P)(*[shard_range(n_gallery, i, P)[0] for i in range(P)])
@@ -169,18 +184,11 @@ class GallerySearchPlan:
             self.out_idx = torch.empty((me - mb, k), **i32)
             self._tabs = {}
         else:
-            self.local = [(torch.empty((self.Qs, k), **f32), torch.empty((self.Qs, k), **i32), 0)]
+            one = (torch.empty((self.Qs, k), **f32), torch.empty((self.Qs, k), **i32), 0)
+            lists = [one, one]
             self.merge_rows = (0, self.Qs)
-            self.out_val, self.out_idx = self.local[0][0], self.local[0][1]
-        self.calls = 0
-        # ---- one-shot problem (device-resident inputs)
-        self.probs = []
-        for (lv, li, _off) in self.local:
-            pr = (N.TopkProblem * 1)()
-            self._fill(pr[0], self.gal16.data_ptr(), self.Gp, lv, li)
-            self.probs.append(pr)
-        self.ws = torch.empty(lib.leccr_sim_topk_workspace(self.probs[0], 1, 0), dtype=torch.uint8, device=dev)
-        # ---- windowed problems (host inputs)
+            self.out_val, self.out_idx = one[0], one[1]
+        # ---- window layout of the host path
         row_blocks = (self.Qs + 127) // 128
         if windows is None:
             subs = _pick_windows(row_blocks, self.Gp)
@@ -195,14 +203,69 @@ class GallerySearchPlan:
         sub_total = sum(subs)
         sub_begin = [sum(subs[:w]) for w in range(W)]
         self.ws_stream = torch.empty(lib.leccr_sim_topk_stream_workspace(self.Qs, sub_total), dtype=torch.uint8, device=dev)
-        self.stream_calls = []
-        esz = 2
-        for (lv, li, _off) in self.local:
+        mb, me = self.merge_rows
+        # ---- lanes: lane l = input buffers l, list slot l, windowed problems, events, pinned results
+        self.lanes = []
+        for l in range(2):
+            L = {"qry16": torch.empty((self.Qs, dim), dtype=dtype, device=dev),
+                 "gal16": gal[l], "lists": lists[l]}
+            self.lanes.append(L)
+        # the second lane's private gallery copy is allocated on first use of the host path (device-only users and
+        # plans without exchange pay for one copy)
+        if self.lanes[0]["gal16"] is None:
+            self.lanes[0]["gal16"] = torch.empty((self.Gp, dim), dtype=dtype, device=dev)
+        for l, L in enumerate(self.lanes):
+            L["ev_q"] = torch.cuda.Event()
+            L["ev_win"] = [torch.cuda.Event() for _ in self.bounds]
+            L["end"] = torch.cuda.Event()
+            L["busy"] = False
+            L["host_val"] = torch.empty((me - mb, k), dtype=torch.float32).pin_memory()
+            L["host_idx"] = torch.empty((me - mb, k), dtype=torch.int32).pin_memory()
+            L["stream_calls"] = None
+        self._stream_layout = (sub_begin, subs, sub_total)
+        self._dev_end = torch.cuda.Event()
+        self._dev_used = False
+        self.calls = 0
+        # ---- one-shot problems (device-resident inputs live in lane 0; the list slots alternate)
+        self.probs = []
+        for (lv, li, _off) in lists:
+            pr = (N.TopkProblem * 1)()
+            self._fill(pr[0], self.lanes[0], self.lanes[0]["gal16"].data_ptr(), self.Gp, lv, li)
+            self.probs.append(pr)
+        self.ws = torch.empty(lib.leccr_sim_topk_workspace(self.probs[0], 1, 0), dtype=torch.uint8, device=dev)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.launches_per_search = 2 + (2 if P > 1 else 0)  # tensor-core pass, finalize (, barrier, merge)
+
+    # convenience views of lane 0 (the device-resident path)
+    @property
+    def qry16(self):
+        return self.lanes[0]["qry16"]
+
+    @property
+    def gal16(self):
+        return self.lanes[0]["gal16"]
+
+    # -------------------------------------------------------------------------------------------------
+    def _fill(self, p, L, cols_ptr, n_cols, lv, li):
+        p.rows16, p.cols16 = L["qry16"].data_ptr(), cols_ptr
+        p.ld_rows16 = p.ld_cols16 = self.D
+        p.n_rows, p.n_cols = self.Qs, n_cols
+        p.topk_val, p.topk_idx = lv.data_ptr(), li.data_ptr()
+
+    def _lane_calls(self, l):
+        """Windowed problems of lane l (built on first use)."""
+        L = self.lanes[l]
+        if L["stream_calls"] is None:
+            if L["gal16"] is None:
+                L["gal16"] = torch.empty((self.Gp, self.D), dtype=self.dtype, device=self.dev)
+            sub_begin, subs, sub_total = self._stream_layout
+            lv, li, _off = L["lists"]
+            W = len(self.bounds)
             calls = []
             for w, (b, e) in enumerate(self.bounds):
                 pr = (N.TopkProblem * 1)()
                 so = (N.TopkStream * 1)()
-                self._fill(pr[0], self.gal16.data_ptr() + b * dim * esz, e - b, lv, li)
+                self._fill(pr[0], L, L["gal16"].data_ptr() + b * self.D * 2, e - b, lv, li)
                 o = so[0]
                 o.phases = N.TOPK_LONG | N.TOPK_GEMM | (N.TOPK_INIT if w == 0 else 0) | (N.TOPK_FINALIZE if w == W - 1 else 0)
                 o.sub_begin, o.sub_count, o.sub_total = sub_begin[w], subs[w], sub_total
@@ -210,26 +273,13 @@ class GallerySearchPlan:
                 o.n_cols_total = self.Gp
                 o.workspace, o.workspace_bytes = self.ws_stream.data_ptr(), self.ws_stream.numel()
                 calls.append((pr, so))
-            self.stream_calls.append(calls)
-        self.copy_stream = torch.cuda.Stream(device=dev)
-        self.ev_q = torch.cuda.Event()
-        self.ev_win = [torch.cuda.Event() for _ in self.bounds]
-        mb, me = self.merge_rows
-        self.host_val = torch.empty((me - mb, k), dtype=torch.float32).pin_memory()
-        self.host_idx = torch.empty((me - mb, k), dtype=torch.int32).pin_memory()
-        self.launches_per_search = 2 + (2 if P > 1 else 0)  # tensor-core pass, finalize (, barrier, merge)
-
-    # -------------------------------------------------------------------------------------------------
-    def _fill(self, p, cols_ptr, n_cols, lv, li):
-        p.rows16, p.cols16 = self.qry16.data_ptr(), cols_ptr
-        p.ld_rows16 = p.ld_cols16 = self.D
-        p.n_rows, p.n_cols = self.Qs, n_cols
-        p.topk_val, p.topk_idx = lv.data_ptr(), li.data_ptr()
+            L["stream_calls"] = calls
+        return L["stream_calls"]
 
     def load_device(self, gallery_part, query_shard):
         """Device-resident inputs: rows `gallery_rows` of the gallery and `query_rows` of the queries."""
-        self.gal16.copy_(gallery_part)
-        self.qry16.copy_(query_shard)
+        self.lanes[0]["gal16"].copy_(gallery_part)
+        self.lanes[0]["qry16"].copy_(query_shard)
 
     # -------------------------------------------------------------------------------------------------
     def _merge(self, slot, host_path=False):
@@ -240,16 +290,16 @@ class GallerySearchPlan:
             return
         pb = self.pb
         tabs = self._tabs.get(slot)
+        lv, li, off = self.lanes[slot]["lists"]
         if pb is None:
-            dist.all_gather_into_tensor(self.gath_val, self.local[0][0], group=self.nccl_group)
-            dist.all_gather_into_tensor(self.gath_idx, self.local[0][1], group=self.nccl_group)
+            dist.all_gather_into_tensor(self.gath_val, lv, group=self.nccl_group)
+            dist.all_gather_into_tensor(self.gath_idx, li, group=self.nccl_group)
             if tabs is None:
                 tabs = (torch.tensor([self.gath_val[i].data_ptr() for i in range(self.P)], dtype=torch.int64, device=self.dev),
                         torch.tensor([self.gath_idx[i].data_ptr() for i in range(self.P)], dtype=torch.int64, device=self.dev))
                 self._tabs[slot] = tabs
         else:
             pb.barrier()
-            off = self.local[slot][2]
             if tabs is None:
                 tabs = (torch.tensor([pb.ptrs[r] + off for r in self.group], dtype=torch.int64, device=self.dev),
                         torch.tensor([pb.ptrs[r] + off + self.Qs * self.k * 4 for r in self.group], dtype=torch.int64,
@@ -268,63 +318,97 @@ class GallerySearchPlan:
     def search(self):
         """Inputs resident in HBM.  Returns (val [n, k], idx int32 [n, k] global gallery rows, (q0, q1)): the
         merged lists of queries [q0, q1) -- this rank's slice; the slices of all ranks tile the query set."""
-        slot = self.calls % len(self.local)
+        slot = self.calls % 2
         self.calls += 1
         N.check(self.lib.leccr_sim_topk(self.probs[slot], 1, self.D, self.fmt, self.k, 0, self.ws.data_ptr(),
                                         self.ws.numel(), N.stream_ptr()), "leccr_sim_topk")
         self._merge(slot)
+        self._dev_end.record(torch.cuda.current_stream())   # a later host search must not refill lane 0 under this one
+        self._dev_used = True
+        if self.P == 1:
+            lv, li, _ = self.lanes[slot]["lists"]
+            return lv, li, self._result_rows()
         return self.out_val, self.out_idx, self._result_rows()
 
     def _issue_host(self, gallery_host, queries_host):
         cur = torch.cuda.current_stream()
         cs = self.copy_stream
-        slot = self.calls % len(self.local)
+        l = self.calls % 2
         self.calls += 1
+        L = self.lanes[l]
+        calls = self._lane_calls(l)
+        if L["busy"]:
+            L["end"].synchronize()   # the search issued two calls ago: its pinned results are about to be reused
         qb, qe = self.query_rows
         gb, _ge = self.gallery_rows
-        cs.wait_stream(cur)  # the previous search has consumed the staging buffers
+        # the lane's buffers were last read by the search issued two calls ago (same stream order on every rank; its
+        # end lies behind the merge barrier every rank enters after its passes, so no mate is still reading them)
+        if L["busy"]:
+            cs.wait_event(L["end"])
+        else:
+            cs.wait_stream(cur)
+        if self._dev_used:
+            cs.wait_event(self._dev_end)
         with torch.cuda.stream(cs):
-            self.qry16.copy_(queries_host[qb:qe], non_blocking=True)
-            self.ev_q.record(cs)
+            L["qry16"].copy_(queries_host[qb:qe], non_blocking=True)
+            L["ev_q"].record(cs)
             for w, (b, e) in enumerate(self.bounds):
                 if self.xchg is None:
-                    self.gal16[b:e].copy_(gallery_host[gb + b: gb + e], non_blocking=True)
+                    L["gal16"][b:e].copy_(gallery_host[gb + b: gb + e], non_blocking=True)
                 else:
                     # my 1/S of the window over PCIe, then pushed to the mates' copies by the copy engines (NVLink)
                     sb, se = shard_range(e - b, self.shard, self.S)
                     sb, se = b + sb, b + se
-                    self.gal16[sb:se].copy_(gallery_host[gb + sb: gb + se], non_blocking=True)
+                    L["gal16"][sb:se].copy_(gallery_host[gb + sb: gb + se], non_blocking=True)
                     nbytes = (se - sb) * self.D * 2
-                    src = self.gal16.data_ptr() + sb * self.D * 2
+                    src = L["gal16"].data_ptr() + sb * self.D * 2
+                    base = self.xchg.slot_offset(l)
                     for r in self.mates:
                         if r == self.rank:
                             continue
-                        dst = self.xchg.ptrs[r] + self.xchg_base + sb * self.D * 2
+                        dst = self.xchg.ptrs[r] + base + sb * self.D * 2
                         _memcpy_async(dst, src, nbytes, cs.cuda_stream)
                     self.xchg.barrier()  # on the copy stream: everybody's pushes of this window have landed
-                self.ev_win[w].record(cs)
+                L["ev_win"][w].record(cs)
         st = cur.cuda_stream
-        cur.wait_event(self.ev_q)
-        for w, (pr, so) in enumerate(self.stream_calls[slot]):
-            cur.wait_event(self.ev_win[w])
+        cur.wait_event(L["ev_q"])
+        for w, (pr, so) in enumerate(calls):
+            cur.wait_event(L["ev_win"][w])
             N.check(self.lib.leccr_sim_topk_stream(pr, so, 1, self.D, self.fmt, self.k, st), "leccr_sim_topk_stream")
-        self._merge(slot, host_path=True)
-        self.host_val.copy_(self.out_val, non_blocking=True)
-        self.host_idx.copy_(self.out_idx, non_blocking=True)
+        self._merge(l, host_path=True)
+        if self.P == 1:
+            lv, li, _ = L["lists"]
+            L["host_val"].copy_(lv, non_blocking=True)
+            L["host_idx"].copy_(li, non_blocking=True)
+        else:
+            L["host_val"].copy_(self.out_val, non_blocking=True)
+            L["host_idx"].copy_(self.out_idx, non_blocking=True)
+        L["end"].record(cur)
+        L["busy"] = True
+        return SearchHandle(self, l)
 
-    @torch.no_grad()
-    def search_host(self, gallery_host, queries_host):
-        """HOST inputs: the whole [G, D] gallery and [Q, D] query arrays in (ideally pinned) host memory, 16-bit.
-        Each rank uploads only what it needs; returns pinned host tensors (val, idx, (q0, q1)) of its slice."""
+    def _check_host(self, gallery_host, queries_host):
         g = torch.as_tensor(gallery_host)
         q = torch.as_tensor(queries_host)
         if g.shape != (self.G, self.D) or q.shape != (self.Q, self.D) or g.dtype != self.dtype or q.dtype != self.dtype:
             raise N.LeccrError("search_host needs the [G, D] gallery and [Q, D] queries in the planned 16-bit dtype")
         if g.is_cuda or q.is_cuda:
             raise N.LeccrError("search_host takes host arrays; use load_device + search for device-resident inputs")
-        self._issue_host(g, q)
-        torch.cuda.current_stream().synchronize()
-        return self.host_val, self.host_idx, self._result_rows()
+        return g, q
+
+    @torch.no_grad()
+    def search_host_async(self, gallery_host, queries_host) -> SearchHandle:
+        """Issue a search of HOST arrays and return at once; `.result()` of the handle waits for it.  Two searches
+        may be in flight: the second one's windows cross PCIe (and NVLink) while the first is being ranked.  The
+        host arrays must stay unchanged until the handle's result has been taken."""
+        g, q = self._check_host(gallery_host, queries_host)
+        return self._issue_host(g, q)
+
+    @torch.no_grad()
+    def search_host(self, gallery_host, queries_host):
+        """HOST inputs: the whole [G, D] gallery and [Q, D] query arrays in (ideally pinned) host memory, 16-bit.
+        Each rank uploads only what it needs; returns pinned host tensors (val, idx, (q0, q1)) of its slice."""
+        return self.search_host_async(gallery_host, queries_host).result()
 
     @property
     def h2d_bytes(self):
@@ -335,7 +419,7 @@ class GallerySearchPlan:
 
     @property
     def d2h_bytes(self):
-        return self.host_val.numel() * 8
+        return self.lanes[0]["host_val"].numel() * 8
 
 
 def _memcpy_async(dst: int, src: int, nbytes: int, stream: int):

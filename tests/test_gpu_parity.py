@@ -692,6 +692,18 @@ def test_gallery_search_plan_device_and_host_paths_against_oracle():
     for c in (1, 5, 10):
         hits = int((idx[:, :c].long() == gt[:, None]).any(dim=1).sum())
         assert 100.0 * hits / Q == ev[f"img_r{c}"], (c, hits, ev)
+    # two searches in flight (the host path's two lanes): the second one's windows upload while the first is ranked
+    qry2 = torch.roll(qry, 7, dims=0).contiguous().pin_memory()
+    gal_p, qry_p = gal.pin_memory(), qry.pin_memory()
+    h1 = plan.search_host_async(gal_p, qry_p)
+    h2 = plan.search_host_async(gal_p, qry2)
+    v1, i1, _ = h1.result()
+    v1, i1 = v1.clone(), i1.clone()
+    v2, i2, _ = h2.result()
+    assert torch.equal(i1, idx) and torch.equal(v1, val)
+    assert torch.equal(i2, torch.roll(idx, 7, dims=0)) and torch.equal(v2, torch.roll(val, 7, dims=0))
+    h3 = plan.search_host_async(gal_p, qry_p)          # lane 0 again
+    assert torch.equal(h3.result()[1], idx)
     with pytest.raises(N.LeccrError):
         plan.search_host(gal.float(), qry.float())   # the plan's dtype is binding: no silent conversion
 

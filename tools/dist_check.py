@@ -145,6 +145,11 @@ for parts in ((2, 1) if world % 2 == 0 else (1,)):
     for rep in range(3):
         hv5, hi5, (h0, h1) = plan.search_host(gal5_h, qry5_h)
         plan_ok &= (h0, h1) == (r0, r1) and bool(torch.equal(hi5.cuda(), full5.idx[r0:r1])) and bool(torch.equal(hv5.cuda(), full5.val[r0:r1]))
+    handles = [plan.search_host_async(gal5_h, qry5_h) for _ in range(2)]   # two searches in flight (both lanes)
+    handles.append(plan.search_host_async(gal5_h, qry5_h))                 # a third: waits for the first lane
+    for hd in handles[1:]:
+        hv5, hi5, _ = hd.result()
+        plan_ok &= bool(torch.equal(hi5.cuda(), full5.idx[r0:r1])) and bool(torch.equal(hv5.cuda(), full5.val[r0:r1]))
     print(f"rank {rank}: GallerySearchPlan parts={parts} shards={plan.S} windows={len(plan.bounds)} exchange={plan.xchg is not None} "
           f"h2d {plan.h2d_bytes} B: {'PASS' if plan_ok else 'FAIL'}", flush=True)
 ok &= plan_ok
