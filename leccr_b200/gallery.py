@@ -274,6 +274,9 @@ class GallerySearchPlan:
                 o.workspace, o.workspace_bytes = self.ws_stream.data_ptr(), self.ws_stream.numel()
                 calls.append((pr, so))
             L["stream_calls"] = calls
+            one = (N.TopkProblem * 1)()
+            self._fill(one[0], L, L["gal16"].data_ptr(), self.Gp, lv, li)
+            L["one_shot"] = one
         return L["stream_calls"]
 
     def load_device(self, gallery_part, query_shard):
@@ -372,9 +375,17 @@ class GallerySearchPlan:
                 L["ev_win"][w].record(cs)
         st = cur.cuda_stream
         cur.wait_event(L["ev_q"])
-        for w, (pr, so) in enumerate(calls):
-            cur.wait_event(L["ev_win"][w])
-            N.check(self.lib.leccr_sim_topk_stream(pr, so, 1, self.D, self.fmt, self.k, st), "leccr_sim_topk_stream")
+        other = self.lanes[1 - l]
+        if other["busy"] and not other["end"].query():
+            # the previous search is still being ranked: by the time this one's pass can start its windows will
+            # have arrived, so it runs as ONE pass over the whole part (no per-window launches, warm thresholds)
+            cur.wait_event(L["ev_win"][-1])
+            N.check(self.lib.leccr_sim_topk(L["one_shot"], 1, self.D, self.fmt, self.k, 0, self.ws.data_ptr(),
+                                            self.ws.numel(), st), "leccr_sim_topk")
+        else:
+            for w, (pr, so) in enumerate(calls):
+                cur.wait_event(L["ev_win"][w])
+                N.check(self.lib.leccr_sim_topk_stream(pr, so, 1, self.D, self.fmt, self.k, st), "leccr_sim_topk_stream")
         self._merge(l, host_path=True)
         if self.P == 1:
             lv, li, _ = L["lists"]
