@@ -250,6 +250,19 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     ms_dev = e0.elapsed_time(e1)
     barrier()
+    # ---- roofline leg: the tensor-core launch alone, CUDA events on its stream
+    import ctypes
+
+    lib.leccr_profile_enable(1)
+    for _ in range(min(steps, 10)):
+        device_step()
+    torch.cuda.synchronize()
+    tot, cnt = ctypes.c_double(), ctypes.c_int()
+    lib.leccr_profile_read(ctypes.byref(tot), ctypes.byref(cnt))
+    lib.leccr_profile_enable(0)
+    gemm_ms = tot.value / max(1, cnt.value)
+    barrier()
+
     t0 = time.perf_counter()
     e0.record()
     prev = None
@@ -264,19 +277,6 @@ def run_ours(args, rank, world, local_rank):
     wall_e2e = (time.perf_counter() - t0) * 1e3
     ms_e2e = e0.elapsed_time(e1)
     clocks = sampler.stop()
-
-    # ---- roofline leg: the tensor-core launch alone, CUDA events on its stream
-    import ctypes
-
-    lib.leccr_profile_enable(1)
-    for _ in range(min(steps, 5)):
-        device_step()
-    torch.cuda.synchronize()
-    tot, cnt = ctypes.c_double(), ctypes.c_int()
-    lib.leccr_profile_read(ctypes.byref(tot), ctypes.byref(cnt))
-    lib.leccr_profile_enable(0)
-    gemm_ms = tot.value / max(1, cnt.value)
-    barrier()
 
     ms_dev, ms_e2e, gemm_ms_max, wall_e2e = max_over_ranks([ms_dev, ms_e2e, gemm_ms, wall_e2e])
     h2d = max_over_ranks([float(plan.h2d_bytes)])[0]
