@@ -916,3 +916,37 @@ def test_recall_only_kernel_variants(n_per, d, dtype):
     plan = leccr_b200.FusedEvalPlan(n, n * n_per, d, rs.txt2img, rs.img2txt, lists=False) if dtype == "f32" else None
     if plan is not None:
         assert_ev_equal(plan.run(image, text), want)
+
+
+def test_cfg5_full_size_search_sampled_rows_and_partition_property():
+    """BASELINE configs[4] at FULL size on one GPU (1,000,000 x 100,000, bf16, top-10, 40 ms): 512 sampled queries
+    against fp32 matmul + top-k of the same bf16 inputs, Recall@1/5/10 of the sample equal, the windowed host path
+    bit-identical to the one-shot pass, and the size-independent partition property: the top-10 of the whole gallery
+    == the merge of the top-10 lists of its two halves (what the multi-GPU layout relies on)."""
+    from leccr_b200 import sharding
+
+    G, Q = 1_000_000, 100_000
+    gal, qry, gt = synth.cfg5_gallery(G, Q, device="cuda")
+    plan = leccr_b200.GallerySearchPlan(G, Q, 256, k=10)
+    plan.load_device(gal, qry)
+    val, idx, rows = plan.search()
+    assert rows == (0, Q)
+    val, idx = val.clone(), idx.clone()
+    samp = torch.linspace(0, Q - 1, 512, device="cuda").long()
+    ref = qry[samp].float() @ gal.float().t()
+    rv, ri = ref.topk(10, dim=1)
+    got_i = idx[samp].long()
+    true_at_got = torch.gather(ref, 1, got_i).sort(dim=1, descending=True).values
+    assert (rv - true_at_got).abs().max() < 1e-3
+    assert (got_i == ri).all(dim=1).float().mean() > 0.99
+    for c in (1, 5, 10):
+        assert int((got_i[:, :c] == gt[samp, None]).any(1).sum()) == int((ri[:, :c] == gt[samp, None]).any(1).sum())
+    del ref
+    hv, hi, _ = plan.search_host(gal.cpu().pin_memory(), qry.cpu().pin_memory())
+    assert torch.equal(hi.cuda(), idx) and torch.equal(hv.cuda(), val)
+    halves = []
+    for b, e in ((0, G // 2), (G // 2, G)):
+        r, = ops.sim_topk([(ops.prep(qry[samp].contiguous(), want_stats=False), ops.prep(gal[b:e], want_stats=False), None)], k=10)
+        halves.append((r.val, r.idx.long() + b))
+    mv, mi = sharding.merge_topk(torch.stack([h[0] for h in halves]), torch.stack([h[1] for h in halves]), 10)
+    assert torch.equal(mi, got_i) and torch.equal(mv, val[samp])
