@@ -444,7 +444,13 @@ def contrastive_leg(torch, dist, leccr_b200, synth, dev, rank, world, peak, max_
         # pays): device-bound time, the eager figure above is bound by the host issuing ~12 launches through autograd
         graph_us = None
         cap_ok, g = True, None
+        from leccr_b200 import peer as _peer_mod
+
+        # with the NCCL fallback (no peer memory) the step contains NCCL collectives: do not capture those here
+        peer_path = world == 1 or any(k[0] == "itc" and v is not None for k, v in _peer_mod._cache.items())
         try:
+            if not peer_path:
+                raise RuntimeError("peer-memory exchange inactive: the step is not captured")
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
