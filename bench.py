@@ -307,8 +307,11 @@ def run_ours(args, rank, world, local_rank):
         "config": CONFIG,
         "layout": {"query_shards": plan.S, "gallery_parts": plan.P, "queries_per_rank": plan.Qs,
                    "gallery_rows_per_rank": plan.Gp,
-                   "exchange": "none" if plan.P == 1 else "top-10 lists merged over NVLink peer memory "
-                               "(leccr_peer_barrier + leccr_topk_merge_peers)",
+                   "exchange": "none" if plan.P == 1 else (
+                       "top-10 lists merged over NVLink peer memory (leccr_peer_barrier + leccr_topk_merge_peers)"
+                       if plan.pb is not None else
+                       "top-10 lists all-gathered with NCCL inside each shard's sub-group, merged by leccr_topk_merge_peers "
+                       "(peer memory unavailable)"),
                    "host_path_windows": len(plan.bounds), "host_path_gallery_exchange": plan.xchg is not None},
         "e2e": {"value": N_QUERY * steps / (ms_e2e * 1e-3), "unit": "queries/s",
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(plan.d2h_bytes),
