@@ -77,9 +77,12 @@ __device__ __forceinline__ uint32_t mbar_try_wait_hint(uint64_t* bar, uint32_t p
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag, uint32_t backoff_ns = 0) {
   if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (backoff_ns) __nanosleep(backoff_ns);
-    if (++spins > 100000000u) {
+  // backoff_ns > 0: the wait is expected to be long (an epilogue warp waiting for the next accumulator, the producer
+  // for a free stage): park the thread in hardware with a suspend-time hint instead of polling -- the polling loop
+  // of the epilogue warps alone executed 300 M try_waits per cfg5 launch (issue slots and power on a part that runs
+  // this kernel under its power cap)
+  while (!(backoff_ns ? mbar_try_wait_hint(bar, parity, 2000u) : mbar_try_wait(bar, parity))) {
+    if (++spins > (backoff_ns ? 4000000u : 100000000u)) {
       printf("leccr: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag,
              (int)blockIdx.x, (int)threadIdx.x, parity);
       __trap();
