@@ -19,8 +19,9 @@ problem is solved at every N: strong scaling.  A "step" is one whole search = 10
           gallery crosses PCIe in windows on a copy stream while the tensor cores rank what has arrived; at
           N > 1 every gallery row crosses PCIe once per node (each rank uploads 1/N of the gallery and pushes
           it to the ranks sharing its part over NVLink); the merged top-10 lists are copied back to the host.
-  roofline : the tensor-core launch (sim_gemm_kernel<EpiTopK>) timed alone with CUDA events on its stream
-          (leccr_profile_*), algorithmic FLOPs 2 * Qs * Gp * D of this rank's launch, vs MEASURED_PEAKS.json.
+  roofline : the tensor-core launches (sim_gemm_kernel<EpiTopK>) of the timed steps themselves, bracketed by CUDA
+          events on their stream (leccr_profile_*, no synchronisation inside the loop), algorithmic FLOPs
+          2 * Qs * Gp * D of this rank's launch, vs MEASURED_PEAKS.json.
   multi_gpu_check : parity guard inside the run (the GPU test box has one GPU): merged lists of sampled queries vs
           a single pass over the whole gallery and vs fp32 matmul + top-k; get_contrastive_loss on the real
           exchange vs the fp64 oracle on the concatenated batch.
@@ -242,6 +243,11 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # roofline: the tensor-core launches of the timed steps themselves, bracketed by CUDA events on their own
+    # stream (recorded without synchronising, resolved after the loop)
+    import ctypes
+
+    lib.leccr_profile_enable(1)
     barrier()
     e0.record()
     for _ in range(steps):
@@ -249,14 +255,6 @@ def run_ours(args, rank, world, local_rank):
     e1.record()
     barrier()
     ms_dev = e0.elapsed_time(e1)
-    barrier()
-    # ---- roofline leg: the tensor-core launch alone, CUDA events on its stream
-    import ctypes
-
-    lib.leccr_profile_enable(1)
-    for _ in range(min(steps, 10)):
-        device_step()
-    torch.cuda.synchronize()
     tot, cnt = ctypes.c_double(), ctypes.c_int()
     lib.leccr_profile_read(ctypes.byref(tot), ctypes.byref(cnt))
     lib.leccr_profile_enable(0)

@@ -62,8 +62,9 @@ const char* leccr_last_cuda_error(void);
 int leccr_abi_version(void);
 /* LECCR_OK when the current CUDA device can run the kernels (cc 10.x). */
 int leccr_check_device(void);
-/* Measurement aid (bench.py roofline leg): while enabled, every tensor-core launch is bracketed with
- * CUDA events on its stream and synchronised; read returns the accumulated device time and count. */
+/* Measurement aid (bench.py roofline figure): while enabled, every tensor-core launch is bracketed with
+ * CUDA events on its own stream (no synchronisation: it can stay on inside a timed loop; not under CUDA-graph
+ * capture); read waits for the recorded launches and returns their accumulated device time and count. */
 void leccr_profile_enable(int on);
 int leccr_profile_read(double* total_ms, int* launches);
 

@@ -127,10 +127,31 @@ int fill_problem(SimProblem& P, const void* rows16, int64_t ld_rows, const void*
 
 // Optional timing of the tensor-core launches with CUDA events on the launch stream (bench.py's
 // roofline leg).  Off by default; when on, every sim_gemm_kernel launch is bracketed.
+// Development aid (leccr_profile_*): CUDA events around every tensor-core launch, recorded on the launch's own
+// stream WITHOUT synchronising, so a timed loop can keep them on; leccr_profile_read resolves them.
 bool g_profile = false;
-cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+struct EventPair {
+  cudaEvent_t begin, end;
+};
+constexpr int kProfilePairs = 256;
+EventPair g_pairs[kProfilePairs];
+int g_pairs_made = 0, g_pairs_used = 0;
 double g_profile_ms = 0.0;
 int g_profile_launches = 0;
+
+cudaError_t profile_resolve() {
+  for (int i = 0; i < g_pairs_used; ++i) {
+    cudaError_t e = cudaEventSynchronize(g_pairs[i].end);
+    if (e != cudaSuccess) return e;
+    float ms = 0.f;
+    e = cudaEventElapsedTime(&ms, g_pairs[i].begin, g_pairs[i].end);
+    if (e != cudaSuccess) return e;
+    g_profile_ms += ms;
+    ++g_profile_launches;
+  }
+  g_pairs_used = 0;
+  return cudaSuccess;
+}
 
 // Development aid (LECCR_STAGE_PROFILE=1): events between the launches of one C-ABI call, printed by
 // leccr_profile_read.  Not used by the product path.
@@ -191,23 +212,20 @@ int launch_gemm(const SimLaunch& L, const typename Epi::Params& EP, cudaStream_t
   }
   if (L.n_items <= 0) return LECCR_OK;
   const int grid = std::min(L.n_items, num_sms());
+  EventPair* pair = nullptr;
   if (g_profile) {
-    if (g_ev0 == nullptr) {
-      CUDA_TRY(cudaEventCreate(&g_ev0));
-      CUDA_TRY(cudaEventCreate(&g_ev1));
+    if (g_pairs_used == kProfilePairs) CUDA_TRY(profile_resolve());  // pool exhausted: drain (synchronises)
+    if (g_pairs_used == g_pairs_made) {
+      CUDA_TRY(cudaEventCreate(&g_pairs[g_pairs_made].begin));
+      CUDA_TRY(cudaEventCreate(&g_pairs[g_pairs_made].end));
+      ++g_pairs_made;
     }
-    CUDA_TRY(cudaEventRecord(g_ev0, stream));
+    pair = &g_pairs[g_pairs_used++];
+    CUDA_TRY(cudaEventRecord(pair->begin, stream));
   }
   kern<<<grid, gemm_threads(Epi::kWGs), smem, stream>>>(L, EP);
   LAUNCH_CHECK("sim_gemm_kernel");
-  if (g_profile) {
-    CUDA_TRY(cudaEventRecord(g_ev1, stream));
-    CUDA_TRY(cudaEventSynchronize(g_ev1));
-    float ms = 0.f;
-    CUDA_TRY(cudaEventElapsedTime(&ms, g_ev0, g_ev1));
-    g_profile_ms += ms;
-    ++g_profile_launches;
-  }
+  if (pair != nullptr) CUDA_TRY(cudaEventRecord(pair->end, stream));
   return LECCR_OK;
 }
 
@@ -237,9 +255,11 @@ void leccr_profile_enable(int on) {
   g_profile = on != 0;
   g_profile_ms = 0.0;
   g_profile_launches = 0;
+  g_pairs_used = 0;
 }
 int leccr_profile_read(double* total_ms, int* launches) {
   if (total_ms == nullptr || launches == nullptr) return LECCR_ERR_ARG;
+  CUDA_TRY(profile_resolve());
   *total_ms = g_profile_ms;
   *launches = g_profile_launches;
   prof_dump();
