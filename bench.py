@@ -496,6 +496,21 @@ def contrastive_leg(torch, dist, leccr_b200, synth, dev, rank, world, peak, max_
                      "frac_of_peak": flops / us / 1e6 / peak,
                      "includes": "cast + exchange (peer-memory push + barrier), forward, backward of the local rows, "
                                  "through torch.autograd; idx labels"}
+    if world == 1:
+        # the reference's own way on the host cores, beside it: fp32 matmul + cross entropy + autograd on
+        # the concatenated 4096-row batch, rank 0's 512-row share of the gradients (oracle port of models/xvlm.py:260-292)
+        cb = synth.cfg3_itc(4096, DIM, seed=7)
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        oracle.contrastive_loss_and_grads(cb.image, cb.text, cb.temp, cb.idx, rank=0, batch_size=512)
+        best = float("inf")
+        for _ in range(5):
+            t0 = time.perf_counter()
+            oracle.contrastive_loss_and_grads(cb.image, cb.text, cb.temp, cb.idx, rank=0, batch_size=512)
+            best = min(best, time.perf_counter() - t0)
+        out["cpu_baseline"] = {"us_per_step": best * 1e6, "cores": threads, "kind": "port",
+                               "sample": "N = 4096 concatenated rows, D = 256, fp32, idx labels, forward + autograd "
+                                         "backward, best of 5 after one warm-up"}
     chk["all_ranks_ok"] = all_ok(chk["ok"])
     from leccr_b200 import peer
 
