@@ -950,3 +950,73 @@ def test_cfg5_full_size_search_sampled_rows_and_partition_property():
         halves.append((r.val, r.idx.long() + b))
     mv, mi = sharding.merge_topk(torch.stack([h[0] for h in halves]), torch.stack([h[1] for h in halves]), 10)
     assert torch.equal(mi, got_i) and torch.equal(mv, val[samp])
+
+
+# ----------------------------------------------------------------------------- randomised shapes (hypothesis)
+from hypothesis import given, settings, strategies as st
+
+
+@settings(max_examples=16, deadline=None, derandomize=True)
+@given(n=st.integers(1, 420), per=st.integers(1, 4), d8=st.integers(1, 40), k=st.integers(1, 16),
+       precision=st.sampled_from(["f16", "bf16"]), dup=st.booleans())
+def test_property_random_shapes_recall_and_lists(n, per, d8, k, precision, dup):
+    """Any set size (not a multiple of the 128 x 256 tile), any D % 8 == 0, any k <= 16, either operand type,
+    optionally with duplicated gallery rows (exact ties): the Recall dict equals the reference's count formulation
+    through the list path AND the Recall-only path, and the lists hold the k best scores."""
+    d = 8 * d8
+    rs = synth.retrieval_set(n, per, d=d, seed=1000 * n + 10 * d8 + per)
+    img, txt = rs.image, rs.text
+    if dup and n > 1:   # the last image repeats the first: ties between their texts' scores
+        img = img.clone()
+        img[-1] = img[0]
+    i2t, t2i = oracle.score_matrices(img, txt)
+    want = oracle.itm_eval_by_count(i2t, t2i, rs.txt2img, rs.img2txt)
+    ev, topk = leccr_b200.fused_eval(img, txt, rs.txt2img, rs.img2txt, k=k, precision=precision)
+    assert_ev_equal(ev, want)
+    assert_ev_equal(leccr_b200.fused_eval(img, txt, rs.txt2img, rs.img2txt, precision=precision, return_topk=False), want)
+    tol = (6e-3 if precision == "bf16" else 8e-4) * (3.0 if d < 64 else 1.0)
+    for name, S in (("i2t", i2t), ("t2i", np.ascontiguousarray(t2i))):
+        val, idx = topk[name][0].cpu().numpy(), topk[name][1].cpu().numpy().astype(np.int64)
+        kk = min(k, S.shape[1])
+        wv = np.sort(S, axis=1)[:, ::-1][:, :kk]
+        assert np.abs(val[:, :kk] - wv).max() < tol
+        assert np.abs(np.take_along_axis(S, idx[:, :kk], 1) - wv).max() < 2 * tol
+        for r in range(0, S.shape[0], max(1, S.shape[0] // 16)):
+            assert len(set(idx[r, :kk].tolist())) == kk, "a column appears twice in a list"
+
+
+@settings(max_examples=12, deadline=None, derandomize=True)
+@given(b=st.integers(1, 300), d8=st.integers(1, 32), labels=st.sampled_from(["none", "unique", "dups"]),
+       temp=st.sampled_from([0.05, 0.07, 0.5]))
+def test_property_contrastive_random_batches(b, d8, labels, temp):
+    """get_contrastive_loss for any batch size and width, with arange labels (idx=None), unique ids, or ids with
+    duplicates (several positives per row, models/xvlm.py:283-292).  The kernels compute with fp16 operands and
+    fp32 accumulation, so the tight check is against the reference's formula in fp64 ON THE fp16-ROUNDED OPERANDS
+    (loss 2e-4, gradients and dtemp 2e-3: the gradient strip is stored in fp16); against the unrounded fp64 answer
+    the north_star tolerance (loss 1e-3, gradients 2e-3) is asserted from D = 128 up -- small batches at small D
+    amplify the operand rounding through the cancellation in dtemp (0.6 % at B = 68, D = 72, also in fp64)."""
+    d = 8 * d8
+    g = torch.Generator().manual_seed(b * 100 + d8)
+    a32 = torch.nn.functional.normalize(torch.randn(b, d, generator=g), dim=-1)
+    b32 = torch.nn.functional.normalize(a32 + 0.5 * torch.randn(b, d, generator=g), dim=-1)
+    idx = None
+    if labels == "unique":
+        idx = torch.randperm(10 * b + 5, generator=g)[:b]
+    elif labels == "dups":
+        idx = torch.randint(0, max(1, b // 2), (b,), generator=g)
+    me = types.SimpleNamespace(embed_dim=d, temp=torch.nn.Parameter(torch.tensor(temp, device="cuda")))
+    a = a32.cuda().requires_grad_(True)
+    bb = b32.cuda().requires_grad_(True)
+    loss = leccr_b200.get_contrastive_loss(me, a, bb, None if idx is None else idx.cuda())
+    loss.backward()
+    refs = [(oracle.contrastive_loss_and_grads(a32.half().float(), b32.half().float(), temp, idx, dtype=torch.float64),
+             2e-4, 2e-3, 2e-3)]
+    if d >= 128:
+        refs.append((oracle.contrastive_loss_and_grads(a32, b32, temp, idx, dtype=torch.float64), 1e-3, 2e-3, None))
+    for (rl, ra, rb, rt), tl, tg, tt in refs:
+        assert abs(loss.item() - rl.item()) <= tl * abs(rl.item()) + 1e-5, (loss.item(), rl.item())
+        for got, ref in ((a.grad, ra), (bb.grad, rb)):
+            err = (got.cpu().double() - ref).norm()
+            assert err <= tg * ref.norm() + 1e-4, (err.item(), ref.norm().item())
+        if tt is not None:
+            assert abs(me.temp.grad.item() - rt.item()) <= tt * abs(rt.item()) + 1e-4, (me.temp.grad.item(), rt.item())
