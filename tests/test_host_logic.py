@@ -310,3 +310,59 @@ def test_new_entries_fail_loudly_without_a_gpu():
         leccr_b200.normalize_rows(torch.randn(4, 8))
     with pytest.raises(N.LeccrError):
         leccr_b200.FeatureGallery(64)
+
+
+def test_property_gallery_layout_and_merge_random():
+    """Randomised (hypothesis) versions of the host-logic checks: window bounds and slot counts for any part size,
+    shard ranges for any (n, world), and the k-way merge of partial top-k lists against a global top-k."""
+    from hypothesis import given, settings, strategies as st
+
+    from leccr_b200.gallery import _pick_windows, _window_bounds
+    from leccr_b200.sharding import merge_topk, shard_range
+
+    @settings(max_examples=200, deadline=None, derandomize=True)
+    @given(part=st.integers(1, 3_000_000), w=st.integers(1, 8))
+    def bounds(part, w):
+        b = _window_bounds(part, w)
+        assert b[0][0] == 0 and b[-1][1] == part and 1 <= len(b) <= w
+        assert all(e0 == b1 for (_, e0), (b1, _) in zip(b[:-1], b[1:]))
+        assert all(e > s for s, e in b) and all(s % 256 == 0 for s, _ in b)
+
+    @settings(max_examples=200, deadline=None, derandomize=True)
+    @given(rb=st.integers(1, 4000), part=st.integers(1, 3_000_000))
+    def slots(rb, part):
+        subs = _pick_windows(rb, part)
+        assert 1 <= len(subs) <= 4 and all(s >= 1 for s in subs) and sum(subs) <= 8
+        assert len(subs) == 1 or part // ((1 << len(subs)) - 1) >= 32768
+
+    @settings(max_examples=200, deadline=None, derandomize=True)
+    @given(n=st.integers(0, 2_000_000), world=st.integers(1, 16))
+    def shards(n, world):
+        spans = [shard_range(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+        assert max(e - s for s, e in spans) - min(e - s for s, e in spans) <= 1
+
+    @settings(max_examples=40, deadline=None, derandomize=True)
+    @given(q=st.integers(1, 40), parts=st.integers(1, 8), per=st.integers(1, 60), k=st.integers(1, 16), seed=st.integers(0, 10**6))
+    def merge(q, parts, per, k, seed):
+        g = torch.Generator().manual_seed(seed)
+        S = torch.randn(q, parts * per, generator=g)
+        vals, idxs = [], []
+        for p in range(parts):
+            kk = min(k, per)
+            v, i = S[:, p * per:(p + 1) * per].topk(kk, dim=1)
+            if kk < k:   # short lists are padded the way the kernels pad them
+                v = torch.cat([v, torch.full((q, k - kk), float("-inf"))], 1)
+                i = torch.cat([i, torch.full((q, k - kk), -1, dtype=i.dtype)], 1)
+            vals.append(v)
+            idxs.append(torch.where(i >= 0, i + p * per, i))
+        mv, mi = merge_topk(torch.stack(vals), torch.stack(idxs), k)
+        kk = min(k, parts * per)
+        wv, wi = S.topk(kk, dim=1)
+        assert torch.equal(mv[:, :kk], wv) and torch.equal(mi[:, :kk].long(), wi)
+
+    bounds()
+    slots()
+    shards()
+    merge()
