@@ -195,7 +195,10 @@ int leccr_sim_topk_stream(const leccr_topk_problem* probs, const leccr_topk_stre
  *   out          : [6] loss, dloss/dtemp, loss_i2t, loss_t2i, dloss_i2t/dtemp, dloss_t2i/dtemp
  *   lse2 / rcnt  : [2][n] per-row log2-domain log-sum-exp and 1/|positives| (saved for backward)
  * Backward (local rows [row_begin, row_begin + row_count) only):
- *   aT16, bT16   : [D][ldT] transposed operands (leccr_transpose16)
+ *   aT16, bT16   : ignored (may be null): the gradient products dA = G' B, dB = G'^T A read the gathered rows
+ *                  as MN-major tensor-core operands (the contraction index is the row index of a16 / b16, no
+ *                  transposed copy).  Only with LECCR_BWD_MN=0 (development comparison) they are the [D][ldT]
+ *                  transposed operands (leccr_transpose16)
  *   grad_out     : device scalar dL/dloss
  *   dA, dB       : [row_count][D] fp32 (overwritten)
  * ------------------------------------------------------------------------------------------ */

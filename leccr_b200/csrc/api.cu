@@ -65,12 +65,24 @@ int num_sms() {
   return sms;
 }
 
+// cuTensorMapEncodeTiled is a driver entry point: it needs the device's primary context current on the calling
+// thread.  A thread whose first CUDA call is ours (torch's autograd thread running a backward that starts with a
+// tensor-core launch) has none yet -- runtime calls that only query the device do not bind it.
+void bind_primary_context() {
+  thread_local bool bound = false;
+  if (!bound) {
+    cudaFree(nullptr);
+    bound = true;
+  }
+}
+
 // 2-D K-major 16-bit operand [n][K] (ld elements) with a {BK, box_rows} box and 128-byte swizzle.
 int make_tmap(CUtensorMap* tm, const void* base, int64_t n, int64_t K, int64_t ld, int fmt, int box_rows, int bk = BK) {
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld & 7) != 0) return LECCR_ERR_ALIGN;
   if (n <= 0 || K <= 0 || ld < K) return LECCR_ERR_ARG;
   EncodeTiledFn enc = get_encode_fn();
   if (enc == nullptr) return LECCR_ERR_DRIVER;
+  bind_primary_context();
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(n)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(box_rows)};
@@ -81,6 +93,28 @@ int make_tmap(CUtensorMap* tm, const void* base, int64_t n, int64_t K, int64_t l
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_cuda_err, sizeof(g_cuda_err), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return LECCR_ERR_DRIVER;
+  }
+  return LECCR_OK;
+}
+
+// The MN-major column operand of a product whose contraction index is the slow axis of the source: row-major
+// [K rows][n_mn] (ld elements), {64 elements, BK rows} boxes, 128-byte swizzle (gemm_sm100.cuh kBMN).
+int make_tmap_mn(CUtensorMap* tm, const void* base, int64_t k_rows, int64_t n_mn, int64_t ld, int fmt) {
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld & 7) != 0) return LECCR_ERR_ALIGN;
+  if (k_rows <= 0 || n_mn <= 0 || ld < n_mn) return LECCR_ERR_ARG;
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return LECCR_ERR_DRIVER;
+  bind_primary_context();
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(n_mn), static_cast<cuuint64_t>(k_rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(BK)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, fmt == LECCR_FMT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                   2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "cuTensorMapEncodeTiled (MN-major) failed with CUresult %d", (int)r);
     return LECCR_ERR_DRIVER;
   }
   return LECCR_OK;
@@ -125,8 +159,6 @@ int fill_problem(SimProblem& P, const void* rows16, int64_t ld_rows, const void*
   return LECCR_OK;
 }
 
-// Optional timing of the tensor-core launches with CUDA events on the launch stream (bench.py's
-// roofline leg).  Off by default; when on, every sim_gemm_kernel launch is bracketed.
 // Development aid (leccr_profile_*): CUDA events around every tensor-core launch, recorded on the launch's own
 // stream WITHOUT synchronising, so a timed loop can keep them on; leccr_profile_read resolves them.
 bool g_profile = false;
@@ -194,10 +226,10 @@ constexpr int stages_for() {
   return sim_gemm_smem_bytes<Epi, 4, kBK, kARes>() <= 232448 ? 4 : 3;
 }
 
-template <class Epi, int kBK = BK, bool kARes = false>
+template <class Epi, int kBK = BK, bool kARes = false, bool kBMN = false>
 int launch_gemm(const SimLaunch& L, const typename Epi::Params& EP, cudaStream_t stream) {
   constexpr int kStages = stages_for<Epi, kBK, kARes>();
-  auto kern = sim_gemm_kernel<Epi, kStages, kBK, kARes>;
+  auto kern = sim_gemm_kernel<Epi, kStages, kBK, kARes, kBMN>;
   constexpr size_t smem = sim_gemm_smem_bytes<Epi, kStages, kBK, kARes>();
   static_assert(smem <= 232448, "exceeds the 227 KB shared memory limit of sm_100");
   // function attributes are per device: one flag per device ordinal (a process may drive several GPUs)
@@ -406,6 +438,9 @@ struct StoreProblem {
   float* out;
   int64_t ld_out;
   float* parts;  // split-K partial planes (nullptr when k_splits <= 1)
+  // cols16 is the row-major [K][n_cols] source itself (MN-major operand) instead of a K-major [n_cols][K] matrix:
+  // no transposed copy of an operand whose contraction index is its row index (all problems of a launch alike)
+  bool cols_mn;
 };
 
 static int launch_store(const StoreProblem* sp, int n_prob, int K, int fmt, float scale, const float* scale_dev,
@@ -441,8 +476,14 @@ static int launch_store(const StoreProblem* sp, int n_prob, int K, int fmt, floa
         tiles += ((sp[q].n_rows + BM - 1) / BM) * ((sp[q].n_cols + BN - 1) / BN);
       pl = plan_problem(sp[p].n_cols, 0, sp[p].n_rows, auto_tiles_per_chunk(tiles, 1));
     }
-    int rc = fill_problem(L.prob[p], sp[p].rows16, sp[p].ld_rows, sp[p].cols16, sp[p].ld_cols, sp[p].n_rows,
-                          sp[p].n_cols, K, fmt, pl, item_base);
+    if (sp[p].cols_mn != sp[0].cols_mn) return LECCR_ERR_ARG;
+    int rc = fill_problem(L.prob[p], sp[p].rows16, sp[p].ld_rows, sp[p].cols_mn ? sp[p].rows16 : sp[p].cols16,
+                          sp[p].cols_mn ? sp[p].ld_rows : sp[p].ld_cols, sp[p].n_rows, sp[p].cols_mn ? sp[p].n_rows : sp[p].n_cols,
+                          K, fmt, pl, item_base);
+    if (rc == LECCR_OK && sp[p].cols_mn) {
+      rc = make_tmap_mn(&L.prob[p].tm_cols, sp[p].cols16, K, sp[p].n_cols, sp[p].ld_cols, fmt);
+      L.prob[p].n_cols = static_cast<int>(sp[p].n_cols);
+    }
     if (rc != LECCR_OK) return rc;
     item_base += pl.row_blocks * pl.n_chunks;
     EP.out[p] = split ? sp[p].parts : sp[p].out;
@@ -453,7 +494,7 @@ static int launch_store(const StoreProblem* sp, int n_prob, int K, int fmt, floa
     EP.split_stride[p] = split ? sp[p].n_rows * sp[p].ld_out : 0;
   }
   L.n_items = item_base;
-  int rc = launch_gemm<EpiStore>(L, EP, stream);
+  int rc = sp[0].cols_mn ? launch_gemm<EpiStore, BK, false, true>(L, EP, stream) : launch_gemm<EpiStore>(L, EP, stream);
   if (rc != LECCR_OK) return rc;
   bool prod_done = false;
   if (split) {
@@ -1417,6 +1458,16 @@ static int infonce_fwd_strips(const void* a16, const void* b16, int64_t ld16, co
 
 static int64_t round_up8(int64_t x) { return (x + 7) & ~static_cast<int64_t>(7); }
 
+// The gradient products read the gathered operands as MN-major column operands (no transposed copies);
+// LECCR_BWD_MN=0 keeps the K-major products over transposed copies (development comparison).
+static bool bwd_mn_major() {
+  static const bool on = [] {
+    const char* e = getenv("LECCR_BWD_MN");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return on;
+}
+
 // split-K factor of the gradient products: fill the machine, at least 2 K-chunks per split
 static int bwd_splits(int k_chunks, int row_blocks) {
   const int want = std::max(1, num_sms() / std::max(1, 2 * row_blocks));
@@ -1454,7 +1505,8 @@ static int infonce_bwd_impl(const void* a16, const void* b16, int64_t ld16, cons
                             const float* grad_out, float* dA, float* dB, void* workspace, size_t workspace_bytes,
                             const float* prod_b, float* prod_out, int one_dir, leccr_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (a16 == nullptr || b16 == nullptr || aT16 == nullptr || bT16 == nullptr || temp == nullptr ||
+  const bool mn = bwd_mn_major();
+  if (a16 == nullptr || b16 == nullptr || (!mn && (aT16 == nullptr || bT16 == nullptr)) || temp == nullptr ||
       lse2 == nullptr || rcnt == nullptr || dA == nullptr || dB == nullptr || n <= 0 || D <= 0 || bad_fmt(fmt) ||
       row_begin < 0 || row_count <= 0 || row_begin + row_count > n)
     return LECCR_ERR_ARG;
@@ -1512,8 +1564,8 @@ static int infonce_bwd_impl(const void* a16, const void* b16, int64_t ld16, cons
     float* parts0 = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 2 * strip_bytes);
     float* parts1 = parts0 + static_cast<size_t>(splits) * row_count * D;
     StoreProblem sp[2] = {
-        {strip0, bT16, ldS, ldT, row_count, D, dA, D, parts0},
-        {strip1, aT16, ldS, ldT, row_count, D, dB, D, parts1},
+        {strip0, mn ? b16 : bT16, ldS, mn ? ld16 : ldT, row_count, D, dA, D, parts0, mn},
+        {strip1, mn ? a16 : aT16, ldS, mn ? ld16 : ldT, row_count, D, dB, D, parts1, mn},
     };
     rc = launch_store(sp, 2, static_cast<int>(n), fmt, 1.0f / ((one_dir ? 1.0f : 2.0f) * static_cast<float>(n)), grad_out, temp,
                       splits, stream, grad_out, prod_b, prod_out);
@@ -1747,7 +1799,7 @@ int leccr_itc_backward(const void* both16, const int64_t* idx_all, int64_t n, in
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   void* aT = ws;
   void* bT = ws + tr;
-  {
+  if (!bwd_mn_major()) {
     dim3 grid(static_cast<unsigned>((ldT + 31) / 32), static_cast<unsigned>((D + 31) / 32), 2);
     dim3 block(32, 8);
     transpose16_pair_kernel<<<grid, block, 0, stream>>>(both, both + D, 2 * D, (int)n, D, static_cast<uint16_t*>(aT),
@@ -1830,15 +1882,18 @@ int leccr_caploss_bwd(const float* L, const uint8_t* amax, const float* stats, c
   LAUNCH_CHECK("capgrad_kernel");
   int rc = leccr_transpose16(G, nb, b, b8, GT, nb8, stream_);      // [nB][B] -> [B][nB8]
   if (rc != LECCR_OK) return rc;
-  rc = leccr_transpose16(txt16, B, D, ld_txt, TT, b8, stream_);   // [B][D]  -> [D][B8]
-  if (rc != LECCR_OK) return rc;
-  rc = leccr_transpose16(cap16, nb, D, ld_cap, CT, nb8, stream_); // [nB][D] -> [D][nB8]
-  if (rc != LECCR_OK) return rc;
+  const bool mn = bwd_mn_major();  // text and caption rows are read as MN-major operands: no transposed copies
+  if (!mn) {
+    rc = leccr_transpose16(txt16, B, D, ld_txt, TT, b8, stream_);   // [B][D]  -> [D][B8]
+    if (rc != LECCR_OK) return rc;
+    rc = leccr_transpose16(cap16, nb, D, ld_cap, CT, nb8, stream_); // [nB][D] -> [D][nB8]
+    if (rc != LECCR_OK) return rc;
+  }
   // d caption = G' text * s ;  d text = G'^T caption * s   (s = grad_out / (2 B temp), fp32, in the epilogue)
-  StoreProblem p0 = {G, TT, b8, b8, nb, D, dcap, D, nullptr};
+  StoreProblem p0 = {G, mn ? txt16 : TT, b8, mn ? ld_txt : b8, nb, D, dcap, D, nullptr, mn};
   rc = launch_store(&p0, 1, b, fmt, 1.0f, scale, nullptr, 1, stream);
   if (rc != LECCR_OK) return rc;
-  StoreProblem p1 = {GT, CT, nb8, nb8, B, D, dtxt, D, nullptr};
+  StoreProblem p1 = {GT, mn ? cap16 : CT, nb8, mn ? ld_cap : nb8, B, D, dtxt, D, nullptr, mn};
   rc = launch_store(&p1, 1, static_cast<int>(nb), fmt, 1.0f, scale, nullptr, 1, stream, grad_out, out + 1, dtemp);
   return rc;
 }
@@ -1950,7 +2005,8 @@ int leccr_dstl_bwd(const float* Fm, const float* TV, const float* lse, const voi
     dstl_grad_kernel<1><<<n, 256, 0, stream>>>(Fm, TV, n, (int)n8, lse, lse + N, (int)row_begin, (int)row_count, grad_out,
                                               Gr, GcT, scale);
   LAUNCH_CHECK("dstl_grad_kernel");
-  {
+  const bool mn = bwd_mn_major();  // image and text rows are read as MN-major operands: no transposed copies
+  if (!mn) {
     dim3 grid(static_cast<unsigned>((n8 + 31) / 32), static_cast<unsigned>((D + 31) / 32), 2);
     dim3 block(32, 8);
     if (ld_img != ld_tt) return LECCR_ERR_ARG;
@@ -1960,8 +2016,8 @@ int leccr_dstl_bwd(const float* Fm, const float* TV, const float* lse, const voi
   }
   // d text_t[loc] = Gr image * s ;  d image[loc] = GcT text_t * s    (s = grad_out / N^2)
   StoreProblem sp[2] = {
-      {Gr, imgT, n8, n8, row_count, D, dtt, D, parts0},
-      {GcT, ttT, n8, n8, row_count, D, dimg, D, parts1},
+      {Gr, mn ? img16 : imgT, n8, mn ? ld_img : n8, row_count, D, dtt, D, parts0, mn},
+      {GcT, mn ? tt16 : ttT, n8, mn ? ld_tt : n8, row_count, D, dimg, D, parts1, mn},
   };
   return launch_store(sp, 2, n, fmt, 1.0f, scale, nullptr, splits, stream);
 }

@@ -109,11 +109,15 @@ __device__ __forceinline__ void decode_item(const SimLaunch& L, int item, int& p
 // chunk kc (a_empty / a_full barriers per chunk), so items follow each other without draining the pipeline.
 constexpr int kAResChunks = 4;
 
-template <class Epi, int kStages, int kBK = BK, bool kARes = false>
+// kBMN: the column operand is MN-major -- its tensor map describes the row-major [K][n_cols] source (the contraction
+// index is the slow axis) and a stage holds BN / 64 boxes of {64 columns, kBK K-rows} (ptx.cuh make_sw128_mnmajor_desc).
+template <class Epi, int kStages, int kBK = BK, bool kARes = false, bool kBMN = false>
 __global__ void __launch_bounds__(gemm_threads(Epi::kWGs), 1)
 sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typename Epi::Params EP) {
   extern __shared__ uint8_t smem_raw[];
   using SG = StageGeom<kBK>;
+  static_assert(!kBMN || (kBK == 64 && !kARes), "MN-major column operand: 128-byte swizzle, streamed stages");
+  constexpr uint32_t kMnBoxBytes = 64 * kBK * 2;  // one {64 columns, kBK rows} box
   constexpr int kAStageBytes = SG::kA;
   constexpr int kStageBytes = kARes ? SG::kB : SG::kBytes;   // resident A: the stages hold B only
   constexpr int kAResBytes = kARes ? kAResChunks * SG::kA : 0;
@@ -190,7 +194,13 @@ sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typ
             uint8_t* sb = kARes ? sa : sa + kAStageBytes;
             mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
             if (!kARes) tma_load_2d(sa, tmr, &full_bar[stage], kc * kBK, rb * BM);
-            tma_load_2d(sb, tmc, &full_bar[stage], kc * kBK, ct * BN);
+            if (kBMN) {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(sb + j * kMnBoxBytes, tmc, &full_bar[stage], ct * BN + j * 64, kc * kBK);
+            } else {
+              tma_load_2d(sb, tmc, &full_bar[stage], kc * kBK, ct * BN);
+            }
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1u;
@@ -202,7 +212,7 @@ sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typ
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one_sync()) {
-      const uint32_t idesc = make_idesc_f16(L.fmt, BM, BN);
+      const uint32_t idesc = make_idesc_f16(L.fmt, BM, BN, kBMN);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t tile_n = 0;
@@ -222,11 +232,14 @@ sim_gemm_kernel(const __grid_constant__ SimLaunch L, const __grid_constant__ typ
             tc_fence_after();
             const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
             const uint64_t adesc = make_kmajor_desc<kBK>(kARes ? smem_u32(a_res + kc * kAStageBytes) : sa);
-            const uint64_t bdesc = make_kmajor_desc<kBK>(kARes ? sa : sa + kAStageBytes);
+            const uint64_t bdesc = kBMN ? make_sw128_mnmajor_desc(sa + kAStageBytes, kMnBoxBytes)
+                                        : make_kmajor_desc<kBK>(kARes ? sa : sa + kAStageBytes);
+            // K-major: +32 bytes per K step inside the swizzle atom == +2 in the (addr >> 4) field;
+            // MN-major: 16 K-rows of 128 bytes == +128
+            constexpr uint32_t kBStep = kBMN ? 128u : 2u;
 #pragma unroll
             for (int k = 0; k < kBK / UMMA_K; ++k) {
-              // +32 bytes per K step inside the swizzle atom == +2 in the (addr >> 4) field
-              umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kc > kc0 || k > 0) ? 1u : 0u);
+              umma_f16(d_tmem, adesc + 2u * k, bdesc + kBStep * k, idesc, (kc > kc0 || k > 0) ? 1u : 0u);
             }
             umma_commit(&empty_bar[stage]);  // stage reusable once these MMAs have read it
             if (kARes && ct == ct1 - 1) umma_commit(&aempty_bar[kc]);  // the item's last use of row chunk kc

@@ -176,6 +176,20 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand (the contraction index is the SLOW axis of the row-major source, e.g. the gathered [n][D]
+// matrix in  dA = G' * B): TMA lands {64 elements of MN (128 bytes), kBK rows of K} boxes with the 128-byte swizzle;
+// a box is kBK / 8 atoms of 8 K-rows x 128 B (1024 bytes apart = the stride byte offset), the boxes of a tile follow
+// each other along MN `mn_block_bytes` apart (the leading byte offset).  A K step of 16 is 16 rows = +2048 bytes.
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t mn_block_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(mn_block_bytes >> 4) << 16;  // leading byte offset: next 64-element block along MN
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;            // stride byte offset: next group of 8 K-rows
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;                    // SWIZZLE_128B
+  return d;
+}
+
 // The same for rows of kRowBytes = 2 * kBK bytes: 128 (SWIZZLE_128B, 1024-byte atoms) or 64 (SWIZZLE_64B,
 // layout type 4, 8-row x 64 B atoms 512 B apart).  A K step of 16 elements is +32 bytes inside the row either way.
 template <int kBK>
@@ -190,12 +204,13 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor for kind::f16, fp32 accumulate, both operands K-major.
+// Instruction descriptor for kind::f16, fp32 accumulate, A K-major, B K-major or (b_mn) MN-major.
 // fmt: 0 = fp16, 1 = bf16.
-__host__ __device__ constexpr uint32_t make_idesc_f16(int fmt, int m, int n) {
+__host__ __device__ constexpr uint32_t make_idesc_f16(int fmt, int m, int n, bool b_mn = false) {
   return (1u << 4)                          // D format: f32
          | (static_cast<uint32_t>(fmt) << 7)   // A format
          | (static_cast<uint32_t>(fmt) << 10)  // B format
+         | (b_mn ? (1u << 16) : 0u)            // B major: 0 = K, 1 = MN
          | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 

@@ -258,18 +258,20 @@ def infonce_forward(a: Operand, b: Operand, idx: Optional[torch.Tensor], temp: t
     return out, lse2, rcnt
 
 
-def infonce_backward(a: Operand, b: Operand, aT: torch.Tensor, bT: torch.Tensor, idx: Optional[torch.Tensor],
-                     temp: torch.Tensor, lse2: torch.Tensor, rcnt: torch.Tensor, row_begin: int, row_count: int,
-                     grad_out: torch.Tensor):
-    """Gradients w.r.t. the local rows [row_begin, row_begin + row_count) of the gathered operands."""
+def infonce_backward(a: Operand, b: Operand, aT: Optional[torch.Tensor], bT: Optional[torch.Tensor],
+                     idx: Optional[torch.Tensor], temp: torch.Tensor, lse2: torch.Tensor, rcnt: torch.Tensor,
+                     row_begin: int, row_count: int, grad_out: torch.Tensor):
+    """Gradients w.r.t. the local rows [row_begin, row_begin + row_count) of the gathered operands.
+    aT / bT (transposed copies, `transpose16`) are only read with LECCR_BWD_MN=0; pass None otherwise: the
+    gradient products read the gathered rows as MN-major tensor-core operands."""
     lib = N.load()
     dev = a.t16.device
     dA = torch.empty((row_count, a.D), dtype=torch.float32, device=dev)
     dB = torch.empty((row_count, a.D), dtype=torch.float32, device=dev)
     ws_bytes = lib.leccr_infonce_bwd_workspace(a.n, row_count, a.D)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    N.check(lib.leccr_infonce_bwd(N.ptr(a.t16), N.ptr(b.t16), a.t16.stride(0), N.ptr(aT), N.ptr(bT), aT.stride(0),
-                                  N.ptr(idx), a.n, a.D, a.fmt, N.ptr(temp), N.ptr(lse2), N.ptr(rcnt), row_begin,
+    N.check(lib.leccr_infonce_bwd(N.ptr(a.t16), N.ptr(b.t16), a.t16.stride(0), N.ptr(aT), N.ptr(bT),
+                                  aT.stride(0) if aT is not None else 0, N.ptr(idx), a.n, a.D, a.fmt, N.ptr(temp), N.ptr(lse2), N.ptr(rcnt), row_begin,
                                   row_count, N.ptr(grad_out), N.ptr(dA), N.ptr(dB), N.ptr(ws), ws_bytes,
                                   N.stream_ptr()), "leccr_infonce_bwd")
     return dA, dB
