@@ -5,6 +5,7 @@ Tolerances (north_star): Recall@K exactly equal; loss within 1e-3 relative; simi
 16-bit tolerance (fp16 operands: |err| <= sum of row rounding-residual bounds, ~5e-4 on unit vectors;
 split-precision "x3" products: 2e-6); top-k indices identical except at ties inside that tolerance.
 """
+import os
 import types
 
 import numpy as np
@@ -1020,3 +1021,26 @@ def test_property_contrastive_random_batches(b, d8, labels, temp):
             assert err <= tg * ref.norm() + 1e-4, (err.item(), ref.norm().item())
         if tt is not None:
             assert abs(me.temp.grad.item() - rt.item()) <= tt * abs(rt.item()) + 1e-4, (me.temp.grad.item(), rt.item())
+
+
+def test_backward_as_first_cuda_work_of_its_thread_in_a_fresh_process():
+    """Regression: torch runs the backward on its autograd thread.  When the tensor-core launch is the first CUDA
+    work of that thread, the driver-side tensor-map encoding found no current context (CUresult 201) unless the
+    library binds the primary context itself.  A fresh process makes the order deterministic."""
+    import subprocess
+    import sys
+
+    code = (
+        "import types, torch, leccr_b200\n"
+        "g = torch.Generator().manual_seed(0)\n"
+        "a = torch.nn.functional.normalize(torch.randn(96, 256, generator=g), dim=-1).cuda().requires_grad_(True)\n"
+        "b = torch.nn.functional.normalize(torch.randn(96, 256, generator=g), dim=-1).cuda().requires_grad_(True)\n"
+        "me = types.SimpleNamespace(embed_dim=256, temp=torch.nn.Parameter(torch.tensor(0.07, device='cuda')))\n"
+        "loss = leccr_b200.get_contrastive_loss(me, a, b, torch.arange(96, device='cuda'))\n"
+        "loss.backward()\n"
+        "torch.cuda.synchronize()\n"
+        "assert torch.isfinite(a.grad).all() and a.grad.abs().sum() > 0\n"
+        "print('ok', float(loss))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, (r.stdout[-500:], r.stderr[-1500:])
