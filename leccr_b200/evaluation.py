@@ -337,25 +337,27 @@ def _fused_eval_double_sim_materialized(image_embeds, text_embeds, caption_embed
     return ev, {'i2t': ops.topk_dense(F_, k), 't2i': ops.topk_dense(F_, k, by_columns=True)}
 
 
-_gt_inverse_ok = {}
-
-
 def _single_gt_per_text(gt, n_img, n_txt):
     """txt_gt [n_txt] int32 when every text has exactly one ground-truth video AND the video CSR is the inverse
-    map (what the reference's datasets build, dataset/retrieval_dataset_video.py:201-219); else None."""
+    map (what the reference's datasets build, dataset/retrieval_dataset_video.py:201-219); else None.
+    The verdict costs two host syncs, so it is remembered ON the ground-truth tensors themselves (an attribute of
+    v_off naming the three other tensors by weak reference): a cache keyed by device addresses would answer for a
+    different ground truth once the allocator hands the addresses out again."""
+    import weakref
+
     (v_off, v_ids), (t_off, t_ids) = gt
-    key = (v_off.data_ptr(), v_ids.data_ptr(), t_off.data_ptr(), t_ids.data_ptr(), n_img, n_txt)
-    ok = _gt_inverse_ok.get(key)
-    if ok is None:
-        ok = False
-        if t_ids.numel() == n_txt and v_ids.numel() == n_txt and t_off.numel() == n_txt + 1:
-            counts = (v_off[1:] - v_off[:-1]).long()
-            owner = torch.repeat_interleave(torch.arange(n_img, device=v_off.device), counts)
-            ok = bool(torch.equal(t_off.long(), torch.arange(n_txt + 1, device=t_off.device))) and \
-                bool(torch.equal(t_ids.long()[v_ids.long()], owner))
-        if len(_gt_inverse_ok) > 64:
-            _gt_inverse_ok.clear()
-        _gt_inverse_ok[key] = ok
+    memo = getattr(v_off, "_leccr_inverse", None)
+    if memo is not None:
+        r_ids, r_toff, r_tids, m_img, m_txt, ok = memo
+        if r_ids() is v_ids and r_toff() is t_off and r_tids() is t_ids and (m_img, m_txt) == (n_img, n_txt):
+            return t_ids if ok else None
+    ok = False
+    if t_ids.numel() == n_txt and v_ids.numel() == n_txt and t_off.numel() == n_txt + 1 and v_off.numel() == n_img + 1:
+        counts = (v_off[1:] - v_off[:-1]).long()
+        owner = torch.repeat_interleave(torch.arange(n_img, device=v_off.device), counts)
+        ok = bool(torch.equal(t_off.long(), torch.arange(n_txt + 1, device=t_off.device))) and \
+            bool(torch.equal(t_ids.long()[v_ids.long()], owner))
+    v_off._leccr_inverse = (weakref.ref(v_ids), weakref.ref(t_off), weakref.ref(t_ids), n_img, n_txt, ok)
     return t_ids if ok else None
 
 

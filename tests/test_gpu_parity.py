@@ -1044,3 +1044,25 @@ def test_backward_as_first_cuda_work_of_its_thread_in_a_fresh_process():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, (r.stdout[-500:], r.stderr[-1500:])
+
+
+def test_double_sim_contract_check_is_not_fooled_by_recycled_device_addresses():
+    """Regression: whether the ground truth fits the epilogue path (one video per text, inverse maps) used to be
+    remembered under the DEVICE ADDRESSES of the CSR tensors; once the allocator handed the same addresses to another
+    ground truth the stale verdict sent a two-video text down the epilogue path.  Same shapes, tensors freed in
+    between: the second ground truth must take the materialised path and still equal the oracle."""
+    rs = synth.retrieval_set(120, 1, d=64, seed=5, n_caption_queries=1)
+    want_i2t, want_t2i = oracle.double_sim_matrices(rs.image, rs.text, rs.caption, alpha=0.8, fusion="raw")
+    want_t2i = np.ascontiguousarray(want_t2i)
+    for trial in range(6):   # fresh CSR tensors of identical sizes every round: addresses get reused
+        ev, topk = leccr_b200.fused_eval(rs.image, rs.text, rs.txt2img, rs.img2txt, k=10, caption_embeds=rs.caption,
+                                         alpha=0.8, fusion="raw")
+        assert "rank_i2t" in topk
+        del topk
+        i2 = {i: list(v) for i, v in rs.img2txt.items()}
+        i2[1] = i2[1] + [i2[0][0]]          # text 0 now has two ground-truth videos
+        ev_f, topk_f = leccr_b200.fused_eval(rs.image, rs.text, rs.txt2img, i2, k=10, caption_embeds=rs.caption,
+                                             alpha=0.8, fusion="raw")
+        assert "rank_i2t" not in topk_f, f"round {trial}: stale contract verdict"
+        assert_ev_equal(ev_f, oracle.itm_eval_by_count(want_i2t, want_t2i, rs.txt2img, i2))
+        del topk_f
