@@ -366,3 +366,29 @@ def test_property_gallery_layout_and_merge_random():
     slots()
     shards()
     merge()
+
+
+def test_build_staleness_follows_source_contents(tmp_path, monkeypatch):
+    """The library is rebuilt when the CONTENT of any source differs from what it was compiled from (mtimes do not
+    survive the snapshot copy to the GPU box), and only then."""
+    from leccr_b200 import build as B
+
+    srcs = []
+    for i in range(3):
+        p = tmp_path / f"s{i}.cu"
+        p.write_text(f"// source {i}\n")
+        srcs.append(str(p))
+    lib = tmp_path / "lib.so"
+    monkeypatch.setattr(B, "DEPS", srcs)
+    monkeypatch.setattr(B, "LIB", str(lib))
+    monkeypatch.setattr(B, "HASH", str(lib) + ".srchash")
+    assert B.is_stale()                                   # nothing built yet
+    lib.write_bytes(b"\x7fELF")
+    assert B.is_stale()                                   # a library without a recorded hash is not trusted
+    (tmp_path / "lib.so.srchash").write_text(B.source_hash() + "\n")
+    assert not B.is_stale()
+    os.utime(srcs[1], (1, 1))                             # touching a file changes nothing
+    assert not B.is_stale()
+    with open(srcs[2], "a") as f:
+        f.write("// edited\n")
+    assert B.is_stale()
