@@ -392,3 +392,18 @@ def test_build_staleness_follows_source_contents(tmp_path, monkeypatch):
     with open(srcs[2], "a") as f:
         f.write("// edited\n")
     assert B.is_stale()
+
+
+def test_numa_binding_context_leaves_the_affinity_as_it_found_it():
+    """Without NVML / a GPU the context manager must be a no-op (bound False) and the thread's CPU affinity must be
+    what it was, also when the body raises."""
+    from leccr_b200.peer import host_memory_near_device
+
+    before = os.sched_getaffinity(0)
+    with host_memory_near_device(0) as near:
+        assert near.bound in (False, True)
+    assert os.sched_getaffinity(0) == before
+    with pytest.raises(RuntimeError):
+        with host_memory_near_device(3):
+            raise RuntimeError("body failed")
+    assert os.sched_getaffinity(0) == before
